@@ -1,0 +1,154 @@
+/*
+ * nagp.h — C ABI of the B200-native GP hot path behind NowcastAutoGP's public API.
+ *
+ * The reference (CDCgov/NowcastAutoGP, pure Julia) has no FFI of its own: its boundary to the
+ * arithmetic is 13 plain Julia calls into AutoGP.jl. Each entry point below replaces the
+ * arithmetic of one (or a fused run) of those call sites; the reference file:line is cited per
+ * function. INTEGRATION.md shows the `ccall` stubs a maintainer adds on the Julia side.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; all sizes int64_t, reals double, status int32_t.
+ *  - Every data pointer may be a HOST pointer (pageable or pinned) or a DEVICE pointer on the
+ *    context's GPU; the library detects which (cudaPointerGetAttributes). Host inputs are copied
+ *    in, host outputs are copied back and the call blocks until they have landed. If every output
+ *    is a device pointer the call is asynchronous on the context's stream.
+ *  - The caller owns every buffer it passes. The library owns device memory behind nagp_ctx /
+ *    nagp_factor handles, released by nagp_destroy / nagp_factor_free.
+ *  - Return: 0 ok; >0 LAPACK-style "leading minor i not positive definite" for at least one
+ *    instance (per-instance codes in info[], the shim maps it to Julia's PosDefException —
+ *    behaviour pinned by /root/reference/test/test_model_fitting.jl:97-110); <0 bad argument or
+ *    CUDA failure, message via nagp_last_error(). No exception crosses the boundary.
+ *  - A context is not re-entrant: one call at a time per nagp_ctx (use one ctx per host thread).
+ *  - Kernel trees travel as post-order byte programs + theta (docs/KERNEL_SPEC.md §1), packed
+ *    CSR-style: instance p's program is prog[prog_off[p] .. prog_off[p+1]).
+ *  - Times: t[q] rescaled time points; g (nullable) int32 grid indices with `step` selects the
+ *    lag-grid contract of KERNEL_SPEC §2 (Δ_ij = |g_i − g_j|·step).
+ *  - Point order of a forecast problem: [n training | k nowcast | h forecast], m = n+k, q = m+h.
+ */
+#ifndef NAGP_H
+#define NAGP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NAGP_OK 0
+#define NAGP_E_ARG (-1)      /* bad argument                                  */
+#define NAGP_E_CUDA (-2)     /* CUDA runtime failure                          */
+#define NAGP_E_PROGRAM (-3)  /* malformed kernel program / stack or length cap */
+#define NAGP_E_SIZE (-4)     /* problem does not fit the implemented paths     */
+
+typedef struct nagp_ctx nagp_ctx;
+typedef struct nagp_factor nagp_factor;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int32_t nagp_version(void);
+/* Create a context on CUDA device `device`. */
+int32_t nagp_init(int32_t device, nagp_ctx **out);
+void nagp_destroy(nagp_ctx *ctx);
+/* Last error text of this context (or of nagp_init when ctx == NULL). Never NULL. */
+const char *nagp_last_error(const nagp_ctx *ctx);
+/* Run subsequent calls on `cuda_stream` (a cudaStream_t; NULL = the context's own stream). */
+int32_t nagp_set_stream(nagp_ctx *ctx, void *cuda_stream);
+/* Diagonal jitter added to every Gram (AutoGP: 1e-5, KERNEL_SPEC §4). */
+int32_t nagp_set_jitter(nagp_ctx *ctx, double jitter);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+int64_t nagp_launch_count(const nagp_ctx *ctx);
+/* Pick the factorisation kernel: 0 = auto, 1 = shared-memory column kernel, 2 = tile kernel. */
+int32_t nagp_set_variant(nagp_ctx *ctx, int32_t variant);
+
+/* ---- (a2) batched log marginal likelihood ---------------------------------------------------
+ * Replaces the per-particle Gram -> dpotrf -> logdet/quad-form that AutoGP.fit_smc! /
+ * mcmc_structure! evaluate (/root/reference/src/make_and_fit_model.jl:84-91,
+ * /root/reference/src/forecasting.jl:146). B instances over the same n points; y is shared
+ * (y_stride == 0) or per instance (y + b*y_stride). logml[B], info[B]. */
+int32_t nagp_logml_batch(nagp_ctx *ctx, int64_t B,
+                         const uint8_t *prog, const int64_t *prog_off,
+                         const double *theta, const int64_t *theta_off, const double *noise,
+                         int64_t n, const double *t, const int32_t *g, double step,
+                         const double *y, int64_t y_stride,
+                         double *logml, int32_t *info);
+
+/* ---- general per-(scenario, particle) path ---------------------------------------------------
+ * One fused Gram -> Cholesky -> solves per instance for K scenarios x P particles: replaces
+ * GPModel(dict) + add_data! + predict_mvn + MvNormal's Cholesky for each of them
+ * (/root/reference/src/forecasting.jl:133,135,46). Hyperparameters may differ per scenario
+ * (theta_stride_k = total theta length, noise_stride_k = P; as after per-scenario HMC,
+ * forecasting.jl:145-149) or be shared (strides 0). y1[n] and y2[K*k] are in AutoGP's scaled
+ * space, (ya, yb) the scale map y_s = ya*y + yb used to un-scale predictions; noise_pred < 0
+ * means "use each instance's own noise on the forecast block".
+ * Outputs: logw[K*P] = logw0[p] + logML(m) - logML(n); mu[K*P*h]; L[K*P*h*h] (row-major lower
+ * Cholesky factor of the predictive covariance, original units); info[K*P]. */
+int32_t nagp_forecast_instances(nagp_ctx *ctx, int64_t K, int64_t P,
+                                const uint8_t *prog, const int64_t *prog_off,
+                                const double *theta, const int64_t *theta_off, int64_t theta_stride_k,
+                                const double *noise, int64_t noise_stride_k, double noise_pred,
+                                int64_t n, int64_t k, int64_t h,
+                                const double *t, const int32_t *g, double step,
+                                const double *y1, const double *y2, double ya, double yb,
+                                const double *logw0,
+                                double *logw, double *mu, double *L, int32_t *info);
+
+/* ---- (a3) factor store: Dict(model) / GPModel(dict) -------------------------------------------
+ * Factor the P particles of a base model ONCE over [train | nowcast dates | forecast dates] and
+ * keep the factors on the device (/root/reference/src/forecasting.jl:128,133 rebuild them K times).
+ * logml_n[P] (nullable) receives each particle's training log marginal likelihood. */
+int32_t nagp_factor_store(nagp_ctx *ctx, int64_t P,
+                          const uint8_t *prog, const int64_t *prog_off,
+                          const double *theta, const int64_t *theta_off,
+                          const double *noise, double noise_pred,
+                          int64_t n, int64_t k, int64_t h,
+                          const double *t, const int32_t *g, double step,
+                          const double *y1, double ya, double yb, const double *logw0,
+                          nagp_factor **out, double *logml_n, int32_t *info);
+void nagp_factor_free(nagp_factor *f);
+
+/* ---- (a4) add_data! for K scenarios against a stored factor -----------------------------------
+ * /root/reference/src/forecasting.jl:135. y2[K*k] scaled. logw[K*P] = logw0 + Δ logML;
+ * mu[K*P*h] (nullable) = per-scenario predictive means in original units. */
+int32_t nagp_append(nagp_ctx *ctx, const nagp_factor *f, int64_t K, const double *y2,
+                    double *logw, double *mu);
+
+/* ---- (a7) predict_mvn for the stored particles (no nowcast values: k must be 0) ---------------
+ * /root/reference/src/forecasting.jl:46. mu[P*h], L[P*h*h] original units. With k > 0 use
+ * nagp_append for the means; L is scenario-independent and is returned here in either case. */
+int32_t nagp_predict(nagp_ctx *ctx, const nagp_factor *f, double *mu, double *L);
+
+/* ---- (a5) maybe_resample!'s test: ESS per scenario --------------------------------------------
+ * /root/reference/src/forecasting.jl:138-141. logw[K*P] -> ess[K], w[K*P] (nullable). */
+int32_t nagp_ess(nagp_ctx *ctx, int64_t K, int64_t P, const double *logw, double *ess, double *w);
+
+/* ---- (a8) rand(MixtureModel, D) ----------------------------------------------------------------
+ * /root/reference/src/forecasting.jl:47. Per scenario s and draw d: component c = comp[s*D+d] if
+ * comp != NULL and the entry is >= 0, else by inverse CDF of the normalised weights at u[s*D+d]
+ * (after multinomial resampling with u_res[K*P] iff u_res != NULL and ESS < ess_thr*P);
+ * x = mu_c + L_c * zeta in the fixed order of KERNEL_SPEC §7. mu/L are [K,P,h]/[K,P,h,h] with
+ * scenario strides mu_stride_k / l_stride_k in doubles (0 = shared by all scenarios).
+ * x[h, K*D] column-major (scenario-major column blocks); ess_out[K], comp_out[K*D] nullable. */
+int32_t nagp_draw(nagp_ctx *ctx, int64_t K, int64_t P, int64_t h, int64_t D,
+                  const double *logw, const double *mu, int64_t mu_stride_k,
+                  const double *L, int64_t l_stride_k,
+                  const int32_t *comp, const double *u, const double *u_res, double ess_thr,
+                  const double *zeta, double *x, double *ess_out, int32_t *comp_out);
+
+/* ---- fused forecast_with_nowcasts (n_mcmc = n_hmc = 0, forecast_n_hmc = nothing) ---------------
+ * /root/reference/src/forecasting.jl:117-167 in one call: factor once per particle, append the K
+ * scenarios, ESS/resample, draw. x[h, K*D] column-major; logw_out[K*P], ess_out[K] nullable. */
+int32_t nagp_forecast_with_nowcasts(nagp_ctx *ctx, int64_t K, int64_t P, int64_t D,
+                                    const uint8_t *prog, const int64_t *prog_off,
+                                    const double *theta, const int64_t *theta_off,
+                                    const double *noise, double noise_pred,
+                                    int64_t n, int64_t k, int64_t h,
+                                    const double *t, const int32_t *g, double step,
+                                    const double *y1, const double *y2, double ya, double yb,
+                                    const double *logw0,
+                                    const int32_t *comp, const double *u, const double *u_res,
+                                    double ess_thr, const double *zeta,
+                                    double *x, double *logw_out, double *ess_out, int32_t *info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NAGP_H */

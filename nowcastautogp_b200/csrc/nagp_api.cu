@@ -1,0 +1,626 @@
+// nagp_api.cu — the C ABI declared in include/nagp.h: context, host/device buffer staging and
+// the entry points that replace NowcastAutoGP's calls into AutoGP (file:line per function in the
+// header). No torch types, no exceptions across the boundary.
+#include "../../include/nagp.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "nagp_kernels.cuh"
+#include "nagp_tree.cuh"
+
+using namespace nagp;
+
+namespace {
+
+struct PendingOut { void *host; const void *dev; size_t bytes; };
+struct Chunk { char *base; size_t cap; };
+
+std::string g_init_error;
+
+}  // namespace
+
+struct nagp_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    double jitter = 1e-5;
+    int variant = 0;
+    int64_t launches = 0;
+    int smem_optin = 0;
+    std::string err;
+    std::vector<Chunk> chunks;
+    size_t chunk_off = 0;          // bump offset in chunks.back()
+    std::vector<PendingOut> outs;
+};
+
+struct nagp_factor {
+    int device;
+    int64_t P;
+    int n, k, h;
+    double ya, yb;
+    double *proj = nullptr, *Ltail = nullptr, *L33 = nullptr, *logw0 = nullptr, *logml_n = nullptr;
+};
+
+namespace {
+
+int32_t fail(nagp_ctx *ctx, int32_t code, const std::string &msg)
+{
+    if (ctx) ctx->err = msg; else g_init_error = msg;
+    return code;
+}
+
+#define NAGP_CUDA(ctx, expr)                                                                   \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return fail(ctx, NAGP_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+bool on_device(const void *p)
+{
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// ---- grow-only device arena: bump allocation per call, consolidated at the start of the next ----
+int32_t arena_reset(nagp_ctx *ctx)
+{
+    ctx->outs.clear();
+    if (ctx->chunks.size() > 1) {
+        NAGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        size_t total = 0;
+        for (auto &c : ctx->chunks) { total += c.cap; cudaFree(c.base); }
+        ctx->chunks.clear();
+        char *base = nullptr;
+        NAGP_CUDA(ctx, cudaMalloc(&base, total));
+        ctx->chunks.push_back({base, total});
+    }
+    ctx->chunk_off = 0;
+    return NAGP_OK;
+}
+
+void *arena_alloc(nagp_ctx *ctx, size_t bytes)
+{
+    bytes = (bytes + 255) & ~size_t(255);
+    if (bytes == 0) bytes = 256;
+    if (ctx->chunks.empty() || ctx->chunk_off + bytes > ctx->chunks.back().cap) {
+        size_t cap = std::max<size_t>(bytes, ctx->chunks.empty() ? (size_t(8) << 20) : 2 * ctx->chunks.back().cap);
+        char *base = nullptr;
+        if (cudaMalloc(&base, cap) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        ctx->chunks.push_back({base, cap});
+        ctx->chunk_off = 0;
+    }
+    void *p = ctx->chunks.back().base + ctx->chunk_off;
+    ctx->chunk_off += bytes;
+    return p;
+}
+
+template <class T>
+int32_t stage_in(nagp_ctx *ctx, const T *p, size_t count, const T **dev)
+{
+    if (!p || count == 0) { *dev = nullptr; return NAGP_OK; }
+    if (on_device(p)) { *dev = p; return NAGP_OK; }
+    T *d = static_cast<T *>(arena_alloc(ctx, count * sizeof(T)));
+    if (!d) return fail(ctx, NAGP_E_CUDA, "device workspace allocation failed");
+    NAGP_CUDA(ctx, cudaMemcpyAsync(d, p, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    *dev = d;
+    return NAGP_OK;
+}
+
+template <class T>
+int32_t stage_out(nagp_ctx *ctx, T *p, size_t count, T **dev)
+{
+    if (!p || count == 0) { *dev = nullptr; return NAGP_OK; }
+    if (on_device(p)) { *dev = p; return NAGP_OK; }
+    T *d = static_cast<T *>(arena_alloc(ctx, count * sizeof(T)));
+    if (!d) return fail(ctx, NAGP_E_CUDA, "device workspace allocation failed");
+    ctx->outs.push_back({p, d, count * sizeof(T)});
+    *dev = d;
+    return NAGP_OK;
+}
+
+template <class T>
+int32_t scratch(nagp_ctx *ctx, size_t count, T **dev)
+{
+    *dev = static_cast<T *>(arena_alloc(ctx, count * sizeof(T)));
+    if (!*dev) return fail(ctx, NAGP_E_CUDA, "device workspace allocation failed");
+    return NAGP_OK;
+}
+
+// Copy host outputs back; blocks iff there are any.
+int32_t finish(nagp_ctx *ctx)
+{
+    for (auto &o : ctx->outs)
+        NAGP_CUDA(ctx, cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!ctx->outs.empty()) NAGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->outs.clear();
+    return NAGP_OK;
+}
+
+#define NAGP_TRY(expr)                 \
+    do {                               \
+        int32_t rc__ = (expr);         \
+        if (rc__ != NAGP_OK) return rc__; \
+    } while (0)
+
+// Worst positive info over a host-visible info array (after finish()).
+int32_t worst_info(const int32_t *info, int64_t count)
+{
+    int32_t neg = 0, pos = 0;
+    for (int64_t i = 0; i < count; ++i) {
+        if (info[i] < 0) neg = info[i];
+        else if (info[i] > 0 && pos == 0) pos = info[i];
+    }
+    return neg ? neg : pos;
+}
+
+struct GridInfo { int G; };
+
+// Lag-table extent. g may live on either side; q is small, so a device-resident g costs one tiny
+// synchronous copy.
+int32_t grid_extent(nagp_ctx *ctx, const int32_t *g, int64_t q, int *G)
+{
+    *G = 0;
+    if (!g) return NAGP_OK;
+    std::vector<int32_t> host(q);
+    if (on_device(g)) {
+        NAGP_CUDA(ctx, cudaMemcpyAsync(host.data(), g, q * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        NAGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    } else {
+        std::memcpy(host.data(), g, q * sizeof(int32_t));
+    }
+    auto mm = std::minmax_element(host.begin(), host.end());
+    int64_t ext = (int64_t)*mm.second - (int64_t)*mm.first + 1;
+    if (ext > (1 << 20)) return fail(ctx, NAGP_E_ARG, "lag grid extent too large");
+    *G = (int)ext;
+    return NAGP_OK;
+}
+
+// Table capacities: exact maxima when the programs are host-visible, defaults otherwise; shrunk
+// until the launch fits the opt-in shared-memory limit. A smaller capacity only means more
+// sub-trees are evaluated directly per entry — never a different result.
+int32_t plan_tables(nagp_ctx *ctx, int64_t P, const uint8_t *prog, const int64_t *prog_off,
+                    const int64_t *theta_off, int q, int G, int *ntab_cap, int *ncp_cap)
+{
+    int ntab = G > 0 ? 4 : 0, ncp = 4;
+    if (prog && !on_device(prog) && !on_device(prog_off) && !on_device(theta_off)) {
+        ntab = 0; ncp = 0;
+        TreeProgram tp;
+        for (int64_t p = 0; p < P; ++p) {
+            int64_t len = prog_off[p + 1] - prog_off[p];
+            int64_t nth = theta_off[p + 1] - theta_off[p];
+            if (len <= 0 || len > MAX_PROG || nth > MAX_THETA)
+                return fail(ctx, NAGP_E_PROGRAM, "kernel program length outside 1..64");
+            tree_compile(tp, prog + prog_off[p], (int)len, (int)nth, G > 0 ? MAX_TABLES : 0, MAX_CPTAB);
+            if (tp.error) return fail(ctx, NAGP_E_PROGRAM, "malformed kernel program");
+            ntab = std::max(ntab, tp.ntab);
+            ncp = std::max(ncp, tp.ncp);
+        }
+    }
+    while (fused_smem_bytes_v1(q, G, ntab, ncp) > (size_t)ctx->smem_optin && (ntab > 0 || ncp > 0)) {
+        if (ntab * (size_t)std::max(G, 1) >= ncp * (size_t)q && ntab > 0) --ntab;
+        else if (ncp > 0) --ncp;
+        else --ntab;
+    }
+    if (fused_smem_bytes_v1(q, G, ntab, ncp) > (size_t)ctx->smem_optin)
+        return fail(ctx, NAGP_E_SIZE, "problem too large for the shared-memory resident path (n+k+h <= 234)");
+    *ntab_cap = ntab; *ncp_cap = ncp;
+    return NAGP_OK;
+}
+
+int32_t check_dims(nagp_ctx *ctx, int64_t n, int64_t k, int64_t h)
+{
+    if (n < 0 || k < 0 || h < 0 || n + k + h <= 0) return fail(ctx, NAGP_E_ARG, "bad n/k/h");
+    if (n + k + h > 234) return fail(ctx, NAGP_E_SIZE, "n+k+h > 234 not supported by the resident path");
+    return NAGP_OK;
+}
+
+int32_t run_fused(nagp_ctx *ctx, const FusedArgs &a)
+{
+    NAGP_CUDA(ctx, launch_fused_v1(a, ctx->stream));
+    ctx->launches += 1;
+    return NAGP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t nagp_version(void) { return 100; }
+
+int32_t nagp_init(int32_t device, nagp_ctx **out)
+{
+    if (!out) return fail(nullptr, NAGP_E_ARG, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, NAGP_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(nullptr, NAGP_E_ARG, "device index out of range");
+    nagp_ctx *ctx = new (std::nothrow) nagp_ctx();
+    if (!ctx) return fail(nullptr, NAGP_E_ARG, "out of host memory");
+    ctx->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device)) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, NAGP_E_CUDA, std::string("context setup: ") + cudaGetErrorString(e));
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return NAGP_OK;
+}
+
+void nagp_destroy(nagp_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &c : ctx->chunks) cudaFree(c.base);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char *nagp_last_error(const nagp_ctx *ctx) { return ctx ? ctx->err.c_str() : g_init_error.c_str(); }
+
+int32_t nagp_set_stream(nagp_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return NAGP_E_ARG;
+    NAGP_CUDA(ctx, cudaSetDevice(ctx->device));
+    NAGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return NAGP_OK;
+}
+
+int32_t nagp_set_jitter(nagp_ctx *ctx, double jitter)
+{
+    if (!ctx || !(jitter >= 0.0)) return NAGP_E_ARG;
+    ctx->jitter = jitter;
+    return NAGP_OK;
+}
+
+int64_t nagp_launch_count(const nagp_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t nagp_set_variant(nagp_ctx *ctx, int32_t variant)
+{
+    if (!ctx || variant < 0 || variant > 2) return NAGP_E_ARG;
+    ctx->variant = variant;
+    return NAGP_OK;
+}
+
+int32_t nagp_logml_batch(nagp_ctx *ctx, int64_t B, const uint8_t *prog, const int64_t *prog_off,
+                         const double *theta, const int64_t *theta_off, const double *noise,
+                         int64_t n, const double *t, const int32_t *g, double step,
+                         const double *y, int64_t y_stride, double *logml, int32_t *info)
+{
+    if (!ctx) return NAGP_E_ARG;
+    if (B <= 0 || !prog || !prog_off || !theta || !theta_off || !noise || !t || !y || !logml || !info)
+        return fail(ctx, NAGP_E_ARG, "nagp_logml_batch: null or empty argument");
+    NAGP_TRY(check_dims(ctx, n, 0, 0));
+    NAGP_CUDA(ctx, cudaSetDevice(ctx->device));
+    NAGP_TRY(arena_reset(ctx));
+    FusedArgs a{};
+    NAGP_TRY(grid_extent(ctx, g, n, &a.G));
+    NAGP_TRY(plan_tables(ctx, B, prog, prog_off, theta_off, (int)n, a.G, &a.ntab_cap, &a.ncp_cap));
+    int64_t nprog, ntheta;
+    if (on_device(prog_off) || on_device(theta_off))
+        return fail(ctx, NAGP_E_ARG, "prog_off/theta_off must be host arrays");
+    nprog = prog_off[B]; ntheta = theta_off[B];
+    a.B = B; a.P = B;
+    NAGP_TRY(stage_in(ctx, prog, (size_t)nprog, &a.prog));
+    NAGP_TRY(stage_in(ctx, prog_off, (size_t)B + 1, &a.prog_off));
+    NAGP_TRY(stage_in(ctx, theta, (size_t)ntheta, &a.theta));
+    NAGP_TRY(stage_in(ctx, theta_off, (size_t)B + 1, &a.theta_off));
+    NAGP_TRY(stage_in(ctx, noise, (size_t)B, &a.noise));
+    a.jitter = ctx->jitter; a.noise_pred = -1.0;
+    a.n = (int)n; a.k = 0; a.h = 0;
+    NAGP_TRY(stage_in(ctx, t, (size_t)n, &a.t));
+    NAGP_TRY(stage_in(ctx, g, (size_t)n, &a.g));
+    a.step = step;
+    NAGP_TRY(stage_in(ctx, y, (size_t)(y_stride ? (B - 1) * y_stride + n : n), &a.y1));
+    a.y1_stride = y_stride;
+    a.ya = 1.0; a.yb = 0.0;
+    NAGP_TRY(stage_out(ctx, logml, (size_t)B, &a.logml_n));
+    NAGP_TRY(stage_out(ctx, info, (size_t)B, &a.info));
+    const bool host_info = !ctx->outs.empty() && !on_device(info);
+    NAGP_TRY(run_fused(ctx, a));
+    NAGP_TRY(finish(ctx));
+    return host_info ? worst_info(info, B) : NAGP_OK;
+}
+
+int32_t nagp_forecast_instances(nagp_ctx *ctx, int64_t K, int64_t P, const uint8_t *prog,
+                                const int64_t *prog_off, const double *theta, const int64_t *theta_off,
+                                int64_t theta_stride_k, const double *noise, int64_t noise_stride_k,
+                                double noise_pred, int64_t n, int64_t k, int64_t h, const double *t,
+                                const int32_t *g, double step, const double *y1, const double *y2,
+                                double ya, double yb, const double *logw0, double *logw, double *mu,
+                                double *L, int32_t *info)
+{
+    if (!ctx) return NAGP_E_ARG;
+    if (K <= 0 || P <= 0 || !prog || !prog_off || !theta || !theta_off || !noise || !t || !y1 || !info ||
+        (k > 0 && !y2) || ya == 0.0)
+        return fail(ctx, NAGP_E_ARG, "nagp_forecast_instances: null or empty argument");
+    NAGP_TRY(check_dims(ctx, n, k, h));
+    if (on_device(prog_off) || on_device(theta_off))
+        return fail(ctx, NAGP_E_ARG, "prog_off/theta_off must be host arrays");
+    NAGP_CUDA(ctx, cudaSetDevice(ctx->device));
+    NAGP_TRY(arena_reset(ctx));
+    const int64_t q = n + k + h, B = K * P;
+    FusedArgs a{};
+    NAGP_TRY(grid_extent(ctx, g, q, &a.G));
+    NAGP_TRY(plan_tables(ctx, P, prog, prog_off, theta_off, (int)q, a.G, &a.ntab_cap, &a.ncp_cap));
+    const int64_t nprog = prog_off[P], ntheta = theta_off[P];
+    a.B = B; a.P = P;
+    NAGP_TRY(stage_in(ctx, prog, (size_t)nprog, &a.prog));
+    NAGP_TRY(stage_in(ctx, prog_off, (size_t)P + 1, &a.prog_off));
+    NAGP_TRY(stage_in(ctx, theta, (size_t)(theta_stride_k ? (K - 1) * theta_stride_k + ntheta : ntheta), &a.theta));
+    NAGP_TRY(stage_in(ctx, theta_off, (size_t)P + 1, &a.theta_off));
+    a.theta_stride_k = theta_stride_k;
+    NAGP_TRY(stage_in(ctx, noise, (size_t)(noise_stride_k ? (K - 1) * noise_stride_k + P : P), &a.noise));
+    a.noise_stride_k = noise_stride_k;
+    a.jitter = ctx->jitter; a.noise_pred = noise_pred;
+    a.n = (int)n; a.k = (int)k; a.h = (int)h;
+    NAGP_TRY(stage_in(ctx, t, (size_t)q, &a.t));
+    NAGP_TRY(stage_in(ctx, g, (size_t)q, &a.g));
+    a.step = step;
+    NAGP_TRY(stage_in(ctx, y1, (size_t)n, &a.y1));
+    NAGP_TRY(stage_in(ctx, y2, (size_t)(K * k), &a.y2));
+    a.ya = ya; a.yb = yb;
+    NAGP_TRY(stage_in(ctx, logw0, (size_t)P, &a.logw0));
+    NAGP_TRY(stage_out(ctx, logw, (size_t)B, &a.logw));
+    NAGP_TRY(stage_out(ctx, mu, (size_t)(B * h), &a.mu));
+    NAGP_TRY(stage_out(ctx, L, (size_t)(B * h * h), &a.L33));
+    NAGP_TRY(stage_out(ctx, info, (size_t)B, &a.info));
+    const bool host_info = !on_device(info);
+    NAGP_TRY(run_fused(ctx, a));
+    NAGP_TRY(finish(ctx));
+    return host_info ? worst_info(info, B) : NAGP_OK;
+}
+
+int32_t nagp_factor_store(nagp_ctx *ctx, int64_t P, const uint8_t *prog, const int64_t *prog_off,
+                          const double *theta, const int64_t *theta_off, const double *noise,
+                          double noise_pred, int64_t n, int64_t k, int64_t h, const double *t,
+                          const int32_t *g, double step, const double *y1, double ya, double yb,
+                          const double *logw0, nagp_factor **out, double *logml_n, int32_t *info)
+{
+    if (!ctx) return NAGP_E_ARG;
+    if (!out || P <= 0 || !prog || !prog_off || !theta || !theta_off || !noise || !t || !y1 || !info || ya == 0.0)
+        return fail(ctx, NAGP_E_ARG, "nagp_factor_store: null or empty argument");
+    *out = nullptr;
+    NAGP_TRY(check_dims(ctx, n, k, h));
+    if (on_device(prog_off) || on_device(theta_off))
+        return fail(ctx, NAGP_E_ARG, "prog_off/theta_off must be host arrays");
+    NAGP_CUDA(ctx, cudaSetDevice(ctx->device));
+    NAGP_TRY(arena_reset(ctx));
+    const int64_t q = n + k + h, kh = k + h;
+    nagp_factor *f = new (std::nothrow) nagp_factor();
+    if (!f) return fail(ctx, NAGP_E_ARG, "out of host memory");
+    f->device = ctx->device; f->P = P; f->n = (int)n; f->k = (int)k; f->h = (int)h; f->ya = ya; f->yb = yb;
+    auto dalloc = [&](double **p, size_t cnt) { return cudaMalloc(p, std::max<size_t>(cnt, 1) * sizeof(double)); };
+    if (dalloc(&f->proj, P * kh) != cudaSuccess || dalloc(&f->Ltail, P * kh * kh) != cudaSuccess ||
+        dalloc(&f->L33, P * h * h) != cudaSuccess || dalloc(&f->logw0, P) != cudaSuccess ||
+        dalloc(&f->logml_n, P) != cudaSuccess) {
+        nagp_factor_free(f);
+        return fail(ctx, NAGP_E_CUDA, "factor allocation failed");
+    }
+    FusedArgs a{};
+    int32_t rc;
+    auto bail = [&](int32_t code) { nagp_factor_free(f); return code; };
+    if ((rc = grid_extent(ctx, g, q, &a.G)) != NAGP_OK) return bail(rc);
+    if ((rc = plan_tables(ctx, P, prog, prog_off, theta_off, (int)q, a.G, &a.ntab_cap, &a.ncp_cap)) != NAGP_OK) return bail(rc);
+    a.B = P; a.P = P;
+    if ((rc = stage_in(ctx, prog, (size_t)prog_off[P], &a.prog)) != NAGP_OK) return bail(rc);
+    if ((rc = stage_in(ctx, prog_off, (size_t)P + 1, &a.prog_off)) != NAGP_OK) return bail(rc);
+    if ((rc = stage_in(ctx, theta, (size_t)theta_off[P], &a.theta)) != NAGP_OK) return bail(rc);
+    if ((rc = stage_in(ctx, theta_off, (size_t)P + 1, &a.theta_off)) != NAGP_OK) return bail(rc);
+    if ((rc = stage_in(ctx, noise, (size_t)P, &a.noise)) != NAGP_OK) return bail(rc);
+    a.jitter = ctx->jitter; a.noise_pred = noise_pred;
+    a.n = (int)n; a.k = (int)k; a.h = (int)h;
+    if ((rc = stage_in(ctx, t, (size_t)q, &a.t)) != NAGP_OK) return bail(rc);
+    if ((rc = stage_in(ctx, g, (size_t)q, &a.g)) != NAGP_OK) return bail(rc);
+    a.step = step;
+    if ((rc = stage_in(ctx, y1, (size_t)n, &a.y1)) != NAGP_OK) return bail(rc);
+    a.y2 = nullptr; a.ya = ya; a.yb = yb;
+    a.logml_n = f->logml_n; a.proj = f->proj; a.Ltail = f->Ltail; a.L33 = f->L33;
+    if ((rc = stage_out(ctx, info, (size_t)P, &a.info)) != NAGP_OK) return bail(rc);
+    if (logw0) {
+        cudaError_t e = cudaMemcpyAsync(f->logw0, logw0, P * sizeof(double), cudaMemcpyDefault, ctx->stream);
+        if (e != cudaSuccess) return bail(fail(ctx, NAGP_E_CUDA, cudaGetErrorString(e)));
+    } else {
+        cudaMemsetAsync(f->logw0, 0, P * sizeof(double), ctx->stream);
+    }
+    if ((rc = run_fused(ctx, a)) != NAGP_OK) return bail(rc);
+    if (logml_n) {
+        cudaError_t e = cudaMemcpyAsync(logml_n, f->logml_n, P * sizeof(double), cudaMemcpyDefault, ctx->stream);
+        if (e != cudaSuccess) return bail(fail(ctx, NAGP_E_CUDA, cudaGetErrorString(e)));
+    }
+    if ((rc = finish(ctx)) != NAGP_OK) return bail(rc);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return bail(fail(ctx, NAGP_E_CUDA, cudaGetErrorString(e)));
+    *out = f;
+    return on_device(info) ? NAGP_OK : worst_info(info, P);
+}
+
+void nagp_factor_free(nagp_factor *f)
+{
+    if (!f) return;
+    cudaSetDevice(f->device);
+    cudaFree(f->proj); cudaFree(f->Ltail); cudaFree(f->L33); cudaFree(f->logw0); cudaFree(f->logml_n);
+    delete f;
+}
+
+int32_t nagp_append(nagp_ctx *ctx, const nagp_factor *f, int64_t K, const double *y2, double *logw, double *mu)
+{
+    if (!ctx) return NAGP_E_ARG;
+    if (!f || K <= 0 || !logw || (f->k > 0 && !y2)) return fail(ctx, NAGP_E_ARG, "nagp_append: null or empty argument");
+    if (f->device != ctx->device) return fail(ctx, NAGP_E_ARG, "factor lives on another device");
+    NAGP_CUDA(ctx, cudaSetDevice(ctx->device));
+    NAGP_TRY(arena_reset(ctx));
+    AppendArgs a{};
+    a.K = K; a.P = f->P; a.k = f->k; a.h = f->h;
+    NAGP_TRY(stage_in(ctx, y2, (size_t)(K * f->k), &a.y2));
+    a.proj = f->proj; a.Ltail = f->Ltail; a.logw0 = f->logw0; a.ya = f->ya; a.yb = f->yb;
+    NAGP_TRY(stage_out(ctx, logw, (size_t)(K * f->P), &a.logw));
+    NAGP_TRY(stage_out(ctx, mu, (size_t)(K * f->P * f->h), &a.mu));
+    NAGP_CUDA(ctx, launch_append(a, ctx->stream));
+    ctx->launches += 1;
+    return finish(ctx);
+}
+
+int32_t nagp_predict(nagp_ctx *ctx, const nagp_factor *f, double *mu, double *L)
+{
+    if (!ctx) return NAGP_E_ARG;
+    if (!f) return fail(ctx, NAGP_E_ARG, "nagp_predict: null factor");
+    if (f->device != ctx->device) return fail(ctx, NAGP_E_ARG, "factor lives on another device");
+    if (mu && f->k != 0) return fail(ctx, NAGP_E_ARG, "nagp_predict: means need k == 0 (use nagp_append)");
+    NAGP_CUDA(ctx, cudaSetDevice(ctx->device));
+    NAGP_TRY(arena_reset(ctx));
+    if (mu) {
+        // k == 0: the append kernel with zero nowcast points is exactly the un-scaling of proj
+        AppendArgs a{};
+        a.K = 1; a.P = f->P; a.k = 0; a.h = f->h;
+        a.y2 = nullptr; a.proj = f->proj; a.Ltail = f->Ltail; a.logw0 = nullptr; a.ya = f->ya; a.yb = f->yb;
+        double *lw;
+        NAGP_TRY(scratch(ctx, (size_t)f->P, &lw));
+        a.logw = lw;
+        NAGP_TRY(stage_out(ctx, mu, (size_t)(f->P * f->h), &a.mu));
+        NAGP_CUDA(ctx, launch_append(a, ctx->stream));
+        ctx->launches += 1;
+    }
+    if (L)
+        NAGP_CUDA(ctx, cudaMemcpyAsync(L, f->L33, (size_t)(f->P * f->h * f->h) * sizeof(double),
+                                       cudaMemcpyDefault, ctx->stream));
+    NAGP_TRY(finish(ctx));
+    if (L && !on_device(L)) NAGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NAGP_OK;
+}
+
+int32_t nagp_ess(nagp_ctx *ctx, int64_t K, int64_t P, const double *logw, double *ess, double *w)
+{
+    if (!ctx) return NAGP_E_ARG;
+    if (K <= 0 || P <= 0 || !logw || !ess) return fail(ctx, NAGP_E_ARG, "nagp_ess: null or empty argument");
+    NAGP_CUDA(ctx, cudaSetDevice(ctx->device));
+    NAGP_TRY(arena_reset(ctx));
+    DrawArgs a{};
+    a.K = K; a.P = P; a.h = 0; a.D = 0;
+    NAGP_TRY(stage_in(ctx, logw, (size_t)(K * P), &a.logw));
+    NAGP_TRY(stage_out(ctx, ess, (size_t)K, &a.ess_out));
+    NAGP_TRY(stage_out(ctx, w, (size_t)(K * P), &a.w_out));
+    NAGP_CUDA(ctx, launch_draw(a, ctx->stream));
+    ctx->launches += 1;
+    return finish(ctx);
+}
+
+int32_t nagp_draw(nagp_ctx *ctx, int64_t K, int64_t P, int64_t h, int64_t D, const double *logw,
+                  const double *mu, int64_t mu_stride_k, const double *L, int64_t l_stride_k,
+                  const int32_t *comp, const double *u, const double *u_res, double ess_thr,
+                  const double *zeta, double *x, double *ess_out, int32_t *comp_out)
+{
+    if (!ctx) return NAGP_E_ARG;
+    if (K <= 0 || P <= 0 || h <= 0 || D <= 0 || !logw || !mu || !L || !zeta || !x || (!comp && !u))
+        return fail(ctx, NAGP_E_ARG, "nagp_draw: null or empty argument");
+    if (u_res && !u) return fail(ctx, NAGP_E_ARG, "nagp_draw: resampling needs u");
+    NAGP_CUDA(ctx, cudaSetDevice(ctx->device));
+    NAGP_TRY(arena_reset(ctx));
+    DrawArgs a{};
+    a.K = K; a.P = P; a.h = (int)h; a.D = D;
+    NAGP_TRY(stage_in(ctx, logw, (size_t)(K * P), &a.logw));
+    NAGP_TRY(stage_in(ctx, mu, (size_t)((K - 1) * mu_stride_k + P * h), &a.mu));
+    a.mu_stride_k = mu_stride_k;
+    NAGP_TRY(stage_in(ctx, L, (size_t)((K - 1) * l_stride_k + P * h * h), &a.L));
+    a.l_stride_k = l_stride_k;
+    NAGP_TRY(stage_in(ctx, comp, (size_t)(K * D), &a.comp));
+    NAGP_TRY(stage_in(ctx, u, (size_t)(K * D), &a.u));
+    NAGP_TRY(stage_in(ctx, u_res, (size_t)(K * P), &a.u_res));
+    a.ess_thr = ess_thr;
+    NAGP_TRY(stage_in(ctx, zeta, (size_t)(K * D * h), &a.zeta));
+    NAGP_TRY(stage_out(ctx, x, (size_t)(K * D * h), &a.x));
+    NAGP_TRY(stage_out(ctx, ess_out, (size_t)K, &a.ess_out));
+    NAGP_TRY(stage_out(ctx, comp_out, (size_t)(K * D), &a.comp_out));
+    NAGP_CUDA(ctx, launch_draw(a, ctx->stream));
+    ctx->launches += 1;
+    return finish(ctx);
+}
+
+int32_t nagp_forecast_with_nowcasts(nagp_ctx *ctx, int64_t K, int64_t P, int64_t D, const uint8_t *prog,
+                                    const int64_t *prog_off, const double *theta, const int64_t *theta_off,
+                                    const double *noise, double noise_pred, int64_t n, int64_t k, int64_t h,
+                                    const double *t, const int32_t *g, double step, const double *y1,
+                                    const double *y2, double ya, double yb, const double *logw0,
+                                    const int32_t *comp, const double *u, const double *u_res,
+                                    double ess_thr, const double *zeta, double *x, double *logw_out,
+                                    double *ess_out, int32_t *info)
+{
+    if (!ctx) return NAGP_E_ARG;
+    if (K <= 0 || P <= 0 || D <= 0 || h <= 0 || !prog || !prog_off || !theta || !theta_off || !noise || !t ||
+        !y1 || (k > 0 && !y2) || !zeta || !x || !info || (!comp && !u) || ya == 0.0)
+        return fail(ctx, NAGP_E_ARG, "nagp_forecast_with_nowcasts: null or empty argument");
+    if (u_res && !u) return fail(ctx, NAGP_E_ARG, "nagp_forecast_with_nowcasts: resampling needs u");
+    NAGP_TRY(check_dims(ctx, n, k, h));
+    if (on_device(prog_off) || on_device(theta_off))
+        return fail(ctx, NAGP_E_ARG, "prog_off/theta_off must be host arrays");
+    NAGP_CUDA(ctx, cudaSetDevice(ctx->device));
+    NAGP_TRY(arena_reset(ctx));
+    const int64_t q = n + k + h, kh = k + h;
+
+    // (1) one factorisation per particle over [train | nowcast | forecast]
+    FusedArgs a{};
+    NAGP_TRY(grid_extent(ctx, g, q, &a.G));
+    NAGP_TRY(plan_tables(ctx, P, prog, prog_off, theta_off, (int)q, a.G, &a.ntab_cap, &a.ncp_cap));
+    a.B = P; a.P = P;
+    NAGP_TRY(stage_in(ctx, prog, (size_t)prog_off[P], &a.prog));
+    NAGP_TRY(stage_in(ctx, prog_off, (size_t)P + 1, &a.prog_off));
+    NAGP_TRY(stage_in(ctx, theta, (size_t)theta_off[P], &a.theta));
+    NAGP_TRY(stage_in(ctx, theta_off, (size_t)P + 1, &a.theta_off));
+    NAGP_TRY(stage_in(ctx, noise, (size_t)P, &a.noise));
+    a.jitter = ctx->jitter; a.noise_pred = noise_pred;
+    a.n = (int)n; a.k = (int)k; a.h = (int)h;
+    NAGP_TRY(stage_in(ctx, t, (size_t)q, &a.t));
+    NAGP_TRY(stage_in(ctx, g, (size_t)q, &a.g));
+    a.step = step;
+    NAGP_TRY(stage_in(ctx, y1, (size_t)n, &a.y1));
+    a.y2 = nullptr; a.ya = ya; a.yb = yb;
+    NAGP_TRY(scratch(ctx, (size_t)P, &a.logml_n));
+    NAGP_TRY(scratch(ctx, (size_t)(P * kh), &a.proj));
+    NAGP_TRY(scratch(ctx, (size_t)(P * kh * kh), &a.Ltail));
+    NAGP_TRY(scratch(ctx, (size_t)(P * h * h), &a.L33));
+    NAGP_TRY(stage_out(ctx, info, (size_t)P, &a.info));
+    NAGP_TRY(run_fused(ctx, a));
+
+    // (2) add_data! for every scenario: O(k^2 + hk) per (scenario, particle)
+    AppendArgs ap{};
+    ap.K = K; ap.P = P; ap.k = (int)k; ap.h = (int)h;
+    NAGP_TRY(stage_in(ctx, y2, (size_t)(K * k), &ap.y2));
+    ap.proj = a.proj; ap.Ltail = a.Ltail;
+    NAGP_TRY(stage_in(ctx, logw0, (size_t)P, &ap.logw0));
+    ap.ya = ya; ap.yb = yb;
+    if (logw_out) NAGP_TRY(stage_out(ctx, logw_out, (size_t)(K * P), &ap.logw));
+    else NAGP_TRY(scratch(ctx, (size_t)(K * P), &ap.logw));
+    NAGP_TRY(scratch(ctx, (size_t)(K * P * h), &ap.mu));
+    NAGP_CUDA(ctx, launch_append(ap, ctx->stream));
+    ctx->launches += 1;
+
+    // (3) maybe_resample! + rand(MixtureModel, D)
+    DrawArgs d{};
+    d.K = K; d.P = P; d.h = (int)h; d.D = D;
+    d.logw = ap.logw; d.mu = ap.mu; d.mu_stride_k = P * h; d.L = a.L33; d.l_stride_k = 0;
+    NAGP_TRY(stage_in(ctx, comp, (size_t)(K * D), &d.comp));
+    NAGP_TRY(stage_in(ctx, u, (size_t)(K * D), &d.u));
+    NAGP_TRY(stage_in(ctx, u_res, (size_t)(K * P), &d.u_res));
+    d.ess_thr = ess_thr;
+    NAGP_TRY(stage_in(ctx, zeta, (size_t)(K * D * h), &d.zeta));
+    NAGP_TRY(stage_out(ctx, x, (size_t)(K * D * h), &d.x));
+    NAGP_TRY(stage_out(ctx, ess_out, (size_t)K, &d.ess_out));
+    NAGP_CUDA(ctx, launch_draw(d, ctx->stream));
+    ctx->launches += 1;
+    NAGP_TRY(finish(ctx));
+    return on_device(info) ? NAGP_OK : worst_info(info, P);
+}
+
+}  // extern "C"

@@ -1,0 +1,81 @@
+// nagp_kernels.cuh — launch interfaces shared by the C-ABI layer and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nagp {
+
+// One fused Gram -> Cholesky -> solve problem per instance b in [0, B). Instance b belongs to
+// scenario s = b / P and particle p = b % P (P = B for plain logML batches).
+struct FusedArgs {
+    int64_t B;
+    int64_t P;
+    const uint8_t *prog;
+    const int64_t *prog_off;     // [P+1]
+    const double *theta;
+    const int64_t *theta_off;    // [P+1]
+    int64_t theta_stride_k;      // doubles between scenarios (0 = shared)
+    const double *noise;         // [P] or [K,P]
+    int64_t noise_stride_k;
+    double jitter;
+    double noise_pred;           // < 0: instance noise on forecast block
+    int n, k, h;                 // q = n + k + h
+    const double *t;             // [q]
+    const int32_t *g;            // [q] or null
+    double step;
+    int G;                       // max lag + 1 (lag-grid mode), else 0
+    const double *y1;            // [n] (+ b * y1_stride)
+    int64_t y1_stride;           // per-instance stride of y1 (0 = shared)
+    const double *y2;            // [K,k] or null: scenario values, indexed by s
+    double ya, yb;
+    // outputs (all nullable except info)
+    double *logml_n;             // [B]
+    double *logml_m;             // [B] (needs y2 or k == 0)
+    const double *logw0;         // [P] nullable
+    double *logw;                // [B] = logw0[p] + logml_m - logml_n
+    double *mu;                  // [B,h] original units (needs y for all m rows)
+    double *L33;                 // [B,h,h] row-major lower / ya
+    double *proj;                // [B,k+h]: sum_{j<n} L[n+r][j] z1[j]   (scenario-shared fast path)
+    double *Ltail;               // [B,k+h,k+h]: L[n+r][n+c] (scaled space, zeros above diagonal)
+    int32_t *info;               // [B]
+    int ntab_cap, ncp_cap;       // shared-memory table slots per CTA
+};
+
+size_t fused_smem_bytes_v1(int q, int G, int ntab_cap, int ncp_cap);
+cudaError_t launch_fused_v1(const FusedArgs &a, cudaStream_t stream);
+
+// Scenario-shared fast path: per (scenario, particle) O(k^2 + hk) tail of the forward solve.
+struct AppendArgs {
+    int64_t K, P;
+    int k, h;
+    const double *y2;      // [K,k] scaled
+    const double *proj;    // [P,k+h]
+    const double *Ltail;   // [P,k+h,k+h]
+    const double *logw0;   // [P] nullable
+    const double *logml_n; // unused (kept for symmetry)
+    double ya, yb;
+    double *logw;          // [K,P]
+    double *mu;            // [K,P,h] nullable
+};
+cudaError_t launch_append(const AppendArgs &a, cudaStream_t stream);
+
+struct DrawArgs {
+    int64_t K, P;
+    int h;
+    int64_t D;
+    const double *logw;    // [K,P]
+    const double *mu; int64_t mu_stride_k;
+    const double *L; int64_t l_stride_k;
+    const int32_t *comp;   // [K,D] nullable
+    const double *u;       // [K,D] nullable
+    const double *u_res;   // [K,P] nullable
+    double ess_thr;
+    const double *zeta;    // [K,D,h]
+    double *x;             // [h, K*D] column-major (nullable when D == 0)
+    double *ess_out;       // [K] nullable
+    double *w_out;         // [K,P] nullable
+    int32_t *comp_out;     // [K,D] nullable
+};
+cudaError_t launch_draw(const DrawArgs &a, cudaStream_t stream);
+
+}  // namespace nagp
