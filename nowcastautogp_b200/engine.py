@@ -174,20 +174,24 @@ class Engine:
         self._check(self._lib.nagp_ess(self._ctx, K, P, logw.ctypes.data, ess.ctypes.data, w.ctypes.data))
         return ess, w
 
-    def draw(self, logw, mu, L, zeta, comp=None, u=None, u_res=None, ess_thr=0.0, x=None):
-        """mu [K,P,h] or [P,h] (shared); L [K,P,h,h] or [P,h,h]; zeta [K,D,h] → x [h, K·D]."""
+    def draw(self, logw, mu, L, zeta, comp=None, u=None, u_res=None, ess_thr=0.0, x=None, ess=None,
+             comp_out=None, want_aux: bool = True):
+        """mu [K,P,h] or [P,h] (shared); L [K,P,h,h] or [P,h,h]; zeta [K,D,h] → x [h, K·D].
+        With `want_aux=False` and device `x` the call stays asynchronous on the stream."""
         K, P = logw.shape
         D, h = zeta.shape[1], zeta.shape[2]
         mu_stride = P * h if len(mu.shape) == 3 else 0
         l_stride = P * h * h if len(L.shape) == 4 else 0
         xbuf = np.empty((K * D, h)) if x is None else x
-        ess = np.empty(K)
-        comp_out = np.empty((K, D), np.int32)
+        if want_aux:
+            ess = np.empty(K) if ess is None else ess
+            comp_out = np.empty((K, D), np.int32) if comp_out is None else comp_out
         keep = [_ptr(logw, np.float64), _ptr(mu, np.float64), _ptr(L, np.float64), _ptr(comp, np.int32),
-                _ptr(u, np.float64), _ptr(u_res, np.float64), _ptr(zeta, np.float64), _ptr(xbuf)]
+                _ptr(u, np.float64), _ptr(u_res, np.float64), _ptr(zeta, np.float64), _ptr(xbuf),
+                _ptr(ess), _ptr(comp_out)]
         p = [k_[0] for k_ in keep]
         self._check(self._lib.nagp_draw(self._ctx, K, P, h, D, p[0], p[1], mu_stride, p[2], l_stride, p[3],
-                                        p[4], p[5], ess_thr, p[6], p[7], ess.ctypes.data, comp_out.ctypes.data))
+                                        p[4], p[5], ess_thr, p[6], p[7], p[8], p[9]))
         return (xbuf.T if x is None else xbuf), ess, comp_out
 
     # ---- fused forecast_with_nowcasts --------------------------------------------------------------
