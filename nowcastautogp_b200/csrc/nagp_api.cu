@@ -30,7 +30,7 @@ struct nagp_ctx {
     double jitter = 1e-5;
     int variant = 0;
     int64_t launches = 0;
-    int smem_optin = 0;
+    int smem_optin = 0, smem_per_sm = 0, num_sms = 0;
     std::string err;
     std::vector<Chunk> chunks;
     size_t chunk_off = 0;          // bump offset in chunks.back()
@@ -203,13 +203,21 @@ int32_t plan_tables(nagp_ctx *ctx, int64_t P, const uint8_t *prog, const int64_t
             ncp = std::max(ncp, tp.ncp);
         }
     }
+    *ntab_cap = ntab; *ncp_cap = ncp;
+    return NAGP_OK;
+}
+
+// The column kernel keeps its tables in shared memory: shrink the capacities until it fits.
+int32_t fit_tables_v1(nagp_ctx *ctx, int q, int G, int *ntab_cap, int *ncp_cap)
+{
+    int ntab = *ntab_cap, ncp = *ncp_cap;
     while (fused_smem_bytes_v1(q, G, ntab, ncp) > (size_t)ctx->smem_optin && (ntab > 0 || ncp > 0)) {
         if (ntab * (size_t)std::max(G, 1) >= ncp * (size_t)q && ntab > 0) --ntab;
         else if (ncp > 0) --ncp;
         else --ntab;
     }
     if (fused_smem_bytes_v1(q, G, ntab, ncp) > (size_t)ctx->smem_optin)
-        return fail(ctx, NAGP_E_SIZE, "problem too large for the shared-memory resident path (n+k+h <= 234)");
+        return fail(ctx, NAGP_E_SIZE, "problem too large for the shared-memory resident path");
     *ntab_cap = ntab; *ncp_cap = ncp;
     return NAGP_OK;
 }
@@ -221,8 +229,27 @@ int32_t check_dims(nagp_ctx *ctx, int64_t n, int64_t k, int64_t h)
     return NAGP_OK;
 }
 
-int32_t run_fused(nagp_ctx *ctx, const FusedArgs &a)
+// Launch the fused Gram+Cholesky+solve kernel: the tile (DMMA) kernel unless variant 1 is forced
+// or the problem does not fit it. `theta_off` (host) gives the per-program theta counts.
+int32_t run_fused(nagp_ctx *ctx, FusedArgs a, const int64_t *theta_off_host)
 {
+    const int q = a.n + a.k + a.h;
+    if (ctx->variant != 1 && q <= fused_v2_max_q()) {
+        int64_t nth = 1;
+        for (int64_t p = 0; p < a.P; ++p) nth = std::max(nth, theta_off_host[p + 1] - theta_off_host[p]);
+        V2Plan pl = plan_fused_v2(q, a.G, (int)std::min<int64_t>(nth, MAX_THETA), a.ntab_cap, a.ncp_cap,
+                                  ctx->smem_optin, ctx->smem_per_sm);
+        if (pl.ok) {
+            int grid = fused_v2_grid(pl, a.B, ctx->num_sms);
+            char *scr = nullptr;
+            if (pl.scratch_stride) NAGP_TRY(scratch(ctx, (size_t)grid * pl.scratch_stride, &scr));
+            NAGP_CUDA(ctx, launch_fused_v2(a, pl, scr, grid, ctx->stream));
+            ctx->launches += 1;
+            return NAGP_OK;
+        }
+    }
+    if (ctx->variant == 2) return fail(ctx, NAGP_E_SIZE, "problem does not fit the tile kernel");
+    NAGP_TRY(fit_tables_v1(ctx, q, a.G, &a.ntab_cap, &a.ncp_cap));
     NAGP_CUDA(ctx, launch_fused_v1(a, ctx->stream));
     ctx->launches += 1;
     return NAGP_OK;
@@ -248,7 +275,9 @@ int32_t nagp_init(int32_t device, nagp_ctx **out)
     ctx->device = device;
     if ((e = cudaSetDevice(device)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device)) != cudaSuccess) {
+        (e = cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device)) != cudaSuccess ||
+        (e = cudaDeviceGetAttribute(&ctx->smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device)) != cudaSuccess ||
+        (e = cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) {
         delete ctx;
         return fail(nullptr, NAGP_E_CUDA, std::string("context setup: ") + cudaGetErrorString(e));
     }
@@ -329,7 +358,7 @@ int32_t nagp_logml_batch(nagp_ctx *ctx, int64_t B, const uint8_t *prog, const in
     NAGP_TRY(stage_out(ctx, logml, (size_t)B, &a.logml_n));
     NAGP_TRY(stage_out(ctx, info, (size_t)B, &a.info));
     const bool host_info = !ctx->outs.empty() && !on_device(info);
-    NAGP_TRY(run_fused(ctx, a));
+    NAGP_TRY(run_fused(ctx, a, theta_off));
     NAGP_TRY(finish(ctx));
     return host_info ? worst_info(info, B) : NAGP_OK;
 }
@@ -378,7 +407,7 @@ int32_t nagp_forecast_instances(nagp_ctx *ctx, int64_t K, int64_t P, const uint8
     NAGP_TRY(stage_out(ctx, L, (size_t)(B * h * h), &a.L33));
     NAGP_TRY(stage_out(ctx, info, (size_t)B, &a.info));
     const bool host_info = !on_device(info);
-    NAGP_TRY(run_fused(ctx, a));
+    NAGP_TRY(run_fused(ctx, a, theta_off));
     NAGP_TRY(finish(ctx));
     return host_info ? worst_info(info, B) : NAGP_OK;
 }
@@ -435,7 +464,7 @@ int32_t nagp_factor_store(nagp_ctx *ctx, int64_t P, const uint8_t *prog, const i
     } else {
         cudaMemsetAsync(f->logw0, 0, P * sizeof(double), ctx->stream);
     }
-    if ((rc = run_fused(ctx, a)) != NAGP_OK) return bail(rc);
+    if ((rc = run_fused(ctx, a, theta_off)) != NAGP_OK) return bail(rc);
     if (logml_n) {
         cudaError_t e = cudaMemcpyAsync(logml_n, f->logml_n, P * sizeof(double), cudaMemcpyDefault, ctx->stream);
         if (e != cudaSuccess) return bail(fail(ctx, NAGP_E_CUDA, cudaGetErrorString(e)));
@@ -591,7 +620,7 @@ int32_t nagp_forecast_with_nowcasts(nagp_ctx *ctx, int64_t K, int64_t P, int64_t
     NAGP_TRY(scratch(ctx, (size_t)(P * kh * kh), &a.Ltail));
     NAGP_TRY(scratch(ctx, (size_t)(P * h * h), &a.L33));
     NAGP_TRY(stage_out(ctx, info, (size_t)P, &a.info));
-    NAGP_TRY(run_fused(ctx, a));
+    NAGP_TRY(run_fused(ctx, a, theta_off));
 
     // (2) add_data! for every scenario: O(k^2 + hk) per (scenario, particle)
     AppendArgs ap{};

@@ -1,0 +1,552 @@
+// nagp_fused_v2.cu — tile kernel (variant 2): fused Gram -> blocked Cholesky -> forward solve ->
+// logML / predictive moments, one persistent CTA stream of (scenario, particle) instances.
+//
+// Layout: the lower triangle of the joint q x q Gram lives in shared memory as 8x8 FP64 tiles
+// (tile-packed, 512 B each). The factorisation is left-looking by tile column: every warp owns the
+// tiles I == warp (mod 8) of the current column, accumulates sum_P L_IP L_JP^T with DMMA
+// (mma.sync m8n8k4 f64, accumulators in registers, operands fetched as one 16-byte LDS per lane
+// from a fragment-major tile layout), the warp owning the diagonal tile factors it in registers
+// with shuffles while building its inverse by the same row operations, and the column's
+// triangular solve is one more DMMA pair against that inverse. The observation vector rides along
+// as a virtual tile row, so z = L^-1 y needs no separate solve.
+//
+// FP64 has no tcgen05/UMMA kind on sm_100a, so DMMA is the tensor path for this workload; measured
+// DMMA peak on this pool's B200: 37.1 TFLOP/s (profiles/r01_fp64_peak.json).
+//
+// Replaces, per instance, AutoGP's Gram + dpotrf + solves behind
+//   /root/reference/src/forecasting.jl:133 (GPModel(dict)), :135 (add_data!), :46 (predict_mvn)
+//   /root/reference/src/make_and_fit_model.jl:91 (fit_smc! likelihood evaluations)
+// Arithmetic contract: docs/KERNEL_SPEC.md §3-§6.
+#include <algorithm>
+
+#include "nagp_kernels.cuh"
+#include "nagp_tree.cuh"
+
+namespace nagp {
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr int kMaxTilesPerWarp = 4;   // ceil((nt + 1) / kWarps), nt <= 29
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
+
+__device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(kFull, v, src); }
+
+__device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// element (r, c) of an operand-layout tile: both k-chunks of a fragment lane are adjacent
+__device__ __forceinline__ int op_idx(int r, int c) { return ((r * 4 + (c & 3)) << 1) + (c >> 2); }
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+// 4-wide interpreter: entries (i, j0..j0+3) of one matrix row. Top of stack in registers, the rest
+// in local memory. Same formulas/order as tree_eval (docs/KERNEL_SPEC.md §3).
+__device__ __forceinline__ void tree_eval4(const TreeProgram &tp, const double *th, double ti, int i,
+                                           const double (&tj)[4], const double (&delta)[4],
+                                           const int (&lag)[4], int j0, const double *tab, int G,
+                                           const double *sig, int Q, double (&out)[4])
+{
+    double st[MAX_STACK][4];
+    double top[4] = {0, 0, 0, 0};
+    int sp = 0;
+    const int len = tp.clen;
+    for (int o = 0; o < len; ++o) {
+        const int op = tp.cop[o];
+        const double *p = th + tp.carg[o];
+        if (op <= OP_PERIODIC || op == OP_TABLE) {
+            if (sp > 0) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) st[sp - 1][e] = top[e];
+            }
+            ++sp;
+            switch (op) {
+            case OP_CONSTANT:
+#pragma unroll
+                for (int e = 0; e < 4; ++e) top[e] = p[0];
+                break;
+            case OP_LINEAR: {
+                const double u = ti - p[0];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) top[e] = fma(p[2], u * (tj[e] - p[0]), p[1]);
+                break;
+            }
+            case OP_SQEXP:
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { double r = delta[e] / p[0]; top[e] = p[1] * exp(-0.5 * (r * r)); }
+                break;
+            case OP_GAMMAEXP:
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { double r = delta[e] / p[0]; top[e] = p[2] * exp(-pow(r, p[1])); }
+                break;
+            case OP_PERIODIC:
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    double s = sin(3.14159265358979323846 * (delta[e] / p[1]));
+                    top[e] = p[2] * exp(-2.0 * (s * s) / (p[0] * p[0]));
+                }
+                break;
+            default: {  // OP_TABLE
+                const double *tb = tab + tp.carg[o] * G;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) top[e] = tb[lag[e]];
+                break;
+            }
+            }
+        } else {
+            --sp;   // left operand is st[sp-1], right operand is top
+            switch (op) {
+            case OP_PLUS:
+#pragma unroll
+                for (int e = 0; e < 4; ++e) top[e] = st[sp - 1][e] + top[e];
+                break;
+            case OP_TIMES:
+#pragma unroll
+                for (int e = 0; e < 4; ++e) top[e] = st[sp - 1][e] * top[e];
+                break;
+            case OP_CHANGEPOINT: {
+                const double si = 0.5 * (1.0 + tanh((ti - p[0]) / p[1]));
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    double sj = 0.5 * (1.0 + tanh((tj[e] - p[0]) / p[1]));
+                    top[e] = ((1.0 - si) * (1.0 - sj)) * st[sp - 1][e] + (si * sj) * top[e];
+                }
+                break;
+            }
+            default: {  // OP_CHANGEPOINT_TAB
+                const double *sg = sig + tp.caux[o] * Q;
+                const double si = sg[i];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    double sj = sg[j0 + e];
+                    top[e] = ((1.0 - si) * (1.0 - sj)) * st[sp - 1][e] + (si * sj) * top[e];
+                }
+                break;
+            }
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) out[e] = top[e];
+}
+
+// In-register Cholesky of an 8x8 tile held in DMMA accumulator layout (lane (r = l>>2, j = l&3)
+// holds columns 2j, 2j+1 of row r), together with its inverse built by the same row operations
+// (L^-1 A = L^T, so the operations that reduce A to L^T turn I into L^-1).
+// Returns 0 or 1 + index of the first non-positive pivot among the first `nreal` rows.
+__device__ __forceinline__ int chol8_inv(double &c0, double &c1, double &w0, double &w1, int lane,
+                                         int nreal, double (&piv)[8])
+{
+    const int r = lane >> 2, j = lane & 3;
+    w0 = (r == 2 * j) ? 1.0 : 0.0;
+    w1 = (r == 2 * j + 1) ? 1.0 : 0.0;
+    int bad = 0;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+        const int pl = p >> 1;
+        const double colv = (p & 1) ? c1 : c0;
+        const double d = shfl(colv, p * 4 + pl);
+        piv[p] = d;
+        if (!(d > 0.0) && p < nreal && bad == 0) bad = p + 1;
+        const double rinv = rsqrt(d);
+        const double lrp = shfl(colv, r * 4 + pl) * rinv;
+        const double lc0 = shfl(colv, (2 * j) * 4 + pl) * rinv;
+        const double lc1 = shfl(colv, (2 * j + 1) * 4 + pl) * rinv;
+        const double wp0 = shfl(w0, p * 4 + j) * rinv;
+        const double wp1 = shfl(w1, p * 4 + j) * rinv;
+        if (r == p) { w0 = wp0; w1 = wp1; }
+        else if (r > p) { w0 = fma(-lrp, wp0, w0); w1 = fma(-lrp, wp1, w1); }
+        if (r > p) {
+            if (2 * j > p) c0 = fma(-lrp, lc0, c0);
+            if (2 * j + 1 > p) c1 = fma(-lrp, lc1, c1);
+        }
+        if (j == pl) {
+            const double fin = r >= p ? lrp : 0.0;
+            if (p & 1) c1 = fin; else c0 = fin;
+        }
+    }
+    return bad;
+}
+
+struct V2Layout {
+    int nt;            // tile rows/cols of the matrix (rows padded to Q = 8 nt)
+    int aux_off[5];    // byte offsets of th, gg, tt, sig, tab inside their home
+    int aux_smem[5];   // 1: shared memory (offset from aux base), 0: per-CTA global scratch
+    int scratch_stride;   // bytes of global scratch per CTA
+    char *scratch;
+};
+
+__global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a, const V2Layout lay)
+{
+    extern __shared__ __align__(16) double smem[];
+    __shared__ TreeProgram tp;
+    __shared__ int s_info;
+    __shared__ double s_red[4][kWarps];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = a.n, k = a.k, h = a.h, m = n + k, q = m + h;
+    const int nt = lay.nt, Q = nt * 8, ntiles = tri(nt);
+    const bool have_y2 = (a.y2 != nullptr) || k == 0;
+    const int ny = have_y2 ? m : n;
+    const int G = a.G;
+
+    double *tiles = smem;
+    double *yv = tiles + ntiles * 64;
+    double *invL = yv + Q;
+    char *aux_s = reinterpret_cast<char *>(invL + 64);
+    char *aux_g = lay.scratch + (size_t)blockIdx.x * lay.scratch_stride;
+    auto aux = [&](int i) { return (lay.aux_smem[i] ? aux_s : aux_g) + lay.aux_off[i]; };
+    double *th = reinterpret_cast<double *>(aux(0));
+    int *gg = reinterpret_cast<int *>(aux(1));
+    double *tt = reinterpret_cast<double *>(aux(2));
+    double *sig = reinterpret_cast<double *>(aux(3));
+    double *tab = reinterpret_cast<double *>(aux(4));
+
+    // times are common to every instance of the launch
+    for (int i = tid; i < Q; i += kThreads) {
+        tt[i] = i < q ? a.t[i] : 0.0;
+        gg[i] = (a.g && i < q) ? a.g[i] : 0;
+    }
+
+    for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x) {
+        const int64_t s = b / a.P;
+        const int p = (int)(b % a.P);
+        const int64_t po = a.prog_off[p], plen = a.prog_off[p + 1] - po;
+        const int64_t to = a.theta_off[p], ntheta = a.theta_off[p + 1] - to;
+        const double *theta_g = a.theta + s * a.theta_stride_k + to;
+
+        __syncthreads();   // previous instance fully consumed
+        if (tid == 0) {
+            s_info = 0;
+            if (ntheta > MAX_THETA) tp.error = -3;
+            else tree_compile(tp, a.prog + po, (int)plen, (int)ntheta, G > 0 ? a.ntab_cap : 0, a.ncp_cap);
+        }
+        for (int i = tid; i < ntheta && i < MAX_THETA; i += kThreads) th[i] = theta_g[i];
+        __syncthreads();
+        if (tp.error) {
+            if (tid == 0) {
+                a.info[b] = tp.error;
+                if (a.logml_n) a.logml_n[b] = nan("");
+                if (a.logml_m) a.logml_m[b] = nan("");
+                if (a.logw) a.logw[b] = nan("");
+            }
+            continue;
+        }
+        const int ntab = tp.ntab, ncp = tp.ncp;
+
+        // ---- lag tables and changepoint sigma tables ------------------------------------------------
+        for (int e = tid; e < ntab * G; e += kThreads) {
+            int id = e / G, lg = e - id * G;
+            int s0 = tp.tab_src0[id], s1 = tp.tab_src1[id];
+            tab[e] = tree_eval(tp.sop + s0, tp.sarg + s0, nullptr, s1 - s0, th, 0.0, 0.0,
+                               (double)lg * a.step, 0, nullptr, 0, nullptr, 0, 0, 0);
+        }
+        for (int e = tid; e < ncp * Q; e += kThreads) {
+            int id = e / Q, i = e - id * Q;
+            const double *cp = th + tp.cp_theta[id];
+            sig[e] = 0.5 * (1.0 + tanh((tt[i] - cp[0]) / cp[1]));
+        }
+        __syncthreads();
+
+        // ---- Gram into row-major tiles: one unit = 4 consecutive columns of one tile row ------------
+        const double nz = a.noise[s * a.noise_stride_k + p];
+        const double d_lo = nz + a.jitter;
+        const double d_hi = (a.noise_pred >= 0.0 ? a.noise_pred : nz) + a.jitter;
+        const bool single_table = (tp.clen == 1 && tp.cop[0] == OP_TABLE);
+        for (int unit = tid; unit < ntiles * 16; unit += kThreads) {
+            const int tix = unit >> 4, r = (unit >> 1) & 7, c4 = (unit & 1) << 2;
+            int I = (int)((sqrtf(8.0f * (float)tix + 1.0f) - 1.0f) * 0.5f);
+            while (tri(I + 1) <= tix) ++I;
+            while (tri(I) > tix) --I;
+            const int J = tix - tri(I);
+            const int i = I * 8 + r, j0 = J * 8 + c4;
+            double out[4];
+            if (i >= q) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) out[e] = (i == j0 + e) ? 1.0 : 0.0;
+            } else {
+                double tj[4], delta[4];
+                int lag[4];
+                const int gi = gg[i];
+                const double ti = tt[i];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    tj[e] = tt[j0 + e];
+                    if (a.g) {
+                        int lg = gi - gg[j0 + e];
+                        lag[e] = lg < 0 ? -lg : lg;
+                        delta[e] = (double)lag[e] * a.step;
+                    } else {
+                        lag[e] = 0;
+                        delta[e] = fabs(ti - tj[e]);
+                    }
+                }
+                if (single_table) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) out[e] = tab[lag[e]];
+                } else {
+                    tree_eval4(tp, th, ti, i, tj, delta, lag, j0, tab, G, sig, Q, out);
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int jj = j0 + e;
+                    if (jj >= q) out[e] = 0.0;
+                    else if (jj == i) out[e] += (i < m) ? d_lo : d_hi;
+                }
+            }
+            double2 *dst = reinterpret_cast<double2 *>(tiles + tix * 64 + r * 8 + c4);
+            dst[0] = make_double2(out[0], out[1]);
+            dst[1] = make_double2(out[2], out[3]);
+        }
+        {
+            const double *y1 = a.y1 + b * a.y1_stride;
+            for (int jx = tid; jx < Q; jx += kThreads) {
+                double v = 0.0;
+                if (jx < n) v = y1[jx];
+                else if (jx < ny) v = a.y2 ? a.y2[s * k + (jx - n)] : y1[jx];
+                yv[jx] = v;
+            }
+        }
+        __syncthreads();
+
+        // ---- left-looking tile-column Cholesky --------------------------------------------------------
+        const int lr = lane >> 2, lj = lane & 3;
+        for (int J = 0; J < nt; ++J) {
+            const int I0 = J + ((warp - J) & (kWarps - 1));   // first tile row >= J owned by this warp
+            double acc[kMaxTilesPerWarp][2];
+#pragma unroll
+            for (int t = 0; t < kMaxTilesPerWarp; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+            const double *rowJ = tiles + tri(J) * 64;
+            for (int P = 0; P < J; ++P) {
+                const double2 bf = *reinterpret_cast<const double2 *>(rowJ + P * 64 + lane * 2);
+#pragma unroll
+                for (int t = 0; t < kMaxTilesPerWarp; ++t) {
+                    const int I = I0 + t * kWarps;
+                    if (I < nt) {
+                        const double2 af = *reinterpret_cast<const double2 *>(tiles + (tri(I) + P) * 64 + lane * 2);
+                        dmma(acc[t][0], acc[t][1], af.x, bf.x);
+                        dmma(acc[t][0], acc[t][1], af.y, bf.y);
+                    } else if (I == nt) {   // observation row: only tile row 0 is populated
+                        const double a0 = lr == 0 ? yv[P * 8 + lj] : 0.0;
+                        const double a1 = lr == 0 ? yv[P * 8 + 4 + lj] : 0.0;
+                        dmma(acc[t][0], acc[t][1], a0, bf.x);
+                        dmma(acc[t][0], acc[t][1], a1, bf.y);
+                    }
+                }
+            }
+            // C = A_IJ - sum
+            double c[kMaxTilesPerWarp][2];
+#pragma unroll
+            for (int t = 0; t < kMaxTilesPerWarp; ++t) {
+                const int I = I0 + t * kWarps;
+                c[t][0] = 0.0; c[t][1] = 0.0;
+                if (I < nt) {
+                    const double2 g2 = *reinterpret_cast<const double2 *>(tiles + (tri(I) + J) * 64 + lane * 2);
+                    c[t][0] = g2.x - acc[t][0];
+                    c[t][1] = g2.y - acc[t][1];
+                } else if (I == nt) {
+                    const double y0 = lr == 0 ? yv[J * 8 + 2 * lj] : 0.0;
+                    const double y1v = lr == 0 ? yv[J * 8 + 2 * lj + 1] : 0.0;
+                    c[t][0] = y0 - acc[t][0];
+                    c[t][1] = y1v - acc[t][1];
+                }
+            }
+            // diagonal tile: factor + invert in registers (the owner's tile t == 0)
+            if (I0 == J) {
+                double w0, w1, piv[8];
+                const int nreal = q - J * 8;
+                const int bad = chol8_inv(c[0][0], c[0][1], w0, w1, lane, nreal, piv);
+                double *dt = tiles + (tri(J) + J) * 64;
+                dt[op_idx(lr, 2 * lj)] = c[0][0];
+                dt[op_idx(lr, 2 * lj + 1)] = c[0][1];
+                invL[op_idx(lr, 2 * lj)] = w0;
+                invL[op_idx(lr, 2 * lj + 1)] = w1;
+                if (bad && lane == 0) s_info = J * 8 + bad;
+            }
+            __syncthreads();
+            if (s_info) break;
+            // triangular solve of the column: X = C * invL^T, stored in operand layout
+            {
+                const double2 ib = *reinterpret_cast<const double2 *>(invL + lane * 2);
+#pragma unroll
+                for (int t = 0; t < kMaxTilesPerWarp; ++t) {
+                    const int I = I0 + t * kWarps;
+                    if (I > J && I <= nt) {
+                        const int src0 = (lane & ~3) + (lj >> 1), src1 = src0 + 2;
+                        const double v00 = shfl(c[t][0], src0), v01 = shfl(c[t][1], src0);
+                        const double v10 = shfl(c[t][0], src1), v11 = shfl(c[t][1], src1);
+                        const double a0 = (lane & 1) ? v01 : v00;
+                        const double a1 = (lane & 1) ? v11 : v10;
+                        double x0 = 0.0, x1 = 0.0;
+                        dmma(x0, x1, a0, ib.x);
+                        dmma(x0, x1, a1, ib.y);
+                        if (I < nt) {
+                            double *dt = tiles + (tri(I) + J) * 64;
+                            dt[op_idx(lr, 2 * lj)] = x0;
+                            dt[op_idx(lr, 2 * lj + 1)] = x1;
+                        } else if (lr == 0) {
+                            yv[J * 8 + 2 * lj] = x0;
+                            yv[J * 8 + 2 * lj + 1] = x1;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+
+        if (s_info) {
+            if (tid == 0) {
+                a.info[b] = s_info;
+                if (a.logml_n) a.logml_n[b] = nan("");
+                if (a.logml_m) a.logml_m[b] = nan("");
+                if (a.logw) a.logw[b] = nan("");
+            }
+            continue;
+        }
+
+        // element (i, j), i >= j, of the factor
+        auto Lel = [&](int i, int j) {
+            return tiles[(tri(i >> 3) + (j >> 3)) * 64 + op_idx(i & 7, j & 7)];
+        };
+
+        // ---- logML(n), logML(m) ----------------------------------------------------------------------
+        const double *z = yv;
+        double ld_n = 0, ld_m = 0, qd_n = 0, qd_m = 0;
+        for (int r = tid; r < m; r += kThreads) {
+            double l = log(Lel(r, r));
+            double zz = r < ny ? z[r] * z[r] : 0.0;
+            ld_m += l; qd_m += zz;
+            if (r < n) { ld_n += l; qd_n += zz; }
+        }
+        ld_n = warp_sum(ld_n); ld_m = warp_sum(ld_m); qd_n = warp_sum(qd_n); qd_m = warp_sum(qd_m);
+        if (lane == 0) { s_red[0][warp] = ld_n; s_red[1][warp] = ld_m; s_red[2][warp] = qd_n; s_red[3][warp] = qd_m; }
+        __syncthreads();
+        if (tid == 0) {
+            double r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+            for (int w = 0; w < kWarps; ++w) { r0 += s_red[0][w]; r1 += s_red[1][w]; r2 += s_red[2][w]; r3 += s_red[3][w]; }
+            const double log2pi = 1.8378770664093454835606594728112;
+            double lmn = -0.5 * ((double)n * log2pi + 2.0 * r0 + r2);
+            double lmm = have_y2 ? -0.5 * ((double)m * log2pi + 2.0 * r1 + r3) : nan("");
+            if (a.logml_n) a.logml_n[b] = lmn;
+            if (a.logml_m) a.logml_m[b] = lmm;
+            if (a.logw) a.logw[b] = (a.logw0 ? a.logw0[p] : 0.0) + (lmm - lmn);
+            a.info[b] = 0;
+        }
+
+        // ---- predictive moments / fast-path tail blocks ------------------------------------------------
+        const int kh = k + h;
+        if (a.mu && have_y2) {
+            // one warp per forecast row: lanes stride the m columns, then reduce
+            for (int r = warp; r < h; r += kWarps) {
+                double accv = 0.0;
+                for (int cix = lane; cix < m; cix += 32) accv = fma(Lel(m + r, cix), z[cix], accv);
+                accv = warp_sum(accv);
+                if (lane == 0) a.mu[b * h + r] = (accv - a.yb) / a.ya;
+            }
+        }
+        if (a.L33) {
+            for (int e = tid; e < h * h; e += kThreads) {
+                int r = e / h, cix = e - r * h;
+                a.L33[b * h * h + e] = cix <= r ? Lel(m + r, m + cix) / a.ya : 0.0;
+            }
+        }
+        if (a.proj) {
+            for (int r = warp; r < kh; r += kWarps) {
+                double accv = 0.0;
+                for (int cix = lane; cix < n; cix += 32) accv = fma(Lel(n + r, cix), z[cix], accv);
+                accv = warp_sum(accv);
+                if (lane == 0) a.proj[b * kh + r] = accv;
+            }
+        }
+        if (a.Ltail) {
+            for (int e = tid; e < kh * kh; e += kThreads) {
+                int r = e / kh, cix = e - r * kh;
+                a.Ltail[b * kh * kh + e] = cix <= r ? Lel(n + r, n + cix) : 0.0;
+            }
+        }
+    }
+}
+
+// aux arrays: th, gg, tt, sig, tab (bytes)
+void aux_sizes(int Q, int G, int ntheta_cap, int ntab_cap, int ncp_cap, size_t (&sz)[5])
+{
+    auto up = [](size_t x) { return (x + 15) & ~size_t(15); };
+    sz[0] = up((size_t)std::max(ntheta_cap, 1) * sizeof(double));
+    sz[1] = up((size_t)Q * sizeof(int));
+    sz[2] = up((size_t)Q * sizeof(double));
+    sz[3] = up((size_t)ncp_cap * Q * sizeof(double));
+    sz[4] = up((size_t)ntab_cap * (G > 0 ? G : 0) * sizeof(double));
+}
+
+}  // namespace
+
+int fused_v2_max_q() { return 8 * (kMaxTilesPerWarp * kWarps - 1); }
+
+// Plans shared memory for the tile kernel: the tiles, yv and invL are mandatory; the aux arrays go
+// to shared memory in priority order while the CTA stays within `budget` bytes, else to global
+// scratch (L1-resident: a few KB per CTA).
+V2Plan plan_fused_v2(int q, int G, int ntheta_cap, int ntab_cap, int ncp_cap, int smem_optin, int smem_per_sm)
+{
+    V2Plan pl{};
+    const int nt = (q + 7) / 8, Q = nt * 8;
+    pl.nt = nt;
+    size_t base = ((size_t)(nt * (nt + 1) / 2) * 64 + Q + 64) * sizeof(double);
+    size_t sz[5];
+    aux_sizes(Q, G, ntheta_cap, ntab_cap, ncp_cap, sz);
+    size_t total_aux = sz[0] + sz[1] + sz[2] + sz[3] + sz[4];
+    const size_t static_smem = 1536 + 1024;   // TreeProgram + reductions + per-CTA reservation
+    // budget: 2 CTAs/SM if the mandatory part allows it, else everything the opt-in limit gives
+    size_t two = (size_t)smem_per_sm / 2;
+    size_t budget = (base + static_smem <= two) ? two - static_smem : (size_t)smem_optin - 1536;
+    if (base > (size_t)smem_optin - 1536) { pl.ok = 0; return pl; }
+    if (base + total_aux <= budget) budget = base + total_aux;   // everything fits
+    size_t s_off = 0, g_off = 0;
+    const int order[5] = {0, 1, 4, 3, 2};   // th, gg, tab, sig, tt
+    for (int oi = 0; oi < 5; ++oi) {
+        int i = order[oi];
+        if (base + s_off + sz[i] <= budget) { pl.aux_smem[i] = 1; pl.aux_off[i] = (int)s_off; s_off += sz[i]; }
+        else { pl.aux_smem[i] = 0; pl.aux_off[i] = (int)g_off; g_off += sz[i]; }
+    }
+    pl.smem_bytes = base + s_off;
+    pl.scratch_stride = (int)((g_off + 255) & ~size_t(255));
+    pl.ok = 1;
+    return pl;
+}
+
+int fused_v2_grid(const V2Plan &pl, int64_t B, int num_sms)
+{
+    int per_sm = 0;
+    cudaFuncSetAttribute(fused_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_v2_kernel, kThreads, pl.smem_bytes) != cudaSuccess ||
+        per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 1;
+    }
+    int64_t g = (int64_t)per_sm * num_sms;
+    return (int)std::min<int64_t>(g, B);
+}
+
+cudaError_t launch_fused_v2(const FusedArgs &a, const V2Plan &pl, char *scratch, int grid, cudaStream_t stream)
+{
+    V2Layout lay{};
+    lay.nt = pl.nt;
+    for (int i = 0; i < 5; ++i) { lay.aux_off[i] = pl.aux_off[i]; lay.aux_smem[i] = pl.aux_smem[i]; }
+    lay.scratch_stride = pl.scratch_stride;
+    lay.scratch = scratch;
+    cudaError_t e = cudaFuncSetAttribute(fused_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
+    if (e != cudaSuccess) return e;
+    fused_v2_kernel<<<grid, kThreads, pl.smem_bytes, stream>>>(a, lay);
+    return cudaGetLastError();
+}
+
+}  // namespace nagp

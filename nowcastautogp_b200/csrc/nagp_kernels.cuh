@@ -44,6 +44,20 @@ struct FusedArgs {
 size_t fused_smem_bytes_v1(int q, int G, int ntab_cap, int ncp_cap);
 cudaError_t launch_fused_v1(const FusedArgs &a, cudaStream_t stream);
 
+// Tile (DMMA) kernel: shared-memory plan, persistent grid size and launch.
+struct V2Plan {
+    int ok;
+    int nt;
+    int aux_off[5];
+    int aux_smem[5];
+    int scratch_stride;   // bytes of global scratch per CTA (0 when every table fits in shared memory)
+    size_t smem_bytes;
+};
+int fused_v2_max_q();
+V2Plan plan_fused_v2(int q, int G, int ntheta_cap, int ntab_cap, int ncp_cap, int smem_optin, int smem_per_sm);
+int fused_v2_grid(const V2Plan &pl, int64_t B, int num_sms);
+cudaError_t launch_fused_v2(const FusedArgs &a, const V2Plan &pl, char *scratch, int grid, cudaStream_t stream);
+
 // Scenario-shared fast path: per (scenario, particle) O(k^2 + hk) tail of the forward solve.
 struct AppendArgs {
     int64_t K, P;

@@ -14,6 +14,14 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-9
 
 
+@pytest.fixture(params=[1, 2], ids=["column-kernel", "tile-kernel"])
+def veng(engine, request):
+    """The engine pinned to one factorisation kernel (1 = shared-memory column, 2 = DMMA tile)."""
+    engine.set_variant(request.param)
+    yield engine
+    engine.set_variant(0)
+
+
 def rel(a, b):
     a, b = np.asarray(a, float), np.asarray(b, float)
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
@@ -37,10 +45,10 @@ def _oracle_joint_all(oracle, w, K, use_grid):
 
 @pytest.mark.parametrize("use_grid", [False, True])
 @pytest.mark.parametrize("n,k,h,P", [(30, 2, 5, 6), (150, 1, 9, 8), (123, 1, 4, 5), (10, 2, 10, 3)])
-def test_logml_batch_matches_oracle(engine, oracle, n, k, h, P, use_grid):
+def test_logml_batch_matches_oracle(veng, oracle, n, k, h, P, use_grid):
     w = syn.make_workload(n, k, h, 2, P, seed=100 + n + P)
     g = w.g[:n] if use_grid else None
-    got, info = engine.logml_batch(w.ens, w.t[:n], w.y1, g=g, step=w.step)
+    got, info = veng.logml_batch(w.ens, w.t[:n], w.y1, g=g, step=w.step)
     want, winfo = oracle.logml_batch(w.ens, w.t[:n], w.y1, g=g, step=w.step)
     assert (info == 0).all() and (winfo == 0).all()
     assert rel(got, want) < RTOL
@@ -48,10 +56,10 @@ def test_logml_batch_matches_oracle(engine, oracle, n, k, h, P, use_grid):
 
 @pytest.mark.parametrize("use_grid", [False, True])
 @pytest.mark.parametrize("n,k,h,P,K", [(30, 2, 5, 4, 3), (150, 1, 9, 6, 2), (40, 0, 6, 3, 1)])
-def test_forecast_instances_match_oracle(engine, oracle, n, k, h, P, K, use_grid):
+def test_forecast_instances_match_oracle(veng, oracle, n, k, h, P, K, use_grid):
     w = syn.make_workload(n, k, h, K, P, seed=7 + n)
     g = w.g if use_grid else None
-    got = engine.forecast_instances(w.ens, n, k, h, w.t, w.y1, w.y2, w.logw0, w.ya, w.yb, g=g, step=w.step,
+    got = veng.forecast_instances(w.ens, n, k, h, w.t, w.y1, w.y2, w.logw0, w.ya, w.yb, g=g, step=w.step,
                                     K=K)
     want = _oracle_joint_all(oracle, w, K, use_grid)
     assert (got["info"] == 0).all()
@@ -60,11 +68,11 @@ def test_forecast_instances_match_oracle(engine, oracle, n, k, h, P, K, use_grid
     assert rel(got["L"], want["L"]) < RTOL
 
 
-def test_forecast_instances_per_scenario_theta(engine, oracle):
+def test_forecast_instances_per_scenario_theta(veng, oracle):
     n, k, h, P, K = 60, 1, 4, 5, 4
     w = syn.make_workload(n, k, h, K, P, seed=21)
     th, nz = syn.perturbed_theta(w.ens, K, seed=5)
-    got = engine.forecast_instances(w.ens, n, k, h, w.t, w.y1, w.y2, w.logw0, w.ya, w.yb, g=w.g, step=w.step,
+    got = veng.forecast_instances(w.ens, n, k, h, w.t, w.y1, w.y2, w.logw0, w.ya, w.yb, g=w.g, step=w.step,
                                     theta=th, noise=nz)
     want = oracle.forecast_instances(w.ens, n, k, h, w.t, w.y1, w.y2, w.logw0, w.ya, w.yb, g=w.g, step=w.step,
                                      use_joint=True, theta_per_scenario=th, noise_per_scenario=nz)
@@ -73,24 +81,24 @@ def test_forecast_instances_per_scenario_theta(engine, oracle):
     assert rel(got["L"], want["L"]) < RTOL
 
 
-def test_reference_schedule_agrees(engine, oracle):
+def test_reference_schedule_agrees(veng, oracle):
     """Device (one joint factorisation) vs the oracle's REFERENCE schedule (three factorisations,
     LU solves in predict_mvn, Cholesky of Sigma*)."""
     n, k, h, P, K = 150, 1, 9, 8, 3
     w = syn.make_workload(n, k, h, K, P, seed=33)
-    got = engine.forecast_instances(w.ens, n, k, h, w.t, w.y1, w.y2, w.logw0, w.ya, w.yb)
+    got = veng.forecast_instances(w.ens, n, k, h, w.t, w.y1, w.y2, w.logw0, w.ya, w.yb)
     want = oracle.forecast_instances(w.ens, n, k, h, w.t, w.y1, w.y2, w.logw0, w.ya, w.yb, use_joint=False)
     assert rel(got["logw"], want["logw"]) < RTOL
     assert rel(got["mu"], want["mu"]) < 1e-8     # LU vs Cholesky: cond(K)·eps, see DESIGN.md
     assert rel(got["L"], want["L"]) < 1e-8
 
 
-def test_factor_append_predict_fast_path(engine, oracle):
+def test_factor_append_predict_fast_path(veng, oracle):
     n, k, h, P, K = 150, 2, 9, 8, 16
     w = syn.make_workload(n, k, h, K, P, seed=44)
-    f = engine.factor_store(w.ens, n, k, h, w.t, w.y1, w.logw0, w.ya, w.yb, g=w.g, step=w.step)
-    logw, mu = engine.append(f, w.y2)
-    _, L = engine.predict(f, want_mu=False)
+    f = veng.factor_store(w.ens, n, k, h, w.t, w.y1, w.logw0, w.ya, w.yb, g=w.g, step=w.step)
+    logw, mu = veng.append(f, w.y2)
+    _, L = veng.predict(f, want_mu=False)
     want = _oracle_joint_all(oracle, w, K, True)
     assert rel(logw, want["logw"]) < RTOL
     assert rel(mu, want["mu"]) < RTOL
@@ -100,11 +108,11 @@ def test_factor_append_predict_fast_path(engine, oracle):
     f.free()
 
 
-def test_predict_without_nowcast(engine, oracle):
+def test_predict_without_nowcast(veng, oracle):
     n, h, P = 80, 12, 4
     w = syn.make_workload(n, 0, h, 1, P, seed=51)
-    f = engine.factor_store(w.ens, n, 0, h, w.t, w.y1, None, w.ya, w.yb)
-    mu, L = engine.predict(f)
+    f = veng.factor_store(w.ens, n, 0, h, w.t, w.y1, None, w.ya, w.yb)
+    mu, L = veng.predict(f)
     for p, tr in enumerate(w.trees):
         prog, th = kn.flatten(tr)
         r = oracle.instance_joint(prog, th, w.noise[p], n, 0, h, w.t, w.y1, w.ya, w.yb)
@@ -138,7 +146,7 @@ def test_draws_bit_identical(engine, oracle):
     assert np.array_equal(np.asarray(x3), np.asarray(xo3))
 
 
-def test_fused_forecast_with_nowcasts(engine, oracle):
+def test_fused_forecast_with_nowcasts(veng, oracle):
     n, k, h, P, K, D = 150, 1, 9, 8, 50, 20
     w = syn.make_workload(n, k, h, K, P, seed=61)
     rng = np.random.default_rng(9)
@@ -146,7 +154,7 @@ def test_fused_forecast_with_nowcasts(engine, oracle):
     u = rng.uniform(size=(K, D))
     logw = np.empty((K, P))
     ess = np.empty(K)
-    x = engine.forecast_with_nowcasts(w.ens, n, k, h, w.t, w.y1, w.y2, w.logw0, zeta, w.ya, w.yb, g=w.g,
+    x = veng.forecast_with_nowcasts(w.ens, n, k, h, w.t, w.y1, w.y2, w.logw0, zeta, w.ya, w.yb, g=w.g,
                                       step=w.step, u=u, logw=logw, ess=ess)
     assert x.shape == (h, K * D)
     want = oracle.forecast_instances(w.ens, n, k, h, w.t, w.y1, w.y2, w.logw0, w.ya, w.yb, g=w.g, step=w.step,
@@ -156,30 +164,30 @@ def test_fused_forecast_with_nowcasts(engine, oracle):
     assert rel(ess, esso) < 1e-8
     assert rel(x, xo) < 1e-8
     # draw stage in isolation is bit-exact: feed the oracle the device's own moments
-    f = engine.factor_store(w.ens, n, k, h, w.t, w.y1, w.logw0, w.ya, w.yb, g=w.g, step=w.step)
-    lw, mu = engine.append(f, w.y2)
-    _, L = engine.predict(f, want_mu=False)
-    xb, _, comp = engine.draw(lw, mu, L, zeta, u=u)
+    f = veng.factor_store(w.ens, n, k, h, w.t, w.y1, w.logw0, w.ya, w.yb, g=w.g, step=w.step)
+    lw, mu = veng.append(f, w.y2)
+    _, L = veng.predict(f, want_mu=False)
+    xb, _, comp = veng.draw(lw, mu, L, zeta, u=u)
     xob, _, _ = oracle.draws(lw, mu, L, zeta, comp=comp)
     assert np.array_equal(np.asarray(xb), np.asarray(xob))
     assert np.array_equal(np.asarray(xb), np.asarray(x))
     f.free()
 
 
-def test_not_positive_definite_reports_info(engine):
+def test_not_positive_definite_reports_info(veng):
     # flat series + zero noise/jitter → singular Gram (issue #51 regression, test_model_fitting.jl:97-98)
     from nowcastautogp_b200.engine import PosDefError
     ens = kn.pack_ensemble([kn.Constant(1.0)], [0.0])
-    engine.set_jitter(0.0)
+    veng.set_jitter(0.0)
     try:
         t = np.linspace(0, 1, 12)
         y = np.ones(12)
-        lm, info = engine.logml_batch(ens, t, y)
+        lm, info = veng.logml_batch(ens, t, y)
         assert info[0] == 2 and np.isnan(lm[0])
         with pytest.raises(PosDefError):
-            engine.logml_batch(ens, t, y, check=True)
+            veng.logml_batch(ens, t, y, check=True)
     finally:
-        engine.set_jitter(1e-5)
+        veng.set_jitter(1e-5)
 
 
 def test_bad_program_rejected(engine):
