@@ -41,6 +41,25 @@ __device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b)
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
+// explicit 32-bit shared-memory accesses: keeps the hot loops free of generic->shared address math
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double2 lds128(uint32_t addr)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double lds64(uint32_t addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, double v)
+{
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+
 // element (r, c) of an operand-layout tile: both k-chunks of a fragment lane are adjacent
 __device__ __forceinline__ int op_idx(int r, int c) { return ((r * 4 + (c & 3)) << 1) + (c >> 2); }
 
@@ -138,6 +157,26 @@ __device__ __forceinline__ void tree_eval4(const TreeProgram &tp, const double *
     }
 #pragma unroll
     for (int e = 0; e < 4; ++e) out[e] = top[e];
+}
+
+// DMMA inner loop of the left-looking update for NA tile rows of one warp: per P one 16-byte LDS for
+// the shared B fragment (tile (Jc, P)), and per row one 16-byte LDS + two DMMAs (one per k-chunk, on
+// separate accumulator chains).
+template <int NA>
+__device__ __forceinline__ void kloop(double (&acc)[kMaxTilesPerWarp][2][2], uint32_t bp,
+                                      const uint32_t (&rowa)[kMaxTilesPerWarp], int P0, int P1)
+{
+#pragma unroll 2
+    for (int P = P0; P < P1; ++P) {
+        const uint32_t off = (uint32_t)P * 512u;
+        const double2 bf = lds128(bp + off);
+#pragma unroll
+        for (int u = 0; u < NA; ++u) {
+            const double2 af = lds128(rowa[u] + off);
+            dmma(acc[u][0][0], acc[u][0][1], af.x, bf.x);
+            dmma(acc[u][1][0], acc[u][1][1], af.y, bf.y);
+        }
+    }
 }
 
 // In-register Cholesky of an 8x8 tile held in DMMA accumulator layout (lane (r = l>>2, j = l&3)
@@ -319,89 +358,133 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
         }
         __syncthreads();
 
-        // ---- left-looking tile-column Cholesky --------------------------------------------------------
+        // ---- left-looking tile-column Cholesky with one column of lookahead ---------------------------
+        // A warp owns the tile rows I == warp (mod 8). Slot u counts them from the bottom (u = 0 is the
+        // last row below nt), so the rows still active in column J are always the prefix u < NA and the
+        // DMMA loop is instantiated per NA without predicates. The observation vector is one more row
+        // (index nt) owned by warp nt mod 8. While the owner of diagonal tile J factors it, the other
+        // warps already accumulate column J+1 over P < J (every term that does not need column J).
         const int lr = lane >> 2, lj = lane & 3;
+        const int oi0 = op_idx(lr, 2 * lj), oi1 = op_idx(lr, 2 * lj + 1);
+        const int cv0 = (lane & ~3) + (lj >> 1), cv1 = cv0 + 2;
+        const bool odd = lane & 1;
+        const int nreg = warp < nt ? (nt - 1 - warp) / kWarps + 1 : 0;   // regular rows of this warp
+        const int Ilast = warp + (nreg - 1) * kWarps;
+        const bool has_y = ((nt - warp) & (kWarps - 1)) == 0;
+        const uint32_t tiles_a = smem_addr(tiles), yv_a = smem_addr(yv), invL_a = smem_addr(invL);
+        uint32_t rowa[kMaxTilesPerWarp];        // shared address of this lane's fragment in tile (I_u, 0)
+#pragma unroll
+        for (int u = 0; u < kMaxTilesPerWarp; ++u) {
+            const int I = Ilast - u * kWarps;
+            rowa[u] = tiles_a + (uint32_t)(tri(I > 0 ? I : 0) * 512 + lane * 16);
+        }
+        double accn[kMaxTilesPerWarp][2][2];   // [slot][k-chunk chain][acc regs] partial sums of the current column
+        double yacc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+        for (int u = 0; u < kMaxTilesPerWarp; ++u) { accn[u][0][0] = accn[u][0][1] = accn[u][1][0] = accn[u][1][1] = 0.0; }
+        int pre_done = 0;                       // terms P < pre_done are already in accn / yacc
+
+        // accumulate sum_{P0 <= P < P1} L_IP L_{Jc,P}^T for the owned rows I >= Jc (and the observation row)
+        auto accumulate = [&](int Jc, int P0, int P1) {
+            if (P0 >= P1) return;
+            const int NA = Ilast >= Jc ? (Ilast - Jc) / kWarps + 1 : 0;
+            const uint32_t bp = tiles_a + (uint32_t)(tri(Jc) * 512 + lane * 16);
+            switch (NA) {
+            case 1: kloop<1>(accn, bp, rowa, P0, P1); break;
+            case 2: kloop<2>(accn, bp, rowa, P0, P1); break;
+            case 3: kloop<3>(accn, bp, rowa, P0, P1); break;
+            case 4: kloop<4>(accn, bp, rowa, P0, P1); break;
+            default: break;
+            }
+            if (has_y) {
+                const uint32_t yp = yv_a + lj * 8;
+#pragma unroll 2
+                for (int P = P0; P < P1; ++P) {
+                    const double2 bf = lds128(bp + (uint32_t)P * 512u);
+                    const double a0 = lr == 0 ? lds64(yp + P * 64) : 0.0;
+                    const double a1 = lr == 0 ? lds64(yp + P * 64 + 32) : 0.0;
+                    dmma(yacc[0][0], yacc[0][1], a0, bf.x);
+                    dmma(yacc[1][0], yacc[1][1], a1, bf.y);
+                }
+            }
+        };
+
         for (int J = 0; J < nt; ++J) {
-            const int I0 = J + ((warp - J) & (kWarps - 1));   // first tile row >= J owned by this warp
-            double acc[kMaxTilesPerWarp][2];
+            const bool owner = (warp == (J & (kWarps - 1)));
+            const int NA = Ilast >= J ? (Ilast - J) / kWarps + 1 : 0;   // active regular rows (I >= J)
+            // (1) remaining terms of column J, (2) C = A_IJ - sum
+            accumulate(J, pre_done, J);
+            double c[kMaxTilesPerWarp][2], cy[2] = {0.0, 0.0};
+            const uint32_t joff = (uint32_t)J * 512u;
 #pragma unroll
-            for (int t = 0; t < kMaxTilesPerWarp; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
-            const double *rowJ = tiles + tri(J) * 64;
-            for (int P = 0; P < J; ++P) {
-                const double2 bf = *reinterpret_cast<const double2 *>(rowJ + P * 64 + lane * 2);
+            for (int u = 0; u < kMaxTilesPerWarp; ++u) {
+                c[u][0] = 0.0; c[u][1] = 0.0;
+                if (u < NA) {
+                    const double2 g2 = lds128(rowa[u] + joff);
+                    c[u][0] = g2.x - (accn[u][0][0] + accn[u][1][0]);
+                    c[u][1] = g2.y - (accn[u][0][1] + accn[u][1][1]);
+                }
+                accn[u][0][0] = accn[u][0][1] = accn[u][1][0] = accn[u][1][1] = 0.0;
+            }
+            if (has_y) {
+                const double y0 = lr == 0 ? lds64(yv_a + (J * 8 + 2 * lj) * 8) : 0.0;
+                const double y1v = lr == 0 ? lds64(yv_a + (J * 8 + 2 * lj + 1) * 8) : 0.0;
+                cy[0] = y0 - (yacc[0][0] + yacc[1][0]);
+                cy[1] = y1v - (yacc[0][1] + yacc[1][1]);
+                yacc[0][0] = yacc[0][1] = yacc[1][0] = yacc[1][1] = 0.0;
+            }
+            if (owner) {
+                // (3) diagonal tile (slot NA-1): factor + invert in registers, publish, release the others
+                double w0, w1, piv[8], d0 = 0.0, d1 = 0.0;
 #pragma unroll
-                for (int t = 0; t < kMaxTilesPerWarp; ++t) {
-                    const int I = I0 + t * kWarps;
-                    if (I < nt) {
-                        const double2 af = *reinterpret_cast<const double2 *>(tiles + (tri(I) + P) * 64 + lane * 2);
-                        dmma(acc[t][0], acc[t][1], af.x, bf.x);
-                        dmma(acc[t][0], acc[t][1], af.y, bf.y);
-                    } else if (I == nt) {   // observation row: only tile row 0 is populated
-                        const double a0 = lr == 0 ? yv[P * 8 + lj] : 0.0;
-                        const double a1 = lr == 0 ? yv[P * 8 + 4 + lj] : 0.0;
-                        dmma(acc[t][0], acc[t][1], a0, bf.x);
-                        dmma(acc[t][0], acc[t][1], a1, bf.y);
+                for (int u = 0; u < kMaxTilesPerWarp; ++u) if (u == NA - 1) { d0 = c[u][0]; d1 = c[u][1]; }
+                const int bad = chol8_inv(d0, d1, w0, w1, lane, q - J * 8, piv);
+                const uint32_t dt = tiles_a + (uint32_t)((tri(J) + J) * 512);
+                sts64(dt + oi0 * 8, d0);
+                sts64(dt + oi1 * 8, d1);
+                sts64(invL_a + oi0 * 8, w0);
+                sts64(invL_a + oi1 * 8, w1);
+                if (bad && lane == 0) s_info = J * 8 + bad;
+                __syncwarp();
+                asm volatile("bar.arrive 1, %0;" ::"n"(kThreads) : "memory");
+                pre_done = 0;   // its own lookahead is deferred to the next column (hidden behind that owner)
+            } else {
+                // (4) lookahead: column J+1 over P < J
+                if (J + 1 < nt) accumulate(J + 1, 0, J);
+                pre_done = J;
+                asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+            }
+            // (5) triangular solve of the column: X = C * invL^T, stored in operand layout
+            if (!s_info) {
+                const double2 ib = lds128(invL_a + lane * 16);
+                const int nsolve = owner ? NA - 1 : NA;   // rows strictly below the diagonal
+#pragma unroll
+                for (int u = 0; u < kMaxTilesPerWarp; ++u) {
+                    if (u < nsolve) {
+                        const double v00 = shfl(c[u][0], cv0), v01 = shfl(c[u][1], cv0);
+                        const double v10 = shfl(c[u][0], cv1), v11 = shfl(c[u][1], cv1);
+                        double x0 = 0.0, x1 = 0.0;
+                        dmma(x0, x1, odd ? v01 : v00, ib.x);
+                        dmma(x0, x1, odd ? v11 : v10, ib.y);
+                        const uint32_t dt = rowa[u] - lane * 16 + joff;
+                        sts64(dt + oi0 * 8, x0);
+                        sts64(dt + oi1 * 8, x1);
                     }
                 }
-            }
-            // C = A_IJ - sum
-            double c[kMaxTilesPerWarp][2];
-#pragma unroll
-            for (int t = 0; t < kMaxTilesPerWarp; ++t) {
-                const int I = I0 + t * kWarps;
-                c[t][0] = 0.0; c[t][1] = 0.0;
-                if (I < nt) {
-                    const double2 g2 = *reinterpret_cast<const double2 *>(tiles + (tri(I) + J) * 64 + lane * 2);
-                    c[t][0] = g2.x - acc[t][0];
-                    c[t][1] = g2.y - acc[t][1];
-                } else if (I == nt) {
-                    const double y0 = lr == 0 ? yv[J * 8 + 2 * lj] : 0.0;
-                    const double y1v = lr == 0 ? yv[J * 8 + 2 * lj + 1] : 0.0;
-                    c[t][0] = y0 - acc[t][0];
-                    c[t][1] = y1v - acc[t][1];
+                if (has_y) {
+                    const double v00 = shfl(cy[0], cv0), v01 = shfl(cy[1], cv0);
+                    const double v10 = shfl(cy[0], cv1), v11 = shfl(cy[1], cv1);
+                    double x0 = 0.0, x1 = 0.0;
+                    dmma(x0, x1, odd ? v01 : v00, ib.x);
+                    dmma(x0, x1, odd ? v11 : v10, ib.y);
+                    if (lr == 0) {
+                        sts64(yv_a + (J * 8 + 2 * lj) * 8, x0);
+                        sts64(yv_a + (J * 8 + 2 * lj + 1) * 8, x1);
+                    }
                 }
-            }
-            // diagonal tile: factor + invert in registers (the owner's tile t == 0)
-            if (I0 == J) {
-                double w0, w1, piv[8];
-                const int nreal = q - J * 8;
-                const int bad = chol8_inv(c[0][0], c[0][1], w0, w1, lane, nreal, piv);
-                double *dt = tiles + (tri(J) + J) * 64;
-                dt[op_idx(lr, 2 * lj)] = c[0][0];
-                dt[op_idx(lr, 2 * lj + 1)] = c[0][1];
-                invL[op_idx(lr, 2 * lj)] = w0;
-                invL[op_idx(lr, 2 * lj + 1)] = w1;
-                if (bad && lane == 0) s_info = J * 8 + bad;
             }
             __syncthreads();
             if (s_info) break;
-            // triangular solve of the column: X = C * invL^T, stored in operand layout
-            {
-                const double2 ib = *reinterpret_cast<const double2 *>(invL + lane * 2);
-#pragma unroll
-                for (int t = 0; t < kMaxTilesPerWarp; ++t) {
-                    const int I = I0 + t * kWarps;
-                    if (I > J && I <= nt) {
-                        const int src0 = (lane & ~3) + (lj >> 1), src1 = src0 + 2;
-                        const double v00 = shfl(c[t][0], src0), v01 = shfl(c[t][1], src0);
-                        const double v10 = shfl(c[t][0], src1), v11 = shfl(c[t][1], src1);
-                        const double a0 = (lane & 1) ? v01 : v00;
-                        const double a1 = (lane & 1) ? v11 : v10;
-                        double x0 = 0.0, x1 = 0.0;
-                        dmma(x0, x1, a0, ib.x);
-                        dmma(x0, x1, a1, ib.y);
-                        if (I < nt) {
-                            double *dt = tiles + (tri(I) + J) * 64;
-                            dt[op_idx(lr, 2 * lj)] = x0;
-                            dt[op_idx(lr, 2 * lj + 1)] = x1;
-                        } else if (lr == 0) {
-                            yv[J * 8 + 2 * lj] = x0;
-                            yv[J * 8 + 2 * lj + 1] = x1;
-                        }
-                    }
-                }
-            }
-            __syncthreads();
         }
 
         if (s_info) {
