@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnagp.so")
+LIB_PATH = os.environ.get("NAGP_LIB", os.path.join(_HERE, "libnagp.so"))
 
 E_ARG, E_CUDA, E_PROGRAM, E_SIZE = -1, -2, -3, -4
 

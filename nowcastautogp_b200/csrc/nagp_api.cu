@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -241,9 +242,15 @@ int32_t run_fused(nagp_ctx *ctx, FusedArgs a, const int64_t *theta_off_host)
                                   ctx->smem_optin, ctx->smem_per_sm);
         if (pl.ok) {
             int grid = fused_v2_grid(pl, a.B, ctx->num_sms);
+            if (getenv("NAGP_DEBUG"))
+                fprintf(stderr, "[nagp] tile kernel: q=%d G=%d caps(tab=%d,cp=%d,theta=%d) smem=%zu B aux_in_smem(th,gg,tt,sig,tab)=%d%d%d%d%d scratch/CTA=%d grid=%d\n",
+                        q, a.G, a.ntab_cap, a.ncp_cap, (int)nth, pl.smem_bytes, pl.aux_smem[0], pl.aux_smem[1],
+                        pl.aux_smem[2], pl.aux_smem[3], pl.aux_smem[4], pl.scratch_stride, grid);
             char *scr = nullptr;
             if (pl.scratch_stride) NAGP_TRY(scratch(ctx, (size_t)grid * pl.scratch_stride, &scr));
-            NAGP_CUDA(ctx, launch_fused_v2(a, pl, scr, grid, ctx->stream));
+            unsigned long long *counter = nullptr;
+            NAGP_TRY(scratch(ctx, 1, &counter));
+            NAGP_CUDA(ctx, launch_fused_v2(a, pl, scr, counter, grid, ctx->stream));
             ctx->launches += 1;
             return NAGP_OK;
         }

@@ -19,8 +19,25 @@
 // Arithmetic contract: docs/KERNEL_SPEC.md §3-§6.
 #include <algorithm>
 
+#ifndef NAGP_EXP
+#define NAGP_EXP 0   // timing-attribution experiments (tools/exp_build.sh); 0 in every product build
+#endif
+
 #include "nagp_kernels.cuh"
 #include "nagp_tree.cuh"
+
+#if NAGP_EXP == 9
+__device__ long long g_nagp_dbg[8192];
+extern "C" int nagp_debug_read(long long *out, int count)
+{
+    return (int)cudaMemcpyFromSymbol(out, g_nagp_dbg, sizeof(long long) * count);
+}
+#define DBG_T(J, ph) do { if (b == 0 && lane == 0) g_nagp_dbg[((J) * 8 + warp) * 8 + (ph)] = clock64(); } while (0)
+#define DBG_G(ph) do { if (b == 0 && tid == 0) g_nagp_dbg[8000 + (ph)] = clock64(); } while (0)
+#else
+#define DBG_T(J, ph) do { } while (0)
+#define DBG_G(ph) do { } while (0)
+#endif
 
 namespace nagp {
 
@@ -28,7 +45,7 @@ namespace {
 
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
-constexpr int kMaxTilesPerWarp = 4;   // ceil((nt + 1) / kWarps), nt <= 29
+constexpr int kMaxTilesPerWarp = 4;   // ceil(nt / kWarps), nt <= 29
 constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
@@ -69,94 +86,93 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-// 4-wide interpreter: entries (i, j0..j0+3) of one matrix row. Top of stack in registers, the rest
-// in local memory. Same formulas/order as tree_eval (docs/KERNEL_SPEC.md §3).
-__device__ __forceinline__ void tree_eval4(const TreeProgram &tp, const double *th, double ti, int i,
-                                           const double (&tj)[4], const double (&delta)[4],
-                                           const int (&lag)[4], int j0, const double *tab, int G,
-                                           const double *sig, int Q, double (&out)[4])
+// 4-wide interpreter over arbitrary entries (ii[e], jj[e]): one lane evaluates its two accumulator-
+// layout entries of two tiles at once. The two top stack levels live in registers; deeper levels
+// (expression depth >= 3) go to local memory. Same formulas and evaluation order as tree_eval
+// (docs/KERNEL_SPEC.md §3).
+struct EvalCtx {
+    const double *th, *tt, *tab, *sig;
+    double step;
+    int G, Q;
+    bool grid;
+};
+
+__device__ __forceinline__ void tree_eval4(const TreeProgram &tp, const EvalCtx &cx, const int (&ii)[4],
+                                           const int (&jj)[4], const int (&lag)[4], double (&top)[4])
 {
     double st[MAX_STACK][4];
-    double top[4] = {0, 0, 0, 0};
+    double sec[4];
     int sp = 0;
     const int len = tp.clen;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { top[e] = 0.0; sec[e] = 0.0; }
     for (int o = 0; o < len; ++o) {
-        const int op = tp.cop[o];
-        const double *p = th + tp.carg[o];
+        const uint32_t wd = tp.cword[o];
+        const int op = wd & 0xff;
+        const double *p = cx.th + ((wd >> 8) & 0xffff);
         if (op <= OP_PERIODIC || op == OP_TABLE) {
-            if (sp > 0) {
+            if (sp >= 2) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) st[sp - 1][e] = top[e];
+                for (int e = 0; e < 4; ++e) st[sp - 2][e] = sec[e];
             }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) sec[e] = top[e];
             ++sp;
-            switch (op) {
-            case OP_CONSTANT:
-#pragma unroll
-                for (int e = 0; e < 4; ++e) top[e] = p[0];
-                break;
-            case OP_LINEAR: {
-                const double u = ti - p[0];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) top[e] = fma(p[2], u * (tj[e] - p[0]), p[1]);
-                break;
-            }
-            case OP_SQEXP:
-#pragma unroll
-                for (int e = 0; e < 4; ++e) { double r = delta[e] / p[0]; top[e] = p[1] * exp(-0.5 * (r * r)); }
-                break;
-            case OP_GAMMAEXP:
-#pragma unroll
-                for (int e = 0; e < 4; ++e) { double r = delta[e] / p[0]; top[e] = p[2] * exp(-pow(r, p[1])); }
-                break;
-            case OP_PERIODIC:
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    double s = sin(3.14159265358979323846 * (delta[e] / p[1]));
-                    top[e] = p[2] * exp(-2.0 * (s * s) / (p[0] * p[0]));
-                }
-                break;
-            default: {  // OP_TABLE
-                const double *tb = tab + tp.carg[o] * G;
+            if (op == OP_TABLE) {
+                const double *tb = cx.tab + ((wd >> 8) & 0xffff) * cx.G;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) top[e] = tb[lag[e]];
-                break;
-            }
+            } else if (op == OP_LINEAR) {
+                const double c0 = p[0], b0 = p[1], a0 = p[2];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) top[e] = fma(a0, (cx.tt[ii[e]] - c0) * (cx.tt[jj[e]] - c0), b0);
+            } else if (op == OP_CONSTANT) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) top[e] = p[0];
+            } else {
+                // stationary leaf evaluated directly (pairwise times, or no table slot left)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const double delta = cx.grid ? (double)lag[e] * cx.step : fabs(cx.tt[ii[e]] - cx.tt[jj[e]]);
+                    double v;
+                    if (op == OP_SQEXP) { double r = delta / p[0]; v = p[1] * exp(-0.5 * (r * r)); }
+                    else if (op == OP_GAMMAEXP) { double r = delta / p[0]; v = p[2] * exp(-pow(r, p[1])); }
+                    else {
+                        double sn = sin(3.14159265358979323846 * (delta / p[1]));
+                        v = p[2] * exp(-2.0 * (sn * sn) / (p[0] * p[0]));
+                    }
+                    top[e] = v;
+                }
             }
         } else {
-            --sp;   // left operand is st[sp-1], right operand is top
-            switch (op) {
-            case OP_PLUS:
+            --sp;   // left operand is sec, right operand is top
+            if (op == OP_PLUS) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) top[e] = st[sp - 1][e] + top[e];
-                break;
-            case OP_TIMES:
+                for (int e = 0; e < 4; ++e) top[e] = sec[e] + top[e];
+            } else if (op == OP_TIMES) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) top[e] = st[sp - 1][e] * top[e];
-                break;
-            case OP_CHANGEPOINT: {
-                const double si = 0.5 * (1.0 + tanh((ti - p[0]) / p[1]));
+                for (int e = 0; e < 4; ++e) top[e] = sec[e] * top[e];
+            } else if (op == OP_CHANGEPOINT_TAB) {
+                const double *sg = cx.sig + (wd >> 24) * cx.Q;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    double sj = 0.5 * (1.0 + tanh((tj[e] - p[0]) / p[1]));
-                    top[e] = ((1.0 - si) * (1.0 - sj)) * st[sp - 1][e] + (si * sj) * top[e];
+                    const double si = sg[ii[e]], sj = sg[jj[e]];
+                    top[e] = ((1.0 - si) * (1.0 - sj)) * sec[e] + (si * sj) * top[e];
                 }
-                break;
-            }
-            default: {  // OP_CHANGEPOINT_TAB
-                const double *sg = sig + tp.caux[o] * Q;
-                const double si = sg[i];
+            } else {   // OP_CHANGEPOINT evaluated directly
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    double sj = sg[j0 + e];
-                    top[e] = ((1.0 - si) * (1.0 - sj)) * st[sp - 1][e] + (si * sj) * top[e];
+                    const double si = 0.5 * (1.0 + tanh((cx.tt[ii[e]] - p[0]) / p[1]));
+                    const double sj = 0.5 * (1.0 + tanh((cx.tt[jj[e]] - p[0]) / p[1]));
+                    top[e] = ((1.0 - si) * (1.0 - sj)) * sec[e] + (si * sj) * top[e];
                 }
-                break;
             }
+            if (sp >= 2) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) sec[e] = st[sp - 2][e];
             }
         }
     }
-#pragma unroll
-    for (int e = 0; e < 4; ++e) out[e] = top[e];
 }
 
 // DMMA inner loop of the left-looking update for NA tile rows of one warp: per P one 16-byte LDS for
@@ -223,6 +239,7 @@ struct V2Layout {
     int aux_smem[5];   // 1: shared memory (offset from aux base), 0: per-CTA global scratch
     int scratch_stride;   // bytes of global scratch per CTA
     char *scratch;
+    unsigned long long *work_counter;   // dynamic instance scheduler (zeroed before the launch)
 };
 
 __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a, const V2Layout lay)
@@ -230,6 +247,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
     extern __shared__ __align__(16) double smem[];
     __shared__ TreeProgram tp;
     __shared__ int s_info;
+    __shared__ long long s_next;
     __shared__ double s_red[4][kWarps];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -257,14 +275,20 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
         gg[i] = (a.g && i < q) ? a.g[i] : 0;
     }
 
-    for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x) {
+    // instances differ a lot in cost (kernel-tree size): hand them out dynamically
+    for (;;) {
+        __syncthreads();   // previous instance fully consumed (shared memory and s_next)
+        if (tid == 0) s_next = (long long)atomicAdd(lay.work_counter, 1ull);
+        __syncthreads();
+        const int64_t b = s_next;
+        if (b >= a.B) break;
         const int64_t s = b / a.P;
         const int p = (int)(b % a.P);
         const int64_t po = a.prog_off[p], plen = a.prog_off[p + 1] - po;
         const int64_t to = a.theta_off[p], ntheta = a.theta_off[p + 1] - to;
         const double *theta_g = a.theta + s * a.theta_stride_k + to;
 
-        __syncthreads();   // previous instance fully consumed
+        DBG_G(0);
         if (tid == 0) {
             s_info = 0;
             if (ntheta > MAX_THETA) tp.error = -3;
@@ -283,6 +307,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
         }
         const int ntab = tp.ntab, ncp = tp.ncp;
 
+        DBG_G(1);
         // ---- lag tables and changepoint sigma tables ------------------------------------------------
         for (int e = tid; e < ntab * G; e += kThreads) {
             int id = e / G, lg = e - id * G;
@@ -297,55 +322,62 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
         }
         __syncthreads();
 
-        // ---- Gram into row-major tiles: one unit = 4 consecutive columns of one tile row ------------
+        DBG_G(2);
+        // ---- Gram into row-major tiles: a warp writes two whole tiles per iteration; lane (r, c) owns
+        //      the accumulator-layout pair (r, 2c), (r, 2c+1) of each, so stores are contiguous 16 B per lane
         const double nz = a.noise[s * a.noise_stride_k + p];
         const double d_lo = nz + a.jitter;
         const double d_hi = (a.noise_pred >= 0.0 ? a.noise_pred : nz) + a.jitter;
         const bool single_table = (tp.clen == 1 && tp.cop[0] == OP_TABLE);
-        for (int unit = tid; unit < ntiles * 16; unit += kThreads) {
-            const int tix = unit >> 4, r = (unit >> 1) & 7, c4 = (unit & 1) << 2;
-            int I = (int)((sqrtf(8.0f * (float)tix + 1.0f) - 1.0f) * 0.5f);
-            while (tri(I + 1) <= tix) ++I;
-            while (tri(I) > tix) --I;
-            const int J = tix - tri(I);
-            const int i = I * 8 + r, j0 = J * 8 + c4;
-            double out[4];
-            if (i >= q) {
+        EvalCtx cx;
+        cx.th = th; cx.tt = tt; cx.tab = tab; cx.sig = sig;
+        cx.step = a.step; cx.G = G; cx.Q = Q; cx.grid = a.g != nullptr;
+        {
+            const int gr = lane >> 2, gc = (lane & 3) * 2;
+            for (int t0 = warp * 2; t0 < ntiles; t0 += kWarps * 2) {
+                int ii[4], jj[4], lag[4], tixs[2];
+                bool real[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) out[e] = (i == j0 + e) ? 1.0 : 0.0;
-            } else {
-                double tj[4], delta[4];
-                int lag[4];
-                const int gi = gg[i];
-                const double ti = tt[i];
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int tix = min(t0 + h2, ntiles - 1);
+                    tixs[h2] = tix;
+                    int I = (int)((sqrtf(8.0f * (float)tix + 1.0f) - 1.0f) * 0.5f);
+                    I += (tri(I + 1) <= tix);
+                    I -= (tri(I) > tix);
+                    const int J = tix - tri(I);
+                    const int gi = gg[I * 8 + gr];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    tj[e] = tt[j0 + e];
-                    if (a.g) {
-                        int lg = gi - gg[j0 + e];
-                        lag[e] = lg < 0 ? -lg : lg;
-                        delta[e] = (double)lag[e] * a.step;
-                    } else {
-                        lag[e] = 0;
-                        delta[e] = fabs(ti - tj[e]);
+                    for (int e = 0; e < 2; ++e) {
+                        const int x = h2 * 2 + e;
+                        ii[x] = I * 8 + gr;
+                        jj[x] = J * 8 + gc + e;
+                        const int lg = gi - gg[jj[x]];
+                        lag[x] = lg < 0 ? -lg : lg;
+                        real[x] = ii[x] < q && jj[x] < q;
                     }
                 }
+                double out[4];
+#if NAGP_EXP == 3
+                if (true) {
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) out[x] = 0.0;
+                } else
+#endif
                 if (single_table) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) out[e] = tab[lag[e]];
+                    for (int x = 0; x < 4; ++x) out[x] = tab[lag[x]];
                 } else {
-                    tree_eval4(tp, th, ti, i, tj, delta, lag, j0, tab, G, sig, Q, out);
+                    tree_eval4(tp, cx, ii, jj, lag, out);
                 }
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int jj = j0 + e;
-                    if (jj >= q) out[e] = 0.0;
-                    else if (jj == i) out[e] += (i < m) ? d_lo : d_hi;
+                for (int x = 0; x < 4; ++x) {
+                    if (!real[x]) out[x] = (ii[x] == jj[x]) ? 1.0 : 0.0;
+                    else if (ii[x] == jj[x]) out[x] += (ii[x] < m) ? d_lo : d_hi;
                 }
+                *reinterpret_cast<double2 *>(tiles + tixs[0] * 64 + lane * 2) = make_double2(out[0], out[1]);
+                if (t0 + 1 < ntiles)
+                    *reinterpret_cast<double2 *>(tiles + tixs[1] * 64 + lane * 2) = make_double2(out[2], out[3]);
             }
-            double2 *dst = reinterpret_cast<double2 *>(tiles + tix * 64 + r * 8 + c4);
-            dst[0] = make_double2(out[0], out[1]);
-            dst[1] = make_double2(out[2], out[3]);
         }
         {
             const double *y1 = a.y1 + b * a.y1_stride;
@@ -358,6 +390,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
         }
         __syncthreads();
 
+        DBG_G(3);
         // ---- left-looking tile-column Cholesky with one column of lookahead ---------------------------
         // A warp owns the tile rows I == warp (mod 8). Slot u counts them from the bottom (u = 0 is the
         // last row below nt), so the rows still active in column J are always the prefix u < NA and the
@@ -386,6 +419,9 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
 
         // accumulate sum_{P0 <= P < P1} L_IP L_{Jc,P}^T for the owned rows I >= Jc (and the observation row)
         auto accumulate = [&](int Jc, int P0, int P1) {
+#if NAGP_EXP == 2
+            return;
+#endif
             if (P0 >= P1) return;
             const int NA = Ilast >= Jc ? (Ilast - Jc) / kWarps + 1 : 0;
             const uint32_t bp = tiles_a + (uint32_t)(tri(Jc) * 512 + lane * 16);
@@ -413,8 +449,9 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
             const bool owner = (warp == (J & (kWarps - 1)));
             const int NA = Ilast >= J ? (Ilast - J) / kWarps + 1 : 0;   // active regular rows (I >= J)
             // (1) remaining terms of column J, (2) C = A_IJ - sum
+            DBG_T(J, 0);
             accumulate(J, pre_done, J);
-            double c[kMaxTilesPerWarp][2], cy[2] = {0.0, 0.0};
+            double c[kMaxTilesPerWarp][2], cy[2] = {0.0, 0.0}, d0 = 0.0, d1 = 0.0;
             const uint32_t joff = (uint32_t)J * 512u;
 #pragma unroll
             for (int u = 0; u < kMaxTilesPerWarp; ++u) {
@@ -423,6 +460,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
                     const double2 g2 = lds128(rowa[u] + joff);
                     c[u][0] = g2.x - (accn[u][0][0] + accn[u][1][0]);
                     c[u][1] = g2.y - (accn[u][0][1] + accn[u][1][1]);
+                    d0 = c[u][0]; d1 = c[u][1];   // ends up holding slot NA-1: the diagonal tile of its owner
                 }
                 accn[u][0][0] = accn[u][0][1] = accn[u][1][0] = accn[u][1][1] = 0.0;
             }
@@ -433,29 +471,45 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
                 cy[1] = y1v - (yacc[0][1] + yacc[1][1]);
                 yacc[0][0] = yacc[0][1] = yacc[1][0] = yacc[1][1] = 0.0;
             }
+            DBG_T(J, 1);
             if (owner) {
                 // (3) diagonal tile (slot NA-1): factor + invert in registers, publish, release the others
-                double w0, w1, piv[8], d0 = 0.0, d1 = 0.0;
-#pragma unroll
-                for (int u = 0; u < kMaxTilesPerWarp; ++u) if (u == NA - 1) { d0 = c[u][0]; d1 = c[u][1]; }
+                double w0, w1, piv[8];
+#if NAGP_EXP == 1
+                const int bad = 0; w0 = (lr == 2 * lj) ? 1.0 : 0.0; w1 = (lr == 2 * lj + 1) ? 1.0 : 0.0; (void)piv;
+#else
                 const int bad = chol8_inv(d0, d1, w0, w1, lane, q - J * 8, piv);
+#endif
                 const uint32_t dt = tiles_a + (uint32_t)((tri(J) + J) * 512);
                 sts64(dt + oi0 * 8, d0);
                 sts64(dt + oi1 * 8, d1);
                 sts64(invL_a + oi0 * 8, w0);
                 sts64(invL_a + oi1 * 8, w1);
-                if (bad && lane == 0) s_info = J * 8 + bad;
+                if (bad && lane == 0 && NAGP_EXP == 0) s_info = J * 8 + bad;
                 __syncwarp();
+                DBG_T(J, 2);
                 asm volatile("bar.arrive 1, %0;" ::"n"(kThreads) : "memory");
                 pre_done = 0;   // its own lookahead is deferred to the next column (hidden behind that owner)
+            } else if ((warp & 3) == (J & 3)) {
+                // shares its scheduler (and FP64 pipe) with the owner: leave the pipe to the serial
+                // diagonal factorisation and catch up at the top of the next column
+                pre_done = 0;
+                DBG_T(J, 2);
+                asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
             } else {
                 // (4) lookahead: column J+1 over P < J
                 if (J + 1 < nt) accumulate(J + 1, 0, J);
                 pre_done = J;
+                DBG_T(J, 2);
                 asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
             }
             // (5) triangular solve of the column: X = C * invL^T, stored in operand layout
+            DBG_T(J, 3);
+#if NAGP_EXP == 4
+            if (false) {
+#else
             if (!s_info) {
+#endif
                 const double2 ib = lds128(invL_a + lane * 16);
                 const int nsolve = owner ? NA - 1 : NA;   // rows strictly below the diagonal
 #pragma unroll
@@ -483,9 +537,12 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
                     }
                 }
             }
+            DBG_T(J, 4);
             __syncthreads();
+            DBG_T(J, 5);
             if (s_info) break;
         }
+        DBG_G(4);
 
         if (s_info) {
             if (tid == 0) {
@@ -526,6 +583,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
             a.info[b] = 0;
         }
 
+        DBG_G(5);
         // ---- predictive moments / fast-path tail blocks ------------------------------------------------
         const int kh = k + h;
         if (a.mu && have_y2) {
@@ -619,9 +677,13 @@ int fused_v2_grid(const V2Plan &pl, int64_t B, int num_sms)
     return (int)std::min<int64_t>(g, B);
 }
 
-cudaError_t launch_fused_v2(const FusedArgs &a, const V2Plan &pl, char *scratch, int grid, cudaStream_t stream)
+cudaError_t launch_fused_v2(const FusedArgs &a, const V2Plan &pl, char *scratch, unsigned long long *work_counter,
+                            int grid, cudaStream_t stream)
 {
     V2Layout lay{};
+    lay.work_counter = work_counter;
+    cudaError_t e0 = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
+    if (e0 != cudaSuccess) return e0;
     lay.nt = pl.nt;
     for (int i = 0; i < 5; ++i) { lay.aux_off[i] = pl.aux_off[i]; lay.aux_smem[i] = pl.aux_smem[i]; }
     lay.scratch_stride = pl.scratch_stride;

@@ -56,7 +56,8 @@ struct V2Plan {
 int fused_v2_max_q();
 V2Plan plan_fused_v2(int q, int G, int ntheta_cap, int ntab_cap, int ncp_cap, int smem_optin, int smem_per_sm);
 int fused_v2_grid(const V2Plan &pl, int64_t B, int num_sms);
-cudaError_t launch_fused_v2(const FusedArgs &a, const V2Plan &pl, char *scratch, int grid, cudaStream_t stream);
+cudaError_t launch_fused_v2(const FusedArgs &a, const V2Plan &pl, char *scratch, unsigned long long *work_counter,
+                            int grid, cudaStream_t stream);
 
 // Scenario-shared fast path: per (scenario, particle) O(k^2 + hk) tail of the forward solve.
 struct AppendArgs {

@@ -42,6 +42,7 @@ struct TreeProgram {
     uint8_t cop[MAX_PROG];
     int16_t carg[MAX_PROG];
     int8_t caux[MAX_PROG];
+    uint32_t cword[MAX_PROG];   // cop | carg << 8 | caux << 24: one load per op in the hot interpreter
     int clen;
     // lag tables: slice [tab_src0, tab_src1) of the source program
     int ntab;
@@ -119,6 +120,8 @@ __host__ __device__ inline void tree_compile(TreeProgram &tp, const uint8_t *pro
     if (sp != 1 || th != ntheta || th > MAX_THETA) { tp.error = -3; return; }
     if (st[0].stat && seal(st[0], len)) nout = 1;
     tp.clen = nout;
+    for (int c = 0; c < nout; ++c)
+        tp.cword[c] = (uint32_t)tp.cop[c] | ((uint32_t)(uint16_t)tp.carg[c] << 8) | ((uint32_t)(uint8_t)tp.caux[c] << 24);
 }
 
 // Evaluate ops[0..len) for one pair. `lag` indexes the lag tables (ignored when there are none).
