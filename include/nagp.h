@@ -80,7 +80,9 @@ int32_t nagp_logml_batch(nagp_ctx *ctx, int64_t B,
  * space, (ya, yb) the scale map y_s = ya*y + yb used to un-scale predictions; noise_pred < 0
  * means "use each instance's own noise on the forecast block".
  * Outputs: logw[K*P] = logw0[p] + logML(m) - logML(n); mu[K*P*h]; L[K*P*h*h] (row-major lower
- * Cholesky factor of the predictive covariance, original units); info[K*P]. */
+ * Cholesky factor of the predictive covariance, original units); info[K*P]; logml_n / logml_m
+ * [K*P] (nullable) the two log marginal likelihoods themselves — what a Metropolis/HMC accept
+ * step on the per-scenario hyperparameters needs (mcmc_parameters!, forecasting.jl:148,65). */
 int32_t nagp_forecast_instances(nagp_ctx *ctx, int64_t K, int64_t P,
                                 const uint8_t *prog, const int64_t *prog_off,
                                 const double *theta, const int64_t *theta_off, int64_t theta_stride_k,
@@ -89,7 +91,8 @@ int32_t nagp_forecast_instances(nagp_ctx *ctx, int64_t K, int64_t P,
                                 const double *t, const int32_t *g, double step,
                                 const double *y1, const double *y2, double ya, double yb,
                                 const double *logw0,
-                                double *logw, double *mu, double *L, int32_t *info);
+                                double *logw, double *mu, double *L, int32_t *info,
+                                double *logml_n, double *logml_m);
 
 /* ---- (a3) factor store: Dict(model) / GPModel(dict) -------------------------------------------
  * Factor the P particles of a base model ONCE over [train | nowcast dates | forecast dates] and

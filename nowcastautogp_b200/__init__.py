@@ -1,0 +1,12 @@
+"""nowcastautogp_b200 — B200-native GP hot path behind NowcastAutoGP's public API.
+
+Exports mirror `/root/reference/src/NowcastAutoGP.jl:10-12`. Importing the package does not load
+the CUDA library; the first device call does, and raises if `libnagp.so` or a GPU is missing
+(there is no CPU fallback).
+"""
+from .tdata import TData, create_transformed_data, create_nowcast_data
+from .gpmodel import GPConfig, GPModel
+from .api import make_and_fit_model, forecast, forecast_with_nowcasts
+
+__all__ = ["TData", "GPModel", "GPConfig", "create_transformed_data", "make_and_fit_model", "forecast",
+           "forecast_with_nowcasts", "create_nowcast_data"]

@@ -25,7 +25,7 @@ SIGNATURES = {
     "nagp_logml_batch": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _f64, _vp, _i64, _vp, _vp]),
     "nagp_forecast_instances": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _f64,
                                        _i64, _i64, _i64, _vp, _vp, _f64, _vp, _vp, _f64, _f64, _vp,
-                                       _vp, _vp, _vp, _vp]),
+                                       _vp, _vp, _vp, _vp, _vp, _vp]),
     "nagp_factor_store": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _f64, _i64, _i64, _i64, _vp, _vp, _f64,
                                  _vp, _f64, _f64, _vp, C.POINTER(_vp), _vp, _vp]),
     "nagp_factor_free": (None, [_vp]),

@@ -1,0 +1,241 @@
+"""`make_and_fit_model`, `forecast`, `forecast_with_nowcasts` — the reference's public entry points,
+same names, keyword arguments, assertion behaviour and return shapes.
+
+Mirrors `/root/reference/src/make_and_fit_model.jl:17-27,78-93` and
+`/root/reference/src/forecasting.jl:29-75,117-167`. Where the reference spawns one task per nowcast
+scenario and rebuilds the particle ensemble inside each (`forecasting.jl:131-133`), this module
+issues ONE batched device call over all (scenario, particle) instances; kernel-structure and
+parameter proposals stay on the CPU, every likelihood / factorisation / moment / draw is in libnagp.
+Random numbers come from a NumPy `Generator` (the reference uses Julia's task-local Xoshiro), so
+outputs agree with the reference in distribution, not draw by draw.
+"""
+from __future__ import annotations
+
+import warnings
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+
+from .gpmodel import GPConfig, GPModel, pack_particles, slot_transform
+from .tdata import TData
+from . import kernels as kn
+
+
+def _identity(y):
+    return y
+
+
+def _stabilize_for_fit(y: np.ndarray, *, flat_threshold: float = 1e-3, rng=None) -> np.ndarray:
+    """Jitter guard for near-constant series (`src/make_and_fit_model.jl:17-27`)."""
+    y = np.asarray(y, np.float64)
+    n = len(y)
+    if n <= 1:
+        return y
+    scale = abs(y.sum() / n) + 1
+    rel_range = (y.max() - y.min()) / scale
+    if rel_range >= flat_threshold:
+        return y
+    sigma = flat_threshold * scale
+    warnings.warn(f"Near-constant series (relative range {rel_range} < {flat_threshold}); adding jitter "
+                  f"(sigma = {sigma}) so the GP covariance stays positive-definite (issue #51).")
+    rng = np.random.default_rng() if rng is None else rng
+    return y + sigma * rng.standard_normal(n)
+
+
+def linear_schedule(n: int, proportion: float) -> List[int]:
+    """`AutoGP.Schedule.linear_schedule` [R]: cumulative counts step, 2·step, …, with n appended."""
+    step = max(1, int(round(proportion * n)))
+    sched = list(range(step, n + 1, step))
+    if not sched or sched[-1] != n:
+        sched.append(n)
+    return sched
+
+
+def make_and_fit_model(data: TData, *, n_particles: int = 1, smc_data_proportion: float = 0.1,
+                       flat_threshold: float = 1e-3, config: Optional[GPConfig] = None, rng=None,
+                       engine=None, **kwargs) -> GPModel:
+    """`src/make_and_fit_model.jl:78-93`. `kwargs` go to `fit_smc` (`n_mcmc`, `n_hmc` required)."""
+    if "n_mcmc" not in kwargs or "n_hmc" not in kwargs:
+        raise TypeError("make_and_fit_model: keyword arguments n_mcmc and n_hmc are required")  # UndefKeywordError
+    rng = np.random.default_rng() if rng is None else rng
+    n_train = len(data.y)
+    y_fit = _stabilize_for_fit(data.y, flat_threshold=flat_threshold, rng=rng)
+    model = GPModel(data.ds, y_fit, n_particles=n_particles, config=GPConfig() if config is None else config,
+                    rng=rng, engine=engine)
+    effective_proportion = max(smc_data_proportion, 1.0 / n_train)
+    model.fit_smc(schedule=linear_schedule(n_train, effective_proportion), **kwargs)
+    return model
+
+
+def _apply(inv_transformation: Callable, x: np.ndarray) -> np.ndarray:
+    if inv_transformation is _identity:
+        return x
+    try:
+        out = inv_transformation(x)                 # vectorised closures (np.exp, scaled logistic …)
+        if isinstance(out, np.ndarray) and out.shape == x.shape:
+            return out
+    except Exception:
+        pass
+    return np.vectorize(inv_transformation, otypes=[np.float64])(x)
+
+
+def forecast(model: GPModel, forecast_dates, forecast_draws: int, *, inv_transformation: Callable = _identity,
+             forecast_n_hmc: Optional[int] = None) -> np.ndarray:
+    """`src/forecasting.jl:29-75`: `(len(forecast_dates), forecast_draws)` samples."""
+    dates = np.asarray(list(forecast_dates) if not isinstance(forecast_dates, np.ndarray) else forecast_dates)
+    if forecast_n_hmc is None:
+        x = model.predict_mvn(dates).rand(forecast_draws, rng=model.rng)
+    else:
+        x = np.empty((len(dates), forecast_draws))
+        for i in range(forecast_draws):
+            model.mcmc_parameters(forecast_n_hmc)
+            x[:, i] = model.predict_mvn(dates).rand(rng=model.rng)
+    return _apply(inv_transformation, np.ascontiguousarray(x))
+
+
+class _ScenarioParams:
+    """Per-(scenario, particle) unconstrained hyperparameters of K copies of one particle set, moved
+    by batched Metropolis steps: one `nagp_forecast_instances` call scores all K·P proposals."""
+
+    def __init__(self, model: GPModel, K: int):
+        self.m = model
+        self.K, self.P = K, model.num_particles()
+        self.prog_all = b"".join(p.prog for p in model.particles)
+        self.names = kn.theta_slot_names(self.prog_all)
+        self.z = np.tile(np.concatenate([p.z for p in model.particles]), (K, 1))
+        self.noise_z = np.tile(np.array([p.noise_z for p in model.particles]), (K, 1))
+        self.ens = pack_particles(model.particles, model.config)
+        # particle owning each theta slot (for the per-particle prior term)
+        self.owner = np.repeat(np.arange(self.P), np.diff(self.ens.theta_off))
+
+    def theta(self, z, noise_z):
+        cfg = self.m.config
+        th = np.empty_like(z)
+        for j, nm in enumerate(self.names):
+            th[:, j] = [slot_transform(nm, v, cfg) for v in z[:, j]]
+        if cfg.noise is not None:
+            nz = np.full(noise_z.shape, float(cfg.noise))
+        else:
+            nz = np.vectorize(lambda v: slot_transform("noise", v, cfg))(noise_z)
+        return np.ascontiguousarray(th), np.ascontiguousarray(nz)
+
+    def log_prior(self, z, noise_z):
+        lp = np.zeros((self.K, self.P))
+        np.add.at(lp.T, self.owner, -0.5 * (z * z).T)
+        return lp - 0.5 * noise_z * noise_z
+
+
+def forecast_with_nowcasts(base_model: GPModel, nowcasts: Sequence[TData], forecast_dates,
+                           forecast_draws_per_nowcast: int, *, inv_transformation: Callable = _identity,
+                           n_mcmc: int = 0, n_hmc: int = 0, ess_threshold: float = 0.0,
+                           forecast_n_hmc: Optional[int] = None, verbose: bool = False, rng=None) -> np.ndarray:
+    """`src/forecasting.jl:117-167`: matrix `(len(forecast_dates), len(nowcasts)·D)`, scenario-major
+    column blocks. The base model is not mutated."""
+    assert len(nowcasts) > 0, "nowcasts vector must not be empty"
+    assert not (n_mcmc > 0 and n_hmc == 0), "If n_mcmc > 0, n_hmc must also be > 0 for MCMC refinement"
+    assert 0.0 <= ess_threshold <= 1.0, "ess_threshold must be between 0 and 1"
+    assert forecast_n_hmc is None or forecast_n_hmc > 0, "forecast_n_hmc must be > 0 if specified"
+    rng = base_model.rng if rng is None else rng
+    D = int(forecast_draws_per_nowcast)
+    dates = np.asarray(list(forecast_dates) if not isinstance(forecast_dates, np.ndarray) else forecast_dates)
+    base_dict = base_model.to_dict()                                   # forecasting.jl:128
+    ds0 = np.asarray(nowcasts[0].ds)
+    shared_ds = all(len(nc.ds) == len(ds0) and np.array_equal(np.asarray(nc.ds), ds0) for nc in nowcasts)
+
+    if n_mcmc > 0 or not shared_ds:
+        # structure moves make the programs diverge per scenario: the reference's schedule verbatim,
+        # one model copy per scenario (forecasting.jl:133-155); every likelihood is still a device call
+        blocks = []
+        for nc in nowcasts:
+            m = GPModel.from_dict(base_dict, engine=base_model.engine, rng=rng)
+            m.add_data(nc.ds, nc.y)
+            m.maybe_resample(ess_threshold * m.num_particles())
+            if n_mcmc > 0 and n_hmc > 0:
+                m.mcmc_structure(n_mcmc, n_hmc)
+            elif n_hmc > 0:
+                m.mcmc_parameters(n_hmc)
+            blocks.append(forecast(m, dates, D, forecast_n_hmc=forecast_n_hmc))
+        return _apply(inv_transformation, np.hstack(blocks))
+
+    m = GPModel.from_dict(base_dict, engine=base_model.engine, rng=rng)
+    eng = m._engine()
+    K, P, n, k, h = len(nowcasts), m.num_particles(), len(m.y), len(ds0), len(dates)
+    idx = m._obs_idx()
+    t, g, step = m._times(np.concatenate([m.ds[idx], ds0.astype(m.ds.dtype), dates.astype(m.ds.dtype)]))
+    yt = m.y_transform
+    y1 = yt.apply(m.y[idx])
+    y2 = np.ascontiguousarray(np.stack([yt.apply(np.asarray(nc.y, np.float64)) for nc in nowcasts]))
+    ens = m.ensemble()
+
+    if n_hmc == 0 and forecast_n_hmc is None:
+        # default path: factor once per particle, append K scenarios, ESS/resample, draw — one call
+        zeta = rng.standard_normal((K, D, h))
+        u = rng.uniform(size=(K, D))
+        u_res = rng.uniform(size=(K, P)) if ess_threshold > 0.0 else None
+        x = eng.forecast_with_nowcasts(ens, n, k, h, t, y1, y2, m.log_weights, zeta, yt.slope, yt.intercept,
+                                       g=g, step=step, u=u, u_res=u_res, ess_thr=ess_threshold)
+        return _apply(inv_transformation, np.ascontiguousarray(x))
+
+    # per-scenario parameter rejuvenation: all K·P chains advance together
+    sp = _ScenarioParams(m, K)
+    th, nz = sp.theta(sp.z, sp.noise_z)
+
+    def score(th_, nz_, moments):
+        lm_m = np.empty((K, P))
+        r = eng.forecast_instances(ens, n, k, h, t, y1, y2, m.log_weights, yt.slope, yt.intercept, g=g,
+                                   step=step, theta=th_, noise=nz_, K=K, logml_m=lm_m, want_moments=moments)
+        lm_m = np.where(r["info"] == 0, lm_m, -np.inf)
+        return r, lm_m
+
+    r, lm = score(th, nz, False)
+    logw = r["logw"].copy()                                            # add_data!: forecasting.jl:135
+    if not np.all(np.isfinite(lm)):
+        from .engine import PosDefError
+        raise PosDefError(1)
+    # maybe_resample! per scenario (forecasting.jl:138-141)
+    ess, w = eng.ess(logw)
+    for s in np.nonzero(ess < ess_threshold * P)[0]:
+        parents = rng.choice(P, size=P, p=w[s])
+        off = ens.theta_off
+        sp.z[s] = np.concatenate([sp.z[s, off[a]:off[a + 1]] for a in parents]) \
+            if len({off[a + 1] - off[a] for a in range(P)}) == 1 else sp.z[s]
+        if len({off[a + 1] - off[a] for a in range(P)}) == 1:
+            sp.noise_z[s] = sp.noise_z[s, parents]
+            lm[s] = lm[s, parents]
+            logw[s] = 0.0
+    # NOTE: resampling swaps whole particles; with heterogeneous programs the parents' structures
+    # differ, which the shared-program batch cannot express — such scenarios keep their weights
+    # (weighted mixture, statistically equivalent for the forecast).
+
+    def metropolis(n_steps, step_size=0.15):
+        nonlocal lm
+        for _ in range(n_steps):
+            zp = sp.z + step_size * rng.standard_normal(sp.z.shape)
+            nzp = sp.noise_z + (step_size * rng.standard_normal(sp.noise_z.shape) if m.config.noise is None else 0.0)
+            thp, nzv = sp.theta(zp, nzp)
+            _, lmp = score(thp, nzv, False)
+            acc = np.log(rng.uniform(size=(K, P))) < (lmp - lm) + sp.log_prior(zp, nzp) - sp.log_prior(sp.z, sp.noise_z)
+            slot_acc = acc[:, sp.owner]
+            sp.z = np.where(slot_acc, zp, sp.z)
+            sp.noise_z = np.where(acc, nzp, sp.noise_z)
+            lm = np.where(acc, lmp, lm)
+
+    if n_hmc > 0:
+        metropolis(n_hmc)                                              # mcmc_parameters!: forecasting.jl:148
+
+    def draw_block(Dn):
+        th_, nz_ = sp.theta(sp.z, sp.noise_z)
+        r_, _ = score(th_, nz_, True)
+        zeta = rng.standard_normal((K, Dn, h))
+        u = rng.uniform(size=(K, Dn))
+        x_, _, _ = eng.draw(logw, r_["mu"], r_["L"], zeta, u=u)
+        return np.ascontiguousarray(x_)                                # [h, K*Dn]
+
+    if forecast_n_hmc is None:
+        x = draw_block(D)
+    else:
+        x = np.empty((h, K * D))
+        for i in range(D):                                             # forecasting.jl:63-68
+            metropolis(forecast_n_hmc)
+            x[:, i::D] = draw_block(1)
+    return _apply(inv_transformation, x)

@@ -376,7 +376,7 @@ int32_t nagp_forecast_instances(nagp_ctx *ctx, int64_t K, int64_t P, const uint8
                                 double noise_pred, int64_t n, int64_t k, int64_t h, const double *t,
                                 const int32_t *g, double step, const double *y1, const double *y2,
                                 double ya, double yb, const double *logw0, double *logw, double *mu,
-                                double *L, int32_t *info)
+                                double *L, int32_t *info, double *logml_n, double *logml_m)
 {
     if (!ctx) return NAGP_E_ARG;
     if (K <= 0 || P <= 0 || !prog || !prog_off || !theta || !theta_off || !noise || !t || !y1 || !info ||
@@ -413,6 +413,8 @@ int32_t nagp_forecast_instances(nagp_ctx *ctx, int64_t K, int64_t P, const uint8
     NAGP_TRY(stage_out(ctx, mu, (size_t)(B * h), &a.mu));
     NAGP_TRY(stage_out(ctx, L, (size_t)(B * h * h), &a.L33));
     NAGP_TRY(stage_out(ctx, info, (size_t)B, &a.info));
+    NAGP_TRY(stage_out(ctx, logml_n, (size_t)B, &a.logml_n));
+    NAGP_TRY(stage_out(ctx, logml_m, (size_t)B, &a.logml_m));
     const bool host_info = !on_device(info);
     NAGP_TRY(run_fused(ctx, a, theta_off));
     NAGP_TRY(finish(ctx));

@@ -110,27 +110,29 @@ class Engine:
     # ---- general per-(scenario, particle) path -----------------------------------------------------
     def forecast_instances(self, ens: FlatEnsemble, n, k, h, t, y1, y2, logw0, ya=1.0, yb=0.0, g=None,
                            step=0.0, noise_pred=-1.0, theta=None, noise=None, K=None,
-                           logw=None, mu=None, L=None, info=None, check: bool = False):
+                           logw=None, mu=None, L=None, info=None, check: bool = False,
+                           logml_n=None, logml_m=None, want_moments: bool = True):
         """`theta` [K,total] / `noise` [K,P] switch on per-scenario hyperparameters."""
         P = ens.size
         if K is None:
             K = y2.shape[0]
         logw = np.empty((K, P)) if logw is None else logw
-        mu = np.empty((K, P, h)) if mu is None else mu
-        L = np.empty((K, P, h, h)) if L is None else L
+        if want_moments:
+            mu = np.empty((K, P, h)) if mu is None else mu
+            L = np.empty((K, P, h, h)) if L is None else L
         info = np.zeros((K, P), np.int32) if info is None else info
         th = ens.theta if theta is None else theta
         nz = ens.noise if noise is None else noise
         keep = [_ptr(ens.prog), _ptr(ens.prog_off), _ptr(th), _ptr(ens.theta_off), _ptr(nz),
                 _ptr(t, np.float64), _ptr(g, np.int32), _ptr(y1, np.float64), _ptr(y2, np.float64),
-                _ptr(logw0, np.float64), _ptr(logw), _ptr(mu), _ptr(L), _ptr(info)]
+                _ptr(logw0, np.float64), _ptr(logw), _ptr(mu), _ptr(L), _ptr(info), _ptr(logml_n), _ptr(logml_m)]
         p = [x[0] for x in keep]
         rc = self._lib.nagp_forecast_instances(
             self._ctx, K, P, p[0], p[1], p[2], p[3], 0 if theta is None else int(ens.theta_off[-1]),
             p[4], 0 if noise is None else P, noise_pred, n, k, h, p[5], p[6], step, p[7], p[8], ya, yb,
-            p[9], p[10], p[11], p[12], p[13])
+            p[9], p[10], p[11], p[12], p[13], p[14], p[15])
         self._check(rc, raise_posdef=check)
-        return dict(logw=logw, mu=mu, L=L, info=info)
+        return dict(logw=logw, mu=mu, L=L, info=info, logml_n=logml_n, logml_m=logml_m)
 
     # ---- (a3)/(a4)/(a7) ----------------------------------------------------------------------------
     def factor_store(self, ens: FlatEnsemble, n, k, h, t, y1, logw0=None, ya=1.0, yb=0.0, g=None, step=0.0,

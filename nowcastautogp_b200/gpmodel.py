@@ -1,0 +1,451 @@
+"""`GPConfig` and `GPModel`: the particle-ensemble state the reference keeps inside `AutoGP.GPModel`.
+
+The reference re-exports `AutoGP.GPModel` / `AutoGP.GP.GPConfig` (`/root/reference/src/NowcastAutoGP.jl:8-9`)
+and drives it through 13 calls. This module is the host-side mirror of that object:
+explicit arrays (kernel programs, unconstrained hyperparameters, noise, log-weights, time/target
+transforms) instead of Gen traces, with the same method names as the AutoGP calls the reference
+makes — `add_data`, `maybe_resample`, `mcmc_structure`, `mcmc_parameters`, `predict_mvn`,
+`num_particles`, `to_dict` / `from_dict` (`Dict(model)` / `GPModel(dict)`). Kernel-structure and
+parameter proposals stay on the CPU (BASELINE.json north_star); every likelihood, factorisation
+and predictive moment is a batched call into libnagp.
+
+[R] marks semantics recalled from AutoGP.jl that cannot be checked in this image (docs/KERNEL_SPEC.md).
+"""
+from __future__ import annotations
+
+import copy
+from dataclasses import dataclass, field
+from functools import reduce
+from math import gcd
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import kernels as kn
+from .engine import Engine, PosDefError
+
+_DEFAULT_ENGINES: Dict[int, Engine] = {}
+
+
+def default_engine(device: int = 0) -> Engine:
+    """Process-wide engine for `device` (created on first use; raises without a GPU)."""
+    if device not in _DEFAULT_ENGINES:
+        _DEFAULT_ENGINES[device] = Engine(device)
+    return _DEFAULT_ENGINES[device]
+
+
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class GPConfig:
+    """Mirror of `AutoGP.GP.GPConfig` (fields and defaults as dumped at
+    `/root/reference/docs/src/vignettes/setting-priors.md:228-245`)."""
+    node_dist_leaf: Sequence[float] = (0.0, 1 / 3, 0.0, 1 / 3, 1 / 3)
+    node_dist_nocp: Sequence[float] = tuple(np.array([0, 6, 0, 6, 6, 5, 5], float) / 28)
+    node_dist_cp: Sequence[float] = tuple(np.array([0, 6, 0, 6, 6, 4, 4, 2], float) / 28)
+    max_branch: int = 2
+    max_depth: int = -1
+    changepoints: bool = True
+    noise: Optional[float] = None
+    prior: dict = field(default_factory=lambda: {
+        "gamma": {"mu": 0.0, "sigma": 1.0},        # gamma = 2 logistic(mu + sigma z) [R]
+        "period": {"mu": -1.5, "sigma": 1.0},      # LogNormal [C: setting-priors.md:106-116]
+        "wildcard": {"mu": -1.5, "sigma": 1.0},    # LogNormal for every other positive parameter [R]
+    })
+    cp_scale: float = 1e-3                          # fixed ChangePoint sharpness [R]
+    # depth cap used when max_depth == -1 so that programs respect the wire-format limits
+    hard_max_depth: int = 5
+
+    Constant, Linear, SquaredExponential, GammaExponential, Periodic, Plus, Times, ChangePoint = range(1, 9)
+
+
+@dataclass
+class LinearTransform:
+    """`x -> slope * x + intercept`; `fit` maps [min, max] of the data onto [lo, hi] [R]."""
+    slope: float
+    intercept: float
+
+    @classmethod
+    def fit(cls, x: np.ndarray, lo: float, hi: float) -> "LinearTransform":
+        xmin, xmax = float(np.min(x)), float(np.max(x))
+        if not xmax > xmin:
+            # AutoGP divides by the range: a flat series gives a singular covariance (issue #51,
+            # `/root/reference/src/make_and_fit_model.jl:6-8`)
+            raise PosDefError(1)
+        slope = (hi - lo) / (xmax - xmin)
+        return cls(slope, lo - slope * xmin)
+
+    def apply(self, x):
+        return self.slope * np.asarray(x, np.float64) + self.intercept
+
+    def unapply(self, x):
+        return (np.asarray(x, np.float64) - self.intercept) / self.slope
+
+
+def to_numeric(ds) -> np.ndarray:
+    """Dates → float days (AutoGP uses Unix seconds [R]; the unit cancels in the [0,1] rescaling)."""
+    arr = np.asarray(ds)
+    if arr.dtype.kind == "M":
+        return arr.astype("datetime64[D]").astype(np.int64).astype(np.float64)
+    return arr.astype(np.float64)
+
+
+def lag_grid(num: np.ndarray) -> Tuple[Optional[np.ndarray], float]:
+    """Integer grid indices and grid step (in `num` units) when every time point is an integer
+    multiple of a common step from the first point; (None, 0.0) otherwise."""
+    if len(num) < 2 or not np.all(np.equal(np.mod(num, 1), 0)):
+        return None, 0.0
+    d = (num - num.min()).astype(np.int64)
+    step = reduce(gcd, [int(v) for v in d if v > 0], 0)
+    if step == 0:
+        return None, 0.0
+    g = d // step
+    if g.max() > 8 * len(num) + 64:     # a table this sparse costs more than pairwise evaluation
+        return None, 0.0
+    return g.astype(np.int32), float(step)
+
+
+# ------------------------------------------------------------------------------------------------
+# hyperparameters live as standard-normal z; theta = transform(z)  [R]
+def _logistic(x):
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+def _norm_cdf(x):
+    from math import erf, sqrt
+    return 0.5 * (1.0 + erf(x / sqrt(2.0)))
+
+
+def slot_transform(name: str, z: float, config: GPConfig) -> float:
+    pr = config.prior
+    if name == "period":
+        return float(np.exp(pr["period"]["mu"] + pr["period"]["sigma"] * z))
+    if name == "gamma":
+        return float(2.0 * _logistic(pr["gamma"]["mu"] + pr["gamma"]["sigma"] * z))
+    if name == "intercept":
+        return float(z)
+    if name == "location":
+        return float(_norm_cdf(z))
+    if name == "scale":
+        return float(config.cp_scale)
+    return float(np.exp(pr["wildcard"]["mu"] + pr["wildcard"]["sigma"] * z))
+
+
+@dataclass
+class Particle:
+    """One SMC particle: kernel structure + unconstrained hyperparameters."""
+    prog: bytes
+    z: np.ndarray          # one entry per theta slot
+    noise_z: float
+
+    def theta(self, config: GPConfig) -> List[float]:
+        names = kn.theta_slot_names(self.prog)
+        return [slot_transform(nm, zz, config) for nm, zz in zip(names, self.z)]
+
+    def noise(self, config: GPConfig) -> float:
+        if config.noise is not None:
+            return float(config.noise)
+        return slot_transform("noise", self.noise_z, config)
+
+    def copy(self) -> "Particle":
+        return Particle(self.prog, self.z.copy(), float(self.noise_z))
+
+    @property
+    def n_nodes(self) -> int:
+        return len(self.prog)
+
+
+def sample_structure(rng, config: GPConfig, depth: int = 1) -> List[int]:
+    """Post-order opcode list drawn from the PCFG prior (`node_dist_*`)."""
+    max_depth = config.max_depth if config.max_depth > 0 else config.hard_max_depth
+    if depth >= max_depth:
+        probs = np.asarray(config.node_dist_leaf, float)
+        return [1 + int(rng.choice(len(probs), p=probs / probs.sum()))]
+    probs = np.asarray(config.node_dist_cp if config.changepoints else config.node_dist_nocp, float)
+    code = 1 + int(rng.choice(len(probs), p=probs / probs.sum()))
+    if code <= kn.OP_PERIODIC:
+        return [code]
+    return sample_structure(rng, config, depth + 1) + sample_structure(rng, config, depth + 1) + [code]
+
+
+def sample_particle(rng, config: GPConfig) -> Particle:
+    while True:
+        prog = bytes(sample_structure(rng, config))
+        if len(prog) <= kn.MAX_PROG:
+            break
+    nslots = len(kn.theta_slot_names(prog))
+    return Particle(prog, rng.standard_normal(nslots), float(rng.standard_normal()))
+
+
+def subtree_slices(prog: bytes) -> List[Tuple[int, int]]:
+    """(start, end) of the sub-tree rooted at every node of a post-order program."""
+    out, stack = [], []
+    for i, op in enumerate(prog):
+        if op <= kn.OP_PERIODIC:
+            stack.append(i)
+        else:
+            stack.pop()
+            start = stack.pop()
+            stack.append(start)
+        out.append((stack[-1], i + 1))
+    return out
+
+
+def pack_particles(particles: Sequence[Particle], config: GPConfig) -> kn.FlatEnsemble:
+    progs = [p.prog for p in particles]
+    thetas = [p.theta(config) for p in particles]
+    prog_off = np.zeros(len(progs) + 1, np.int64)
+    theta_off = np.zeros(len(progs) + 1, np.int64)
+    np.cumsum([len(p) for p in progs], out=prog_off[1:])
+    np.cumsum([len(t) for t in thetas], out=theta_off[1:])
+    return kn.FlatEnsemble(np.frombuffer(b"".join(progs), np.uint8).copy(), prog_off,
+                           np.asarray([x for t in thetas for x in t], np.float64), theta_off,
+                           np.asarray([p.noise(config) for p in particles], np.float64))
+
+
+# ------------------------------------------------------------------------------------------------
+class MixtureMVN:
+    """What `AutoGP.predict_mvn` returns (`MixtureModel{MvNormal}`): per-particle mean and Cholesky
+    factor in original units plus normalised weights. `rand` = `rand(dist, n)` / `rand(dist)`
+    (`/root/reference/src/forecasting.jl:47,67`), drawn on the device from host-supplied normals."""
+
+    def __init__(self, engine: Engine, logw: np.ndarray, mu: np.ndarray, L: np.ndarray):
+        self.engine, self.logw, self.mu, self.L = engine, logw, mu, L
+
+    @property
+    def weights(self) -> np.ndarray:
+        w = np.exp(self.logw - self.logw.max())
+        return w / w.sum()
+
+    def rand(self, n: Optional[int] = None, rng=None) -> np.ndarray:
+        rng = np.random.default_rng() if rng is None else rng
+        D = 1 if n is None else int(n)
+        h = self.mu.shape[-1]
+        zeta = rng.standard_normal((1, D, h))
+        u = rng.uniform(size=(1, D))
+        x, _, _ = self.engine.draw(self.logw[None, :], self.mu[None], self.L[None], zeta, u=u)
+        x = np.ascontiguousarray(x)
+        return x[:, 0] if n is None else x
+
+
+class GPModel:
+    """Host mirror of `AutoGP.GPModel(ds, y; n_particles, config)` (`src/make_and_fit_model.jl:84`)."""
+
+    def __init__(self, ds, y, *, n_particles: int = 8, config: Optional[GPConfig] = None, rng=None,
+                 engine: Optional[Engine] = None, _state: Optional[dict] = None):
+        self.engine = engine
+        if _state is not None:
+            self.__dict__.update(_state)
+            return
+        self.config = GPConfig() if config is None else config
+        self.rng = np.random.default_rng() if rng is None else rng
+        self.ds = np.asarray(ds)
+        self.y = np.asarray(y, np.float64)
+        assert len(self.ds) == len(self.y)
+        num = to_numeric(self.ds)
+        self.ds_transform = LinearTransform.fit(num, 0.0, 1.0)        # [C] time window → [0,1]
+        self.y_transform = LinearTransform.fit(self.y, -1.0, 1.0)     # [R] target range → [-1,1]
+        self.particles = [sample_particle(self.rng, self.config) for _ in range(n_particles)]
+        self.log_weights = np.zeros(n_particles)
+        self.n_obs = 0                      # observations already absorbed into the weights (SMC)
+        self.obs_order = np.arange(len(self.y))
+        self._logml = np.zeros(n_particles)  # log marginal likelihood of the first n_obs observations
+
+    # ---- plumbing --------------------------------------------------------------------------------
+    def _engine(self) -> Engine:
+        if self.engine is None:
+            self.engine = default_engine()
+        return self.engine
+
+    def num_particles(self) -> int:
+        return len(self.particles)
+
+    def _times(self, ds_all) -> Tuple[np.ndarray, Optional[np.ndarray], float]:
+        num = to_numeric(ds_all)
+        g, step = lag_grid(num)
+        return self.ds_transform.apply(num), g, step * self.ds_transform.slope
+
+    def ensemble(self) -> kn.FlatEnsemble:
+        return pack_particles(self.particles, self.config)
+
+    def kernels(self) -> List[kn.Node]:
+        """The particles' kernels as DSL trees (AutoGP: `covariance_kernels(model)`)."""
+        return [kn.unflatten(p.prog, p.theta(self.config)) for p in self.particles]
+
+    # ---- Dict(model) / GPModel(dict): src/forecasting.jl:128,133 -------------------------------------
+    def to_dict(self) -> dict:
+        return {
+            "ds": self.ds.astype(str).tolist() if self.ds.dtype.kind == "M" else self.ds.tolist(),
+            "ds_is_date": self.ds.dtype.kind == "M",
+            "y": self.y.tolist(),
+            "ds_transform": [self.ds_transform.slope, self.ds_transform.intercept],
+            "y_transform": [self.y_transform.slope, self.y_transform.intercept],
+            "config": copy.deepcopy(self.config.__dict__),
+            "particles": [{"prog": list(p.prog), "z": p.z.tolist(), "noise_z": p.noise_z} for p in self.particles],
+            "log_weights": self.log_weights.tolist(),
+            "n_obs": int(self.n_obs),
+            "obs_order": self.obs_order.tolist(),
+            "logml": self._logml.tolist(),
+        }
+
+    @classmethod
+    def from_dict(cls, d: dict, *, engine: Optional[Engine] = None, rng=None) -> "GPModel":
+        d = copy.deepcopy(d)
+        ds = np.asarray(d["ds"], "datetime64[D]") if d.get("ds_is_date") else np.asarray(d["ds"])
+        state = dict(
+            config=GPConfig(**d["config"]), rng=np.random.default_rng() if rng is None else rng,
+            ds=ds, y=np.asarray(d["y"], np.float64),
+            ds_transform=LinearTransform(*d["ds_transform"]), y_transform=LinearTransform(*d["y_transform"]),
+            particles=[Particle(bytes(p["prog"]), np.asarray(p["z"], np.float64), float(p["noise_z"]))
+                       for p in d["particles"]],
+            log_weights=np.asarray(d["log_weights"], np.float64), n_obs=int(d["n_obs"]),
+            obs_order=np.asarray(d["obs_order"], np.int64), _logml=np.asarray(d["logml"], np.float64))
+        return cls(None, None, engine=engine, _state=state)
+
+    # ---- batched likelihood: the primitive fit_smc! and the MCMC moves call ---------------------------
+    def logml(self, particles: Sequence[Particle], idx: np.ndarray) -> np.ndarray:
+        """log p(y[idx] | particle) for every particle in one device call; -inf where the Gram is
+        not positive definite."""
+        if len(idx) == 0:
+            return np.zeros(len(particles))
+        t, g, step = self._times(self.ds[idx])
+        ens = pack_particles(particles, self.config)
+        lm, info = self._engine().logml_batch(ens, t, self.y_transform.apply(self.y[idx]), g=g, step=step)
+        return np.where(info == 0, lm, -np.inf)
+
+    # ---- AutoGP.fit_smc!: src/make_and_fit_model.jl:91 --------------------------------------------------
+    def fit_smc(self, *, schedule: Sequence[int], n_mcmc: int, n_hmc: int, shuffle: bool = True,
+                biased: bool = False, adaptive_rejuvenation: bool = False, hmc_config=None,
+                verbose: bool = False, ess_fraction: float = 0.5) -> None:
+        """Data-annealed SMC [R]: for each cumulative count in `schedule` absorb the next batch of
+        observations (one batched device logML call for all particles), resample when the ESS
+        drops below `ess_fraction`·P (AutoGP's adaptive default, `docs/vignettes/setting-priors.jl:
+        174-175`), then rejuvenate with `n_mcmc` structure moves × `n_hmc` parameter steps.
+        `n_mcmc` and `n_hmc` are required keywords, as in AutoGP (`test/test_gpconfig.jl:37-43`)."""
+        n = len(self.y)
+        self.obs_order = self.rng.permutation(n) if shuffle else np.arange(n)
+        for step in schedule:
+            step = int(min(step, n))
+            idx = np.sort(self.obs_order[:step])
+            new = self.logml(self.particles, idx)
+            if not np.any(np.isfinite(new)):
+                raise PosDefError(1)
+            with np.errstate(invalid="ignore"):
+                self.log_weights = self.log_weights + np.where(np.isfinite(self._logml), new - self._logml, 0.0)
+            self._logml = new
+            self.n_obs = step
+            resampled = self.maybe_resample(ess_fraction * self.num_particles())
+            if not adaptive_rejuvenation or resampled:
+                self.mcmc_structure(n_mcmc, n_hmc)
+            if verbose:
+                print(f"fit_smc: {step}/{n} observations, ESS {self.effective_sample_size():.2f}")
+
+    # ---- AutoGP.add_data!: src/forecasting.jl:135 -----------------------------------------------------
+    def add_data(self, ds, y) -> None:
+        ds, y = np.asarray(ds), np.asarray(y, np.float64)
+        assert len(ds) == len(y)
+        assert self.n_obs == len(self.y), "add_data! on a model that has not absorbed its own data"
+        old = self._logml
+        self.ds = np.concatenate([self.ds, ds.astype(self.ds.dtype)])
+        self.y = np.concatenate([self.y, y])
+        self.obs_order = np.concatenate([self.obs_order, np.arange(self.n_obs, len(self.y))])
+        new = self.logml(self.particles, np.arange(len(self.y)))
+        if not np.all(np.isfinite(new)):
+            raise PosDefError(1)
+        self.log_weights = self.log_weights + (new - old)     # log w += logML(m) - logML(n) [R]
+        self._logml = new
+        self.n_obs = len(self.y)
+
+    # ---- AutoGP.maybe_resample!: src/forecasting.jl:138-141 ---------------------------------------------
+    def effective_sample_size(self) -> float:
+        ess, _ = self._engine().ess(self.log_weights[None, :])
+        return float(ess[0])
+
+    def maybe_resample(self, ess_threshold: float) -> bool:
+        if not self.effective_sample_size() < ess_threshold:
+            return False
+        w = np.exp(self.log_weights - self.log_weights.max())
+        parents = self.rng.choice(len(w), size=len(w), p=w / w.sum())   # multinomial [R]
+        self.particles = [self.particles[a].copy() for a in parents]
+        self._logml = self._logml[parents]
+        self.log_weights = np.zeros(len(w))
+        return True
+
+    # ---- rejuvenation moves (proposals on the CPU, likelihoods batched on the device) -------------------
+    def _obs_idx(self) -> np.ndarray:
+        return np.sort(self.obs_order[:self.n_obs])
+
+    def mcmc_parameters(self, n_hmc: int, step_size: float = 0.15) -> float:
+        """`AutoGP.mcmc_parameters!(model, n_hmc)` (`src/forecasting.jl:148,65`). Round-1 stand-in for
+        HMC: `n_hmc` Gaussian random-walk Metropolis steps on all unconstrained hyperparameters of
+        every particle at once (N(0,1) prior on z [R]); SURVEY §8 f1 replaces it with gradient HMC.
+        Returns the acceptance rate."""
+        idx = self._obs_idx()
+        P = len(self.particles)
+        acc = 0
+        for _ in range(n_hmc):
+            props = []
+            for p in self.particles:
+                q = p.copy()
+                q.z = p.z + step_size * self.rng.standard_normal(len(p.z))
+                if self.config.noise is None:
+                    q.noise_z = p.noise_z + step_size * self.rng.standard_normal()
+                props.append(q)
+            lm_new = self.logml(props, idx)
+            for i, (p, q) in enumerate(zip(self.particles, props)):
+                lp = -0.5 * (q.z @ q.z + q.noise_z ** 2) + 0.5 * (p.z @ p.z + p.noise_z ** 2)
+                if np.log(self.rng.uniform()) < lm_new[i] - self._logml[i] + lp:
+                    self.particles[i] = q
+                    self._logml[i] = lm_new[i]
+                    acc += 1
+        return acc / max(1, n_hmc * P)
+
+    def mcmc_structure(self, n_mcmc: int, n_hmc: int) -> float:
+        """`AutoGP.mcmc_structure!(model, n_mcmc, n_hmc)` (`src/forecasting.jl:146`): `n_mcmc` rounds of
+        a sub-tree regeneration Metropolis move (replace a uniformly chosen sub-tree by a fresh prior
+        draw; the prior terms cancel, leaving the likelihood ratio times the node-count ratio), each
+        followed by `n_hmc` parameter steps. AutoGP's own involutive move set differs in detail [R];
+        like it, the proposals run on the CPU and only the likelihoods go to the device."""
+        idx = self._obs_idx()
+        acc = 0
+        for _ in range(n_mcmc):
+            props = []
+            for p in self.particles:
+                slices = subtree_slices(p.prog)
+                node = int(self.rng.integers(len(slices)))
+                s0, s1 = slices[node]
+                names = kn.theta_slot_names(p.prog)
+                z0 = len(kn.theta_slot_names(p.prog[:s0]))
+                z1 = len(kn.theta_slot_names(p.prog[:s1]))
+                depth = 1 + sum(1 for (a, b) in slices if a <= s0 and b >= s1 and (a, b) != (s0, s1))
+                sub = bytes(sample_structure(self.rng, self.config, depth))
+                prog = p.prog[:s0] + sub + p.prog[s1:]
+                if len(prog) > kn.MAX_PROG:
+                    props.append(p.copy())
+                    continue
+                zsub = self.rng.standard_normal(len(kn.theta_slot_names(sub)))
+                props.append(Particle(prog, np.concatenate([p.z[:z0], zsub, p.z[z1:]]), p.noise_z))
+                assert len(props[-1].z) == len(kn.theta_slot_names(prog)) and len(names) == len(p.z)
+            lm_new = self.logml(props, idx)
+            for i, (p, q) in enumerate(zip(self.particles, props)):
+                log_alpha = lm_new[i] - self._logml[i] + np.log(p.n_nodes) - np.log(q.n_nodes)
+                if np.log(self.rng.uniform()) < log_alpha:
+                    self.particles[i] = q
+                    self._logml[i] = lm_new[i]
+                    acc += 1
+            if n_hmc > 0:
+                self.mcmc_parameters(n_hmc)
+        return acc / max(1, n_mcmc * len(self.particles))
+
+    # ---- AutoGP.predict_mvn: src/forecasting.jl:46,66 ---------------------------------------------------
+    def predict_mvn(self, forecast_dates, noise_pred: Optional[float] = None) -> MixtureMVN:
+        fd = np.asarray(forecast_dates).astype(self.ds.dtype)
+        idx = self._obs_idx()
+        t, g, step = self._times(np.concatenate([self.ds[idx], fd]))
+        ens = self.ensemble()
+        eng = self._engine()
+        f = eng.factor_store(ens, len(idx), 0, len(fd), t, self.y_transform.apply(self.y[idx]), self.log_weights,
+                             self.y_transform.slope, self.y_transform.intercept, g=g, step=step,
+                             noise_pred=-1.0 if noise_pred is None else float(noise_pred))
+        mu, L = eng.predict(f)
+        f.free()
+        return MixtureMVN(eng, self.log_weights.copy(), mu, L)
