@@ -131,6 +131,42 @@ def forecast_with_nowcasts(base_model: GPModel, nowcasts: Sequence[TData], forec
                            forecast_n_hmc: Optional[int] = None, verbose: bool = False, rng=None) -> np.ndarray:
     """`src/forecasting.jl:117-167`: matrix `(len(forecast_dates), len(nowcasts)·D)`, scenario-major
     column blocks. The base model is not mutated."""
+    x, _ = _forecast_with_nowcasts(base_model, nowcasts, forecast_dates, forecast_draws_per_nowcast,
+                                   n_mcmc=n_mcmc, n_hmc=n_hmc, ess_threshold=ess_threshold,
+                                   forecast_n_hmc=forecast_n_hmc, rng=rng)
+    return _apply(inv_transformation, x)
+
+
+def forecast_with_nowcasts_sharded(base_models: Sequence[GPModel], nowcasts: Sequence[Sequence[TData]],
+                                   forecast_dates, forecast_draws_per_nowcast: int, *,
+                                   inv_transformation: Callable = _identity, n_mcmc: int = 0, n_hmc: int = 0,
+                                   ess_threshold: float = 0.0, forecast_n_hmc: Optional[int] = None,
+                                   group=None, device=None):
+    """One `forecast_with_nowcasts` per series (the per-jurisdiction loop of
+    `docs/vignettes/getting-started.jl:540-552`), with the (series, scenario) pairs partitioned over
+    the ranks of the current `torch.distributed` group (one process per GPU) and one final all-gather.
+    Returns `(draws, logw)`: per series the `(h, K_s·D)` matrix and the `[K_s, P]` log-weights, on
+    every rank. All models must have the same number of particles."""
+    from .sharding import sharded_forecast
+    D = int(forecast_draws_per_nowcast)
+    P = base_models[0].num_particles()
+    assert all(m.num_particles() == P for m in base_models), "all series must use the same n_particles"
+    h = len(list(forecast_dates))
+
+    def compute(sl):
+        return _forecast_with_nowcasts(base_models[sl.series], nowcasts[sl.series][sl.k0:sl.k1], forecast_dates, D,
+                                       n_mcmc=n_mcmc, n_hmc=n_hmc, ess_threshold=ess_threshold,
+                                       forecast_n_hmc=forecast_n_hmc, rng=None)
+
+    draws, logw = sharded_forecast(compute, len(base_models), [len(nc) for nc in nowcasts], h, D, P,
+                                   group=group, device=device)
+    return {s: _apply(inv_transformation, np.ascontiguousarray(x)) for s, x in draws.items()}, logw
+
+
+def _forecast_with_nowcasts(base_model: GPModel, nowcasts: Sequence[TData], forecast_dates,
+                            forecast_draws_per_nowcast: int, *, n_mcmc: int = 0, n_hmc: int = 0,
+                            ess_threshold: float = 0.0, forecast_n_hmc: Optional[int] = None, rng=None):
+    """Body of `forecast_with_nowcasts` before the inverse transformation: `(x [h, K·D], logw [K, P])`."""
     assert len(nowcasts) > 0, "nowcasts vector must not be empty"
     assert not (n_mcmc > 0 and n_hmc == 0), "If n_mcmc > 0, n_hmc must also be > 0 for MCMC refinement"
     assert 0.0 <= ess_threshold <= 1.0, "ess_threshold must be between 0 and 1"
@@ -145,7 +181,7 @@ def forecast_with_nowcasts(base_model: GPModel, nowcasts: Sequence[TData], forec
     if n_mcmc > 0 or not shared_ds:
         # structure moves make the programs diverge per scenario: the reference's schedule verbatim,
         # one model copy per scenario (forecasting.jl:133-155); every likelihood is still a device call
-        blocks = []
+        blocks, lws = [], []
         for nc in nowcasts:
             m = GPModel.from_dict(base_dict, engine=base_model.engine, rng=rng)
             m.add_data(nc.ds, nc.y)
@@ -155,7 +191,8 @@ def forecast_with_nowcasts(base_model: GPModel, nowcasts: Sequence[TData], forec
             elif n_hmc > 0:
                 m.mcmc_parameters(n_hmc)
             blocks.append(forecast(m, dates, D, forecast_n_hmc=forecast_n_hmc))
-        return _apply(inv_transformation, np.hstack(blocks))
+            lws.append(np.asarray(m.log_weights, np.float64).copy())
+        return np.hstack(blocks), np.stack(lws)
 
     m = GPModel.from_dict(base_dict, engine=base_model.engine, rng=rng)
     eng = m._engine()
@@ -172,9 +209,10 @@ def forecast_with_nowcasts(base_model: GPModel, nowcasts: Sequence[TData], forec
         zeta = rng.standard_normal((K, D, h))
         u = rng.uniform(size=(K, D))
         u_res = rng.uniform(size=(K, P)) if ess_threshold > 0.0 else None
+        logw = np.empty((K, P))
         x = eng.forecast_with_nowcasts(ens, n, k, h, t, y1, y2, m.log_weights, zeta, yt.slope, yt.intercept,
-                                       g=g, step=step, u=u, u_res=u_res, ess_thr=ess_threshold)
-        return _apply(inv_transformation, np.ascontiguousarray(x))
+                                       g=g, step=step, u=u, u_res=u_res, ess_thr=ess_threshold, logw=logw)
+        return np.ascontiguousarray(x), logw
 
     # per-scenario parameter rejuvenation: all K·P chains advance together
     sp = _ScenarioParams(m, K)
@@ -238,4 +276,4 @@ def forecast_with_nowcasts(base_model: GPModel, nowcasts: Sequence[TData], forec
         for i in range(D):                                             # forecasting.jl:63-68
             metropolis(forecast_n_hmc)
             x[:, i::D] = draw_block(1)
-    return _apply(inv_transformation, x)
+    return x, logw

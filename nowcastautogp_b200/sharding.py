@@ -1,0 +1,120 @@
+"""Multi-GPU partition of the (series, nowcast scenario) work and the final gather.
+
+The instances of the hot path are independent per (series, scenario, particle): the reference runs
+one task per scenario on a private model copy (`/root/reference/src/forecasting.jl:131-133`) and one
+`forecast_with_nowcasts` call per series (`docs/vignettes/getting-started.jl:540-552`). The only
+couplings are the per-scenario weight normalisation over that scenario's P particles and the final
+`hcat` (`forecasting.jl:166`). So: one process per GPU, all particles of a (series, scenario) pair on
+one GPU, pairs split contiguously across ranks — series first, so that in the scenario-shared fast
+path each particle is factored on exactly one GPU — and ONE collective at the end: an all-gather of
+the draws `[h, K·D]` and log-weights `[K, P]` (NCCL over NVLink on the GPU box, gloo in CPU tests).
+No collective on the data path.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Sequence, Tuple
+
+import numpy as np
+
+
+@dataclass(frozen=True)
+class Slice:
+    series: int
+    k0: int     # first scenario (inclusive)
+    k1: int     # last scenario (exclusive)
+
+
+def partition(n_series: int, n_scenarios: Sequence[int] | int, world: int) -> List[List[Slice]]:
+    """Contiguous split of the flattened (series, scenario) pairs over `world` ranks.
+
+    Whole series are kept together whenever there are at least as many series as ranks (C4: 53 series
+    on 8 GPUs → 7/7/7/7/7/6/6/6); otherwise the pair list is cut into `world` near-equal contiguous
+    runs, which splits a series' scenarios across ranks (C2: one series, K scenarios → K/world each).
+    Every pair is owned by exactly one rank; a rank's slices are in global order."""
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    ks = [int(n_scenarios)] * n_series if np.isscalar(n_scenarios) else [int(k) for k in n_scenarios]
+    if len(ks) != n_series:
+        raise ValueError("n_scenarios must have one entry per series")
+    out: List[List[Slice]] = [[] for _ in range(world)]
+    if n_series >= world:
+        base, extra = divmod(n_series, world)
+        s = 0
+        for r in range(world):
+            cnt = base + (1 if r < extra else 0)
+            out[r] = [Slice(i, 0, ks[i]) for i in range(s, s + cnt) if ks[i] > 0]
+            s += cnt
+        return out
+    total = sum(ks)
+    bounds = [(total * r) // world for r in range(world + 1)]
+    starts = np.concatenate([[0], np.cumsum(ks)])
+    for r in range(world):
+        lo, hi = bounds[r], bounds[r + 1]
+        for i in range(n_series):
+            a, b = max(lo, starts[i]), min(hi, starts[i + 1])
+            if a < b:
+                out[r].append(Slice(i, int(a - starts[i]), int(b - starts[i])))
+    return out
+
+
+def sharded_forecast(compute: Callable[[Slice], Tuple[np.ndarray, np.ndarray]], n_series: int,
+                     n_scenarios: Sequence[int] | int, h: int, D: int, P: int,
+                     group=None, device=None) -> Tuple[Dict[int, np.ndarray], Dict[int, np.ndarray]]:
+    """Run `compute(slice) -> (x [h, (k1-k0)·D], logw [(k1-k0), P])` on this rank's slices and gather.
+
+    Returns `(draws, logw)` dicts keyed by series on EVERY rank: `draws[s]` is the reference's
+    `(h, K_s·D)` matrix in scenario-major column order, `logw[s]` is `[K_s, P]`. Works without an
+    initialised process group (world = 1). The gather is a single padded `all_gather_into_tensor` per
+    output (ranks can own different numbers of pairs)."""
+    import torch
+    import torch.distributed as dist
+
+    use_dist = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if use_dist else 1
+    rank = dist.get_rank(group) if use_dist else 0
+    ks = [int(n_scenarios)] * n_series if np.isscalar(n_scenarios) else [int(k) for k in n_scenarios]
+    parts = partition(n_series, ks, world)
+    mine = parts[rank]
+    # local results packed pair-major: draws [pairs, D, h] (column blocks of x transposed), logw [pairs, P]
+    n_pairs = [sum(s.k1 - s.k0 for s in p) for p in parts]
+    cap = max(max(n_pairs), 1)
+    xd = np.zeros((cap, D, h))
+    lw = np.zeros((cap, P))
+    off = 0
+    for sl in mine:
+        x, logw = compute(sl)
+        kk = sl.k1 - sl.k0
+        x = np.asarray(x, np.float64)
+        if x.shape != (h, kk * D):
+            raise ValueError(f"compute returned draws of shape {x.shape}, expected {(h, kk * D)}")
+        xd[off:off + kk] = x.T.reshape(kk, D, h)
+        lw[off:off + kk] = np.asarray(logw, np.float64).reshape(kk, P)
+        off += kk
+    if use_dist:
+        dev = torch.device("cpu") if device is None else device
+        tx = torch.from_numpy(xd).to(dev)
+        tl = torch.from_numpy(lw).to(dev)
+        gx = torch.empty((world,) + tuple(tx.shape), dtype=tx.dtype, device=dev)
+        gl = torch.empty((world,) + tuple(tl.shape), dtype=tl.dtype, device=dev)
+        if dev.type == "cpu":     # gloo has no all_gather_into_tensor on older builds: use the list form
+            lx = list(gx.unbind(0)); ll = list(gl.unbind(0))
+            dist.all_gather(lx, tx, group=group)
+            dist.all_gather(ll, tl, group=group)
+            gx = torch.stack(lx); gl = torch.stack(ll)
+        else:
+            dist.all_gather_into_tensor(gx, tx, group=group)
+            dist.all_gather_into_tensor(gl, tl, group=group)
+        gx, gl = gx.cpu().numpy(), gl.cpu().numpy()
+    else:
+        gx, gl = xd[None], lw[None]
+    draws = {s: np.empty((h, ks[s] * D)) for s in range(n_series)}
+    logws = {s: np.empty((ks[s], P)) for s in range(n_series)}
+    for r in range(world):
+        off = 0
+        for sl in parts[r]:
+            kk = sl.k1 - sl.k0
+            draws[sl.series][:, sl.k0 * D:sl.k1 * D] = gx[r, off:off + kk].reshape(kk * D, h).T
+            logws[sl.series][sl.k0:sl.k1] = gl[r, off:off + kk]
+            off += kk
+    return draws, logws
