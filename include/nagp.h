@@ -24,6 +24,8 @@
  *  - Times: t[q] rescaled time points; g (nullable) int32 grid indices with `step` selects the
  *    lag-grid contract of KERNEL_SPEC §2 (Δ_ij = |g_i − g_j|·step).
  *  - Point order of a forecast problem: [n training | k nowcast | h forecast], m = n+k, q = m+h.
+ *  - Sizes: q <= 232 runs entirely in shared memory; 232 < q <= 4096 keeps the factor in HBM
+ *    (same entry points, same results; NAGP_E_SIZE beyond).
  */
 #ifndef NAGP_H
 #define NAGP_H
@@ -107,6 +109,28 @@ int32_t nagp_factor_store(nagp_ctx *ctx, int64_t P,
                           const double *y1, double ya, double yb, const double *logw0,
                           nagp_factor **out, double *logml_n, int32_t *info);
 void nagp_factor_free(nagp_factor *f);
+
+/* ---- (a2/a4) appendable factor for long series: SMC data annealing, rank-append Cholesky ---------
+ * AutoGP.fit_smc! walks a schedule of growing observation counts (/root/reference/src/make_and_fit_model.jl:
+ * 89-91, linear_schedule) and re-scores every particle from scratch at each step; add_data! does the same
+ * for one batch (/root/reference/src/forecasting.jl:135). nagp_factor_store_large factors the P particles
+ * over the first n points (n <= capacity <= 4096) and keeps the WHOLE factor in device memory;
+ * nagp_factor_append extends it in place by k_new points (streams the stored factor once: HBM-bound,
+ * k/4 FLOP per byte) and returns dlogml[P] = logML(n + k_new) - logML(n) (the SMC log-weight increment)
+ * and, if logml != NULL, the running logML[P]. Valid while the particles' (tree, theta) are unchanged;
+ * after a rejuvenation move the caller stores a new factor. prog/offsets/t/g/y must be host arrays;
+ * y in scaled space; g/g_new both NULL (pairwise times) or both non-NULL (lag grid, same origin). */
+int32_t nagp_factor_store_large(nagp_ctx *ctx, int64_t P,
+                                const uint8_t *prog, const int64_t *prog_off,
+                                const double *theta, const int64_t *theta_off, const double *noise,
+                                int64_t n, int64_t capacity,
+                                const double *t, const int32_t *g, double step, const double *y,
+                                nagp_factor **out, double *logml, int32_t *info);
+int32_t nagp_factor_append(nagp_ctx *ctx, nagp_factor *f, int64_t k_new,
+                           const double *t_new, const int32_t *g_new, const double *y_new,
+                           double *dlogml, double *logml, int32_t *info);
+/* Number of points currently held by a factor (-1 for NULL). */
+int64_t nagp_factor_size(const nagp_factor *f);
 
 /* ---- (a4) add_data! for K scenarios against a stored factor -----------------------------------
  * /root/reference/src/forecasting.jl:135. y2[K*k] scaled. logw[K*P] = logw0 + Δ logML;

@@ -29,6 +29,10 @@ SIGNATURES = {
     "nagp_factor_store": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _f64, _i64, _i64, _i64, _vp, _vp, _f64,
                                  _vp, _f64, _f64, _vp, C.POINTER(_vp), _vp, _vp]),
     "nagp_factor_free": (None, [_vp]),
+    "nagp_factor_store_large": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _f64, _vp,
+                                       C.POINTER(_vp), _vp, _vp]),
+    "nagp_factor_append": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "nagp_factor_size": (_i64, [_vp]),
     "nagp_append": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "nagp_predict": (_i32, [_vp, _vp, _vp, _vp]),
     "nagp_ess": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp]),

@@ -44,6 +44,17 @@ struct nagp_factor {
     int n, k, h;
     double ya, yb;
     double *proj = nullptr, *Ltail = nullptr, *L33 = nullptr, *logw0 = nullptr, *logml_n = nullptr;
+    // appendable store (nagp_factor_store_large): the whole factor stays in HBM
+    bool appendable = false;
+    int64_t cap = 0;
+    int ntab_cap = 0, ncp_cap = 0, nth_cap = 1;
+    double step = 0.0, jitter = 0.0;
+    size_t L_stride = 0, W_stride = 0;
+    double *Lbig = nullptr, *Wbig = nullptr, *d_theta = nullptr, *d_noise = nullptr, *d_t = nullptr, *d_y = nullptr;
+    int32_t *d_g = nullptr;
+    uint8_t *d_prog = nullptr;
+    int64_t *d_prog_off = nullptr, *d_theta_off = nullptr;
+    std::vector<int32_t> g_host;      // lag-grid indices of the stored points (empty: pairwise times)
 };
 
 namespace {
@@ -226,7 +237,7 @@ int32_t fit_tables_v1(nagp_ctx *ctx, int q, int G, int *ntab_cap, int *ncp_cap)
 int32_t check_dims(nagp_ctx *ctx, int64_t n, int64_t k, int64_t h)
 {
     if (n < 0 || k < 0 || h < 0 || n + k + h <= 0) return fail(ctx, NAGP_E_ARG, "bad n/k/h");
-    if (n + k + h > 234) return fail(ctx, NAGP_E_SIZE, "n+k+h > 234 not supported by the resident path");
+    if (n + k + h > large_max_q()) return fail(ctx, NAGP_E_SIZE, "n+k+h > 4096 not supported");
     return NAGP_OK;
 }
 
@@ -255,7 +266,27 @@ int32_t run_fused(nagp_ctx *ctx, FusedArgs a, const int64_t *theta_off_host)
             return NAGP_OK;
         }
     }
-    if (ctx->variant == 2) return fail(ctx, NAGP_E_SIZE, "problem does not fit the tile kernel");
+    if (ctx->variant != 1 || q > 234) {
+        // beyond shared memory: blocked factorisation with the factor in HBM (per-CTA workspace)
+        int64_t nth = 1;
+        for (int64_t p = 0; p < a.P; ++p) nth = std::max(nth, theta_off_host[p + 1] - theta_off_host[p]);
+        LargePlan pl = plan_large(q, q, a.G, (int)std::min<int64_t>(nth, MAX_THETA), a.ntab_cap, a.ncp_cap,
+                                  ctx->smem_per_sm, false);
+        if (!pl.ok) return fail(ctx, NAGP_E_SIZE, "problem too large");
+        const int grid = large_grid(pl, a.B, ctx->num_sms, false);
+        if (getenv("NAGP_DEBUG"))
+            fprintf(stderr, "[nagp] large kernel: q=%d ntp=%d G=%d smem=%zu B scratch/CTA=%d L/CTA=%zu B grid=%d\n",
+                    q, pl.ntp, a.G, pl.smem_bytes, pl.scratch_stride, pl.L_stride * 8, grid);
+        char *scr = nullptr;
+        if (pl.scratch_stride) NAGP_TRY(scratch(ctx, (size_t)grid * pl.scratch_stride, &scr));
+        double *Lws = nullptr;
+        NAGP_TRY(scratch(ctx, (size_t)grid * pl.L_stride, &Lws));
+        unsigned long long *counter = nullptr;
+        NAGP_TRY(scratch(ctx, 1, &counter));
+        NAGP_CUDA(ctx, launch_chol_large(a, pl, scr, Lws, 0, nullptr, counter, grid, ctx->stream));
+        ctx->launches += 1;
+        return NAGP_OK;
+    }
     NAGP_TRY(fit_tables_v1(ctx, q, a.G, &a.ntab_cap, &a.ncp_cap));
     NAGP_CUDA(ctx, launch_fused_v1(a, ctx->stream));
     ctx->launches += 1;
@@ -490,13 +521,137 @@ void nagp_factor_free(nagp_factor *f)
     if (!f) return;
     cudaSetDevice(f->device);
     cudaFree(f->proj); cudaFree(f->Ltail); cudaFree(f->L33); cudaFree(f->logw0); cudaFree(f->logml_n);
+    cudaFree(f->Lbig); cudaFree(f->Wbig); cudaFree(f->d_theta); cudaFree(f->d_noise); cudaFree(f->d_t);
+    cudaFree(f->d_y); cudaFree(f->d_g); cudaFree(f->d_prog); cudaFree(f->d_prog_off); cudaFree(f->d_theta_off);
     delete f;
+}
+
+
+// ---- appendable factor store for long series (SMC data annealing, BASELINE config 5) -----------------
+int32_t nagp_factor_store_large(nagp_ctx *ctx, int64_t P, const uint8_t *prog, const int64_t *prog_off,
+                                const double *theta, const int64_t *theta_off, const double *noise,
+                                int64_t n, int64_t capacity, const double *t, const int32_t *g, double step,
+                                const double *y, nagp_factor **out, double *logml, int32_t *info)
+{
+    if (!ctx) return NAGP_E_ARG;
+    if (!out || P <= 0 || !prog || !prog_off || !theta || !theta_off || !noise || !t || !y || !info || n <= 0)
+        return fail(ctx, NAGP_E_ARG, "nagp_factor_store_large: null or empty argument");
+    *out = nullptr;
+    if (capacity < n) capacity = n;
+    NAGP_TRY(check_dims(ctx, capacity, 0, 0));
+    if (on_device(prog) || on_device(prog_off) || on_device(theta_off) || on_device(t) || on_device(g) || on_device(y))
+        return fail(ctx, NAGP_E_ARG, "nagp_factor_store_large: prog/offsets/t/g/y must be host arrays");
+    NAGP_CUDA(ctx, cudaSetDevice(ctx->device));
+    NAGP_TRY(arena_reset(ctx));
+    nagp_factor *f = new (std::nothrow) nagp_factor();
+    if (!f) return fail(ctx, NAGP_E_ARG, "out of host memory");
+    f->device = ctx->device; f->P = P; f->n = (int)n; f->k = 0; f->h = 0; f->ya = 1.0; f->yb = 0.0;
+    f->appendable = true; f->cap = capacity; f->step = step; f->jitter = ctx->jitter;
+    auto bail = [&](int32_t code) { nagp_factor_free(f); return code; };
+    FusedArgs a{};
+    int32_t rc;
+    if ((rc = grid_extent(ctx, g, n, &a.G)) != NAGP_OK) return bail(rc);
+    // table capacities are fixed for the life of the factor: plan them as for the full capacity
+    if ((rc = plan_tables(ctx, P, prog, prog_off, theta_off, (int)capacity, a.G, &a.ntab_cap, &a.ncp_cap)) != NAGP_OK) return bail(rc);
+    f->ntab_cap = a.ntab_cap; f->ncp_cap = a.ncp_cap;
+    int64_t nth = 1;
+    for (int64_t p = 0; p < P; ++p) nth = std::max(nth, theta_off[p + 1] - theta_off[p]);
+    f->nth_cap = (int)std::min<int64_t>(nth, MAX_THETA);
+    LargePlan pl = plan_large((int)n, (int)capacity, a.G, f->nth_cap, a.ntab_cap, a.ncp_cap, ctx->smem_per_sm, false);
+    f->L_stride = pl.L_stride; f->W_stride = (size_t)pl.ntp_cap * 64;
+    const int64_t nprog = prog_off[P], ntheta = theta_off[P];
+    auto dal = [&](void **p, size_t bytes) { return cudaMalloc(p, std::max<size_t>(bytes, 16)); };
+    if (dal((void **)&f->Lbig, (size_t)P * f->L_stride * 8) != cudaSuccess || dal((void **)&f->Wbig, (size_t)P * f->W_stride * 8) != cudaSuccess ||
+        dal((void **)&f->d_theta, ntheta * 8) != cudaSuccess || dal((void **)&f->d_noise, P * 8) != cudaSuccess ||
+        dal((void **)&f->d_t, capacity * 8) != cudaSuccess || dal((void **)&f->d_y, capacity * 8) != cudaSuccess ||
+        dal((void **)&f->d_g, capacity * 4) != cudaSuccess || dal((void **)&f->d_prog, nprog) != cudaSuccess ||
+        dal((void **)&f->d_prog_off, (P + 1) * 8) != cudaSuccess || dal((void **)&f->d_theta_off, (P + 1) * 8) != cudaSuccess ||
+        dal((void **)&f->logml_n, P * 8) != cudaSuccess) {
+        cudaGetLastError();
+        return bail(fail(ctx, NAGP_E_CUDA, "factor allocation failed (capacity too large for device memory?)"));
+    }
+    cudaStream_t st = ctx->stream;
+    cudaError_t e = cudaSuccess;
+    auto cp = [&](void *d, const void *s_, size_t bytes) { if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(d, s_, bytes, cudaMemcpyDefault, st); };
+    cp(f->d_theta, theta, ntheta * 8); cp(f->d_noise, noise, P * 8); cp(f->d_t, t, n * 8); cp(f->d_y, y, n * 8);
+    if (g) { cp(f->d_g, g, n * 4); f->g_host.assign(g, g + n); }
+    cp(f->d_prog, prog, nprog); cp(f->d_prog_off, prog_off, (P + 1) * 8); cp(f->d_theta_off, theta_off, (P + 1) * 8);
+    if (e != cudaSuccess) return bail(fail(ctx, NAGP_E_CUDA, cudaGetErrorString(e)));
+    a.B = P; a.P = P; a.prog = f->d_prog; a.prog_off = f->d_prog_off; a.theta = f->d_theta; a.theta_off = f->d_theta_off;
+    a.noise = f->d_noise; a.jitter = ctx->jitter; a.noise_pred = -1.0;
+    a.n = (int)n; a.k = 0; a.h = 0; a.t = f->d_t; a.g = g ? f->d_g : nullptr; a.step = step;
+    a.y1 = f->d_y; a.ya = 1.0; a.yb = 0.0; a.logml_n = f->logml_n;
+    if ((rc = stage_out(ctx, info, (size_t)P, &a.info)) != NAGP_OK) return bail(rc);
+    const int grid = large_grid(pl, P, ctx->num_sms, false);
+    char *scr = nullptr;
+    if (pl.scratch_stride && (rc = scratch(ctx, (size_t)grid * pl.scratch_stride, &scr)) != NAGP_OK) return bail(rc);
+    unsigned long long *counter = nullptr;
+    if ((rc = scratch(ctx, 1, &counter)) != NAGP_OK) return bail(rc);
+    e = launch_chol_large(a, pl, scr, f->Lbig, 1, f->Wbig, counter, grid, st);
+    if (e != cudaSuccess) return bail(fail(ctx, NAGP_E_CUDA, cudaGetErrorString(e)));
+    ctx->launches += 1;
+    if (logml) {
+        e = cudaMemcpyAsync(logml, f->logml_n, P * sizeof(double), cudaMemcpyDefault, st);
+        if (e != cudaSuccess) return bail(fail(ctx, NAGP_E_CUDA, cudaGetErrorString(e)));
+    }
+    if ((rc = finish(ctx)) != NAGP_OK) return bail(rc);
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return bail(fail(ctx, NAGP_E_CUDA, cudaGetErrorString(e)));
+    *out = f;
+    return on_device(info) ? NAGP_OK : worst_info(info, P);
+}
+
+int64_t nagp_factor_size(const nagp_factor *f) { return f ? f->n : -1; }
+
+int32_t nagp_factor_append(nagp_ctx *ctx, nagp_factor *f, int64_t k_new, const double *t_new, const int32_t *g_new,
+                           const double *y_new, double *dlogml, double *logml, int32_t *info)
+{
+    if (!ctx) return NAGP_E_ARG;
+    if (!f || !f->appendable || k_new <= 0 || !t_new || !y_new || !info)
+        return fail(ctx, NAGP_E_ARG, "nagp_factor_append: null argument or factor not appendable");
+    if (f->device != ctx->device) return fail(ctx, NAGP_E_ARG, "factor lives on another device");
+    if ((int64_t)f->n + k_new > f->cap) return fail(ctx, NAGP_E_SIZE, "nagp_factor_append: capacity exceeded");
+    if (f->g_host.empty() != (g_new == nullptr)) return fail(ctx, NAGP_E_ARG, "nagp_factor_append: lag-grid mode must match the stored factor");
+    if (on_device(t_new) || on_device(g_new) || on_device(y_new)) return fail(ctx, NAGP_E_ARG, "nagp_factor_append: t/g/y must be host arrays");
+    NAGP_CUDA(ctx, cudaSetDevice(ctx->device));
+    NAGP_TRY(arena_reset(ctx));
+    const int n_old = f->n, n_new = f->n + (int)k_new;
+    cudaStream_t st = ctx->stream;
+    NAGP_CUDA(ctx, cudaMemcpyAsync(f->d_t + n_old, t_new, k_new * 8, cudaMemcpyHostToDevice, st));
+    NAGP_CUDA(ctx, cudaMemcpyAsync(f->d_y + n_old, y_new, k_new * 8, cudaMemcpyHostToDevice, st));
+    FusedArgs a{};
+    if (g_new) {
+        NAGP_CUDA(ctx, cudaMemcpyAsync(f->d_g + n_old, g_new, k_new * 4, cudaMemcpyHostToDevice, st));
+        f->g_host.insert(f->g_host.end(), g_new, g_new + k_new);
+        NAGP_TRY(grid_extent(ctx, f->g_host.data(), n_new, &a.G));
+    }
+    a.B = f->P; a.P = f->P; a.prog = f->d_prog; a.prog_off = f->d_prog_off; a.theta = f->d_theta; a.theta_off = f->d_theta_off;
+    a.noise = f->d_noise; a.jitter = f->jitter; a.noise_pred = -1.0;
+    a.n = n_new; a.k = 0; a.h = 0; a.t = f->d_t; a.g = g_new ? f->d_g : nullptr; a.step = f->step;
+    a.y1 = f->d_y; a.ya = 1.0; a.yb = 0.0;
+    a.ntab_cap = f->ntab_cap; a.ncp_cap = f->ncp_cap;
+    NAGP_TRY(stage_out(ctx, info, (size_t)f->P, &a.info));
+    double *d_dl = nullptr;
+    NAGP_TRY(stage_out(ctx, dlogml, (size_t)f->P, &d_dl));
+    LargePlan pl = plan_large(n_new, (int)f->cap, a.G, f->nth_cap, a.ntab_cap, a.ncp_cap, ctx->smem_per_sm, true);
+    if (pl.L_stride != f->L_stride) return fail(ctx, NAGP_E_ARG, "nagp_factor_append: internal layout mismatch");
+    const int grid = large_grid(pl, f->P, ctx->num_sms, true);
+    char *scr = nullptr;
+    if (pl.scratch_stride) NAGP_TRY(scratch(ctx, (size_t)grid * pl.scratch_stride, &scr));
+    NAGP_CUDA(ctx, launch_rank_append(a, pl, scr, f->Lbig, f->Wbig, n_old, f->logml_n, d_dl, grid, st));
+    ctx->launches += 1;
+    f->n = n_new;
+    if (logml) NAGP_CUDA(ctx, cudaMemcpyAsync(logml, f->logml_n, f->P * sizeof(double), cudaMemcpyDefault, st));
+    NAGP_TRY(finish(ctx));
+    NAGP_CUDA(ctx, cudaStreamSynchronize(st));
+    return on_device(info) ? NAGP_OK : worst_info(info, f->P);
 }
 
 int32_t nagp_append(nagp_ctx *ctx, const nagp_factor *f, int64_t K, const double *y2, double *logw, double *mu)
 {
     if (!ctx) return NAGP_E_ARG;
     if (!f || K <= 0 || !logw || (f->k > 0 && !y2)) return fail(ctx, NAGP_E_ARG, "nagp_append: null or empty argument");
+    if (f->appendable) return fail(ctx, NAGP_E_ARG, "nagp_append: factor was created by nagp_factor_store_large (use nagp_factor_append)");
     if (f->device != ctx->device) return fail(ctx, NAGP_E_ARG, "factor lives on another device");
     NAGP_CUDA(ctx, cudaSetDevice(ctx->device));
     NAGP_TRY(arena_reset(ctx));
@@ -514,7 +669,7 @@ int32_t nagp_append(nagp_ctx *ctx, const nagp_factor *f, int64_t K, const double
 int32_t nagp_predict(nagp_ctx *ctx, const nagp_factor *f, double *mu, double *L)
 {
     if (!ctx) return NAGP_E_ARG;
-    if (!f) return fail(ctx, NAGP_E_ARG, "nagp_predict: null factor");
+    if (!f || f->appendable) return fail(ctx, NAGP_E_ARG, "nagp_predict: null or appendable-only factor");
     if (f->device != ctx->device) return fail(ctx, NAGP_E_ARG, "factor lives on another device");
     if (mu && f->k != 0) return fail(ctx, NAGP_E_ARG, "nagp_predict: means need k == 0 (use nagp_append)");
     NAGP_CUDA(ctx, cudaSetDevice(ctx->device));

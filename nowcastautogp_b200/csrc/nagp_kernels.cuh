@@ -59,6 +59,29 @@ int fused_v2_grid(const V2Plan &pl, int64_t B, int num_sms);
 cudaError_t launch_fused_v2(const FusedArgs &a, const V2Plan &pl, char *scratch, unsigned long long *work_counter,
                             int grid, cudaStream_t stream);
 
+// Large path (q beyond shared memory): factor in HBM as tile-packed operand-layout tiles.
+struct LargePlan {
+    int ok;
+    int nt, ntp;          // tile rows of the problem / rounded up to a block of 8
+    int ntp_cap;          // tile rows of the storage capacity (>= ntp)
+    int yrow;             // tile row index of z = L^-1 y inside the storage (= ntp_cap)
+    size_t L_stride;      // doubles per factor slot
+    int aux_off[5];
+    int aux_smem[5];
+    int scratch_stride;
+    size_t smem_bytes;
+};
+int large_max_q();
+LargePlan plan_large(int q, int q_cap, int G, int ntheta_cap, int ntab_cap, int ncp_cap, int smem_per_sm, bool append);
+int large_grid(const LargePlan &pl, int64_t B, int num_sms, bool append);
+// keep = 1: instance b's factor goes to slot b of L (and its inverse diagonal tiles to W); 0: L is a
+// per-CTA workspace of `grid` slots.
+cudaError_t launch_chol_large(const FusedArgs &a, const LargePlan &pl, char *scratch, double *L, int keep, double *W,
+                              unsigned long long *work_counter, int grid, cudaStream_t stream);
+// Extend the stored factors (slots 0..B-1) from n_old to a.n points in place; a.t/a.g/a.y1 cover all a.n points.
+cudaError_t launch_rank_append(const FusedArgs &a, const LargePlan &pl, char *scratch, double *L, double *W,
+                               int n_old, double *logml, double *dlogml, int grid, cudaStream_t stream);
+
 // Scenario-shared fast path: per (scenario, particle) O(k^2 + hk) tail of the forward solve.
 struct AppendArgs {
     int64_t K, P;

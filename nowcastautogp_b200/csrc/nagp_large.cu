@@ -1,0 +1,759 @@
+// nagp_large.cu — factorisation beyond shared-memory size (q up to 4096) and the in-place rank-append.
+//
+//  chol_large_kernel   one CTA per instance, persistent grid with a dynamic instance queue. Blocked
+//                      left-looking Cholesky by block columns of 8 tiles (64 columns): the factor lives
+//                      in HBM/L2 as 8x8 FP64 tiles in DMMA operand order (tile-packed lower triangle,
+//                      plus one tile row for z = L^-1 y), Gram tiles are evaluated on the fly by the
+//                      kernel-tree interpreter and never stored. Per block column the warps pull row
+//                      tiles from a shared queue: a row accumulates sum_P L_IP L_JP^T for all 8 column
+//                      tiles in registers (DMMA; one 16-byte fragment load per operand tile), the 8
+//                      rows of the diagonal block go to shared memory where one warp factors the 64x64
+//                      block (8x8 in-register Cholesky + inverse per tile), every other row finishes with
+//                      an in-register triangular solve against that block and writes its 8 tiles.
+//  rank_append_kernel  one CTA per particle: extends a stored factor by new rows in place (up-looking):
+//                      streams the existing L once in storage order, split-K over the warps.
+//
+// Replaces, for long series, AutoGP's Gram + dpotrf per likelihood evaluation behind
+//   /root/reference/src/make_and_fit_model.jl:84-91 (GPModel + fit_smc! data annealing: add a batch of
+//   observations, re-score every particle) and /root/reference/src/forecasting.jl:133,135,46.
+// Arithmetic contract: docs/KERNEL_SPEC.md §3-§6.
+#include <algorithm>
+
+#include "nagp_kernels.cuh"
+#include "nagp_tree.cuh"
+#include "nagp_tile.cuh"
+
+namespace nagp {
+
+namespace {
+
+constexpr int kBlk = 8;   // tile columns per block column
+
+__device__ __forceinline__ double2 ldg128(const double *p)
+{
+    return *reinterpret_cast<const double2 *>(p);
+}
+__device__ __forceinline__ double2 ldg128_stream(const double *p)
+{
+    return __ldcg(reinterpret_cast<const double2 *>(p));
+}
+
+// accumulator layout (lane (r, j) holds (r, 2j), (r, 2j+1)) -> A-operand fragment (lane (r, kk) holds
+// (r, kk) and (r, kk + 4))
+__device__ __forceinline__ double2 acc_to_frag(double c0, double c1, int lane)
+{
+    const int lj = lane & 3;
+    const int cv0 = (lane & ~3) + (lj >> 1), cv1 = cv0 + 2;
+    const bool odd = lane & 1;
+    const double v00 = shfl(c0, cv0), v01 = shfl(c1, cv0);
+    const double v10 = shfl(c0, cv1), v11 = shfl(c1, cv1);
+    return make_double2(odd ? v01 : v00, odd ? v11 : v10);
+}
+
+// store an accumulator-layout tile in operand layout
+__device__ __forceinline__ void store_op(double *tile, double c0, double c1, int lane)
+{
+    const int lr = lane >> 2, lj = lane & 3;
+    tile[op_idx(lr, 2 * lj)] = c0;
+    tile[op_idx(lr, 2 * lj + 1)] = c1;
+}
+
+struct LargeLayout {
+    int nt;              // tile rows holding real points: ceil(q / 8)
+    int ntp;             // nt rounded up to a multiple of kBlk
+    int yrow;            // tile row index of the z = L^-1 y row (>= ntp)
+    int aux_off[5];      // th, gg, tt, sig, tab
+    int aux_smem[5];
+    int scratch_stride;
+    char *scratch;
+    double *L;           // factor storage
+    size_t L_stride;     // doubles per slot
+    int keep;            // 1: slot = instance b (factor kept), 0: slot = blockIdx.x (workspace)
+    double *W;           // [slot][ntp_cap] inverse diagonal tiles (operand layout), nullable
+    size_t W_stride;
+    unsigned long long *work_counter;
+};
+
+struct Setup {
+    double *th; int *gg; double *tt; double *sig; double *tab;
+};
+
+__device__ __forceinline__ Setup aux_pointers(const LargeLayout &lay, char *aux_s)
+{
+    char *aux_g = lay.scratch + (size_t)blockIdx.x * lay.scratch_stride;
+    Setup s;
+    auto aux = [&](int i) { return (lay.aux_smem[i] ? aux_s : aux_g) + lay.aux_off[i]; };
+    s.th = reinterpret_cast<double *>(aux(0));
+    s.gg = reinterpret_cast<int *>(aux(1));
+    s.tt = reinterpret_cast<double *>(aux(2));
+    s.sig = reinterpret_cast<double *>(aux(3));
+    s.tab = reinterpret_cast<double *>(aux(4));
+    return s;
+}
+
+// Program compile + theta + lag / sigma tables for one instance (all threads; ends with a barrier).
+__device__ __forceinline__ void instance_setup(TreeProgram &tp, const FusedArgs &a, const Setup &su, int64_t s, int p,
+                                               int Q, int tid)
+{
+    const int64_t po = a.prog_off[p], plen = a.prog_off[p + 1] - po;
+    const int64_t to = a.theta_off[p], ntheta = a.theta_off[p + 1] - to;
+    const double *theta_g = a.theta + s * a.theta_stride_k + to;
+    if (tid == 0) {
+        if (ntheta > MAX_THETA) tp.error = -3;
+        else tree_compile(tp, a.prog + po, (int)plen, (int)ntheta, a.G > 0 ? a.ntab_cap : 0, a.ncp_cap);
+    }
+    for (int i = tid; i < ntheta && i < MAX_THETA; i += kThreads) su.th[i] = theta_g[i];
+    __syncthreads();
+    if (tp.error) return;
+    const int G = a.G;
+    for (int e = tid; e < tp.ntab * G; e += kThreads) {
+        int id = e / G, lg = e - id * G;
+        int s0 = tp.tab_src0[id], s1 = tp.tab_src1[id];
+        su.tab[e] = tree_eval(tp.sop + s0, tp.sarg + s0, nullptr, s1 - s0, su.th, 0.0, 0.0,
+                              (double)lg * a.step, 0, nullptr, 0, nullptr, 0, 0, 0);
+    }
+    for (int e = tid; e < tp.ncp * Q; e += kThreads) {
+        int id = e / Q, i = e - id * Q;
+        const double *cp = su.th + tp.cp_theta[id];
+        su.sig[e] = 0.5 * (1.0 + tanh((su.tt[i] - cp[0]) / cp[1]));
+    }
+    __syncthreads();
+}
+
+struct GramCtx {
+    EvalCtx cx;
+    const int *gg;
+    int q, m;
+    double d_lo, d_hi;
+    bool single_table;
+};
+
+// Gram tiles (I, Ja) and (I, Jb) in accumulator layout: out[0..1] of the first, out[2..3] of the second.
+// Rows/columns >= q are identity padding.
+__device__ __forceinline__ void gram_pair(const TreeProgram &tp, const GramCtx &gc, int I, int Ja, int Jb, int lane,
+                                          double (&out)[4])
+{
+    const int gr = lane >> 2, gcn = (lane & 3) * 2;
+    int ii[4], jj[4], lag[4];
+    bool real[4];
+    const int gi = gc.gg[I * 8 + gr];
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+        const int J = h2 ? Jb : Ja;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int x = h2 * 2 + e;
+            ii[x] = I * 8 + gr;
+            jj[x] = J * 8 + gcn + e;
+            const int lg = gi - gc.gg[jj[x]];
+            lag[x] = lg < 0 ? -lg : lg;
+            real[x] = ii[x] < gc.q && jj[x] < gc.q;
+        }
+    }
+    if (gc.single_table) {
+#pragma unroll
+        for (int x = 0; x < 4; ++x) out[x] = gc.cx.tab[lag[x]];
+    } else {
+        tree_eval4(tp, gc.cx, ii, jj, lag, out);
+    }
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+        if (!real[x]) out[x] = (ii[x] == jj[x]) ? 1.0 : 0.0;
+        else if (ii[x] == jj[x]) out[x] += (ii[x] < gc.m) ? gc.d_lo : gc.d_hi;
+    }
+}
+
+// observation values of columns [J*8, J*8+8) as the row-0 entries of an accumulator-layout tile
+__device__ __forceinline__ void y_tile(const FusedArgs &a, int64_t b, int64_t s, int J, int ny, int lane, double &c0, double &c1)
+{
+    c0 = 0.0; c1 = 0.0;
+    if ((lane >> 2) != 0) return;
+    const double *y1 = a.y1 + b * a.y1_stride;
+    const int n = a.n, k = a.k;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const int jx = J * 8 + (lane & 3) * 2 + e;
+        double v = 0.0;
+        if (jx < n) v = y1[jx];
+        else if (jx < ny) v = a.y2 ? a.y2[s * k + (jx - n)] : y1[jx];
+        if (e) c1 = v; else c0 = v;
+    }
+}
+
+// Factor the 64x64 diagonal block held in s_C (lower tiles, accumulator/row-major layout) by ONE warp:
+// right-looking over its 8 tile columns. Writes L tiles (operand layout) to s_L and to the factor, inverse
+// diagonal tiles to s_W (and the factor's W store). Returns 0 or the 1-based index of the first bad pivot.
+__device__ __forceinline__ int factor_diag_block(double *s_C, double *s_L, double *s_W, double *Lb, double *Wb, int c0,
+                                                 int q, int n, int m, int lane, double &ld_n, double &ld_m)
+{
+    int info = 0;
+    for (int j = 0; j < kBlk; ++j) {
+        const int Jg = c0 + j;
+        double2 cj = *reinterpret_cast<double2 *>(s_C + (tri(j) + j) * 64 + lane * 2);
+        double d0 = cj.x, d1 = cj.y, w0, w1, piv[8];
+        const int bad = chol8_inv(d0, d1, w0, w1, lane, q - Jg * 8, piv);
+        if (bad && !info) info = Jg * 8 + bad;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            const int row = Jg * 8 + p;
+            if (row < m) {
+                const double l = 0.5 * log(piv[p]);
+                ld_m += l;
+                if (row < n) ld_n += l;
+            }
+        }
+        double *ltile = s_L + (tri(j) + j) * 64;
+        store_op(ltile, d0, d1, lane);
+        store_op(Lb + ((size_t)tri(Jg) + Jg) * 64, d0, d1, lane);
+        store_op(s_W + j * 64, w0, w1, lane);
+        if (Wb) store_op(Wb + (size_t)Jg * 64, w0, w1, lane);
+        __syncwarp();
+        const double2 ib = *reinterpret_cast<double2 *>(s_W + j * 64 + lane * 2);
+        // column trsm: X_aj = C_aj W_jj^T
+        for (int a = j + 1; a < kBlk; ++a) {
+            const double2 c = *reinterpret_cast<double2 *>(s_C + (tri(a) + j) * 64 + lane * 2);
+            const double2 fr = acc_to_frag(c.x, c.y, lane);
+            double x0 = 0.0, x1 = 0.0;
+            dmma(x0, x1, fr.x, ib.x);
+            dmma(x0, x1, fr.y, ib.y);
+            store_op(s_L + (tri(a) + j) * 64, x0, x1, lane);
+            store_op(Lb + ((size_t)tri(c0 + a) + Jg) * 64, x0, x1, lane);
+        }
+        __syncwarp();
+        // trailing update inside the block: C_ab -= X_aj X_bj^T
+        for (int a = j + 1; a < kBlk; ++a) {
+            double2 af = *reinterpret_cast<double2 *>(s_L + (tri(a) + j) * 64 + lane * 2);
+            af.x = -af.x; af.y = -af.y;
+            for (int b = j + 1; b <= a; ++b) {
+                const double2 bf = *reinterpret_cast<double2 *>(s_L + (tri(b) + j) * 64 + lane * 2);
+                double2 *cp = reinterpret_cast<double2 *>(s_C + (tri(a) + b) * 64 + lane * 2);
+                double2 c = *cp;
+                dmma(c.x, c.y, af.x, bf.x);
+                dmma(c.x, c.y, af.y, bf.y);
+                *cp = c;
+            }
+        }
+        __syncwarp();
+    }
+    return info;
+}
+
+__global__ void __launch_bounds__(kThreads, 2) chol_large_kernel(const FusedArgs a, const LargeLayout lay)
+{
+    extern __shared__ __align__(16) double smem[];
+    __shared__ TreeProgram tp;
+    __shared__ int s_info;
+    __shared__ long long s_next;
+    __shared__ int s_queue, s_diagdone;
+    __shared__ volatile int s_flag;
+    __shared__ double s_ld[2];
+    __shared__ double s_red[4][kWarps];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = a.n, k = a.k, h = a.h, m = n + k, q = m + h;
+    const int ntp = lay.ntp, Q = ntp * 8, yrow = lay.yrow;
+    const bool have_y2 = (a.y2 != nullptr) || k == 0;
+    const int ny = have_y2 ? m : n;
+
+    double *s_C = smem;                    // 36 tiles, accumulator layout
+    double *s_L = s_C + 36 * 64;           // 36 tiles, operand layout
+    double *s_W = s_L + 36 * 64;           // 8 tiles, operand layout
+    char *aux_s = reinterpret_cast<char *>(s_W + kBlk * 64);
+    const Setup su = aux_pointers(lay, aux_s);
+
+    for (int i = tid; i < Q; i += kThreads) {
+        su.tt[i] = i < q ? a.t[i] : 0.0;
+        su.gg[i] = (a.g && i < q) ? a.g[i] : 0;
+    }
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_next = (long long)atomicAdd(lay.work_counter, 1ull);
+        __syncthreads();
+        const int64_t b = s_next;
+        if (b >= a.B) break;
+        const int64_t s = b / a.P;
+        const int p = (int)(b % a.P);
+        const size_t slot = lay.keep ? (size_t)b : (size_t)blockIdx.x;
+        double *Lb = lay.L + slot * lay.L_stride;
+        double *Wb = lay.W ? lay.W + slot * lay.W_stride : nullptr;
+
+        if (tid == 0) { s_info = 0; s_flag = 0; s_queue = 0; s_diagdone = 0; s_ld[0] = 0.0; s_ld[1] = 0.0; }
+        instance_setup(tp, a, su, s, p, Q, tid);
+        if (tp.error) {
+            if (tid == 0) {
+                a.info[b] = tp.error;
+                if (a.logml_n) a.logml_n[b] = nan("");
+                if (a.logml_m) a.logml_m[b] = nan("");
+                if (a.logw) a.logw[b] = nan("");
+            }
+            continue;
+        }
+        GramCtx gc;
+        gc.cx.th = su.th; gc.cx.tt = su.tt; gc.cx.tab = su.tab; gc.cx.sig = su.sig;
+        gc.cx.step = a.step; gc.cx.G = a.G; gc.cx.Q = Q; gc.cx.grid = a.g != nullptr;
+        gc.gg = su.gg; gc.q = q; gc.m = m;
+        {
+            const double nz = a.noise[s * a.noise_stride_k + p];
+            gc.d_lo = nz + a.jitter;
+            gc.d_hi = (a.noise_pred >= 0.0 ? a.noise_pred : nz) + a.jitter;
+        }
+        gc.single_table = (tp.clen == 1 && tp.cop[0] == OP_TABLE);
+
+        const int nbc = ntp / kBlk;
+        for (int Jb = 0; Jb < nbc; ++Jb) {
+            const int c0 = Jb * kBlk;
+            const int nitems = kBlk + (ntp - c0 - kBlk) + 1;   // diagonal-block rows, rows below, the y row
+            for (;;) {
+                int item = 0;
+                if (lane == 0) item = atomicAdd(&s_queue, 1);
+                item = __shfl_sync(kFull, item, 0);
+                if (item >= nitems) break;
+                const bool diag = item < kBlk;
+                const int arow = kBlk - 1 - item;                       // longest diagonal rows first
+                const bool is_y = (item == nitems - 1);
+                const int I = diag ? c0 + arow : (is_y ? yrow : c0 + item);
+                const int NC = diag ? arow + 1 : kBlk;
+
+                // ---- sum_{P < c0} L_IP L_{c0+b,P}^T for the NC column tiles ------------------------
+                double acc[kBlk][2];
+#pragma unroll
+                for (int bb = 0; bb < kBlk; ++bb) { acc[bb][0] = 0.0; acc[bb][1] = 0.0; }
+                {
+                    const double *arowp = Lb + (size_t)tri(I) * 64 + lane * 2;
+                    const double *browp = Lb + (size_t)tri(c0) * 64 + lane * 2;
+                    if (NC == kBlk) {
+#pragma unroll 2
+                        for (int P = 0; P < c0; ++P) {
+                            const double2 af = ldg128_stream(arowp + (size_t)P * 64);
+#pragma unroll
+                            for (int bb = 0; bb < kBlk; ++bb) {
+                                // tile (c0+bb, P) sits tri(c0+bb) - tri(c0) = bb*c0 + tri(bb) tiles after (c0, P)
+                                const double2 bf = ldg128(browp + ((size_t)(bb * c0 + ((bb * (bb + 1)) >> 1)) + P) * 64);
+                                dmma(acc[bb][0], acc[bb][1], af.x, bf.x);
+                                dmma(acc[bb][0], acc[bb][1], af.y, bf.y);
+                            }
+                        }
+                    } else {
+                        for (int P = 0; P < c0; ++P) {
+                            const double2 af = ldg128(arowp + (size_t)P * 64);
+#pragma unroll
+                            for (int bb = 0; bb < kBlk; ++bb) {
+                                if (bb < NC) {
+                                    const double2 bf = ldg128(browp + ((size_t)(bb * c0 + ((bb * (bb + 1)) >> 1)) + P) * 64);
+                                    dmma(acc[bb][0], acc[bb][1], af.x, bf.x);
+                                    dmma(acc[bb][0], acc[bb][1], af.y, bf.y);
+                                }
+                            }
+                        }
+                    }
+                }
+                // ---- C_b = A(I, c0+b) - acc_b --------------------------------------------------------
+                if (is_y) {
+#pragma unroll
+                    for (int bb = 0; bb < kBlk; ++bb) {
+                        double y0, y1v;
+                        y_tile(a, b, s, c0 + bb, ny, lane, y0, y1v);
+                        acc[bb][0] = y0 - acc[bb][0];
+                        acc[bb][1] = y1v - acc[bb][1];
+                    }
+                } else {
+#pragma unroll
+                    for (int bb = 0; bb < kBlk; bb += 2) {
+                        if (bb < NC) {
+                            double out[4];
+                            gram_pair(tp, gc, I, c0 + bb, c0 + bb + 1, lane, out);
+                            acc[bb][0] = out[0] - acc[bb][0];
+                            acc[bb][1] = out[1] - acc[bb][1];
+                            acc[bb + 1][0] = out[2] - acc[bb + 1][0];
+                            acc[bb + 1][1] = out[3] - acc[bb + 1][1];
+                        }
+                    }
+                }
+                if (diag) {
+#pragma unroll
+                    for (int bb = 0; bb < kBlk; ++bb)
+                        if (bb < NC)
+                            *reinterpret_cast<double2 *>(s_C + (tri(arow) + bb) * 64 + lane * 2) = make_double2(acc[bb][0], acc[bb][1]);
+                    __threadfence_block();
+                    __syncwarp();
+                    int done = 0;
+                    if (lane == 0) done = atomicAdd(&s_diagdone, 1);
+                    done = __shfl_sync(kFull, done, 0);
+                    if (done == kBlk - 1) {
+                        // last diagonal row in: this warp factors the block while the others run ahead
+                        __threadfence_block();
+                        double ld_n = 0.0, ld_m = 0.0;
+                        const int bad = factor_diag_block(s_C, s_L, s_W, Lb, Wb, c0, q, n, m, lane, ld_n, ld_m);
+                        if (lane == 0) {
+                            if (bad && !s_info) s_info = bad;
+                            s_ld[0] += ld_n; s_ld[1] += ld_m;
+                        }
+                        __threadfence_block();
+                        __syncwarp();
+                        if (lane == 0) s_flag = Jb + 1;
+                    }
+                    continue;
+                }
+                // ---- wait for the diagonal block, then the in-register triangular solve -------------------
+                while (s_flag < Jb + 1) __nanosleep(64);
+                __threadfence_block();
+                __syncwarp();
+                double2 xa[kBlk];
+#pragma unroll
+                for (int bb = 0; bb < kBlk; ++bb) {
+#pragma unroll
+                    for (int aa = 0; aa < bb; ++aa) {
+                        const double2 bf = *reinterpret_cast<const double2 *>(s_L + (tri(bb) + aa) * 64 + lane * 2);
+                        dmma(acc[bb][0], acc[bb][1], xa[aa].x, bf.x);
+                        dmma(acc[bb][0], acc[bb][1], xa[aa].y, bf.y);
+                    }
+                    const double2 fr = acc_to_frag(acc[bb][0], acc[bb][1], lane);
+                    const double2 ib = *reinterpret_cast<const double2 *>(s_W + bb * 64 + lane * 2);
+                    double x0 = 0.0, x1 = 0.0;
+                    dmma(x0, x1, fr.x, ib.x);
+                    dmma(x0, x1, fr.y, ib.y);
+                    store_op(Lb + ((size_t)tri(I) + c0 + bb) * 64, x0, x1, lane);
+                    if (bb + 1 < kBlk) {
+                        const double2 xf = acc_to_frag(x0, x1, lane);
+                        xa[bb] = make_double2(-xf.x, -xf.y);
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid == 0) { s_queue = 0; s_diagdone = 0; }
+            __syncthreads();
+            if (s_info) break;
+        }
+
+        if (s_info) {
+            if (tid == 0) {
+                a.info[b] = s_info;
+                if (a.logml_n) a.logml_n[b] = nan("");
+                if (a.logml_m) a.logml_m[b] = nan("");
+                if (a.logw) a.logw[b] = nan("");
+            }
+            continue;
+        }
+
+        auto Lel = [&](int i, int j) {
+            return Lb[((size_t)tri(i >> 3) + (j >> 3)) * 64 + op_idx(i & 7, j & 7)];
+        };
+        auto zel = [&](int r) { return Lb[((size_t)tri(yrow) + (r >> 3)) * 64 + op_idx(0, r & 7)]; };
+
+        // ---- logML(n), logML(m) ----------------------------------------------------------------------
+        double qd_n = 0, qd_m = 0;
+        for (int r = tid; r < ny; r += kThreads) {
+            const double zz = zel(r);
+            qd_m = fma(zz, zz, qd_m);
+            if (r < n) qd_n = fma(zz, zz, qd_n);
+        }
+        qd_n = warp_sum(qd_n); qd_m = warp_sum(qd_m);
+        if (lane == 0) { s_red[0][warp] = qd_n; s_red[1][warp] = qd_m; }
+        __syncthreads();
+        if (tid == 0) {
+            double r2 = 0, r3 = 0;
+            for (int w = 0; w < kWarps; ++w) { r2 += s_red[0][w]; r3 += s_red[1][w]; }
+            const double log2pi = 1.8378770664093454835606594728112;
+            double lmn = -0.5 * ((double)n * log2pi + 2.0 * s_ld[0] + r2);
+            double lmm = have_y2 ? -0.5 * ((double)m * log2pi + 2.0 * s_ld[1] + r3) : nan("");
+            if (a.logml_n) a.logml_n[b] = lmn;
+            if (a.logml_m) a.logml_m[b] = lmm;
+            if (a.logw) a.logw[b] = (a.logw0 ? a.logw0[p] : 0.0) + (lmm - lmn);
+            a.info[b] = 0;
+        }
+
+        // ---- predictive moments / fast-path tail blocks ------------------------------------------------
+        const int kh = k + h;
+        if (a.mu && have_y2) {
+            for (int r = warp; r < h; r += kWarps) {
+                double accv = 0.0;
+                for (int cix = lane; cix < m; cix += 32) accv = fma(Lel(m + r, cix), zel(cix), accv);
+                accv = warp_sum(accv);
+                if (lane == 0) a.mu[b * h + r] = (accv - a.yb) / a.ya;
+            }
+        }
+        if (a.L33) {
+            for (int e = tid; e < h * h; e += kThreads) {
+                int r = e / h, cix = e - r * h;
+                a.L33[b * h * h + e] = cix <= r ? Lel(m + r, m + cix) / a.ya : 0.0;
+            }
+        }
+        if (a.proj) {
+            for (int r = warp; r < kh; r += kWarps) {
+                double accv = 0.0;
+                for (int cix = lane; cix < n; cix += 32) accv = fma(Lel(n + r, cix), zel(cix), accv);
+                accv = warp_sum(accv);
+                if (lane == 0) a.proj[b * kh + r] = accv;
+            }
+        }
+        if (a.Ltail) {
+            for (int e = tid; e < kh * kh; e += kThreads) {
+                int r = e / kh, cix = e - r * kh;
+                a.Ltail[b * kh * kh + e] = cix <= r ? Lel(n + r, n + cix) : 0.0;
+            }
+        }
+    }
+}
+
+// ---- rank-append ---------------------------------------------------------------------------------------
+// Extends each particle's stored factor from n_old to n_new = a.n points in place. Tile rows
+// I0 = floor(n_old / 8) .. nt-1 are (re)computed up-looking in groups of <= 8 tile rows:
+//   X_J = (A(I, J) - sum_{P<J} X_P L_JP^T) W_J^T   for J < I,   chol8 of the remainder for J == I,
+// and the same recurrence gives the new entries of z = L^-1 y. The sum over P is split across the 8
+// warps (warp w takes P = w, w+8, ...; each stored tile of L is read exactly once per group, in storage
+// order), reduced through shared memory, and row r of the group is finished by warp r.
+struct AppendLayout {
+    LargeLayout base;
+    int n_old;
+    double *logml;       // [P] in/out: running log marginal likelihood of the stored factor
+    double *dlogml;      // [P] out
+};
+
+__global__ void __launch_bounds__(kThreads, 2) rank_append_kernel(const FusedArgs a, const AppendLayout al)
+{
+    extern __shared__ __align__(16) double smem[];
+    __shared__ TreeProgram tp;
+    __shared__ int s_info;
+    __shared__ double s_acc[2];   // sum log L_ii, sum z_i^2 over the new rows
+
+    const LargeLayout &lay = al.base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = a.n, q = n;                 // append works on observed points only (k = h = 0)
+    const int nt = lay.nt, Q = lay.ntp * 8, yrow = lay.yrow;
+    const int n_old = al.n_old;
+    const int I0 = n_old >> 3;
+
+    double *s_part = smem;                               // [kWarps][9] partial tiles, accumulator layout
+    char *aux_s = reinterpret_cast<char *>(s_part + kWarps * 9 * 64);
+    const Setup su = aux_pointers(lay, aux_s);
+
+    for (int i = tid; i < Q; i += kThreads) {
+        su.tt[i] = i < q ? a.t[i] : 0.0;
+        su.gg[i] = (a.g && i < q) ? a.g[i] : 0;
+    }
+    __syncthreads();
+
+    for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x) {
+        __syncthreads();
+        const int p = (int)b;
+        double *Lb = lay.L + (size_t)b * lay.L_stride;
+        double *Wb = lay.W + (size_t)b * lay.W_stride;
+        if (tid == 0) { s_info = 0; s_acc[0] = 0.0; s_acc[1] = 0.0; }
+        instance_setup(tp, a, su, 0, p, Q, tid);
+        if (tp.error) {
+            if (tid == 0) { a.info[b] = tp.error; if (al.dlogml) al.dlogml[b] = nan(""); }
+            continue;
+        }
+        GramCtx gc;
+        gc.cx.th = su.th; gc.cx.tt = su.tt; gc.cx.tab = su.tab; gc.cx.sig = su.sig;
+        gc.cx.step = a.step; gc.cx.G = a.G; gc.cx.Q = Q; gc.cx.grid = a.g != nullptr;
+        gc.gg = su.gg; gc.q = q; gc.m = q;
+        gc.d_lo = gc.d_hi = a.noise[p] + a.jitter;
+        gc.single_table = (tp.clen == 1 && tp.cop[0] == OP_TABLE);
+
+        for (int g0 = I0; g0 < nt && !s_info; g0 += kBlk) {
+            const int R = min(kBlk, nt - g0);           // new tile rows g0 .. g0+R-1; row index R = the y row
+            const int Jend = g0 + R;                    // sweep J = 0 .. Jend-1
+            for (int J = 0; J < Jend; ++J) {
+                // rows active at this J: new rows r with g0 + r >= J, and the y row once J >= g0
+                const int r_lo = J > g0 ? J - g0 : 0;
+                const bool y_on = J >= g0;   // z of this group's rows
+                // ---- split-K partial sums ------------------------------------------------------------
+                double acc[kBlk + 1][2];
+#pragma unroll
+                for (int r = 0; r <= kBlk; ++r) { acc[r][0] = 0.0; acc[r][1] = 0.0; }
+                const double *lrow = Lb + (size_t)tri(J) * 64 + lane * 2;
+                for (int P = warp; P < J; P += kWarps) {
+                    const double2 bf = ldg128_stream(lrow + (size_t)P * 64);
+#pragma unroll
+                    for (int r = 0; r < kBlk; ++r) {
+                        if (r >= r_lo && r < R) {
+                            const double2 af = ldg128(Lb + ((size_t)tri(g0 + r) + P) * 64 + lane * 2);
+                            dmma(acc[r][0], acc[r][1], af.x, bf.x);
+                            dmma(acc[r][0], acc[r][1], af.y, bf.y);
+                        }
+                    }
+                    if (y_on) {
+                        const double2 af = ldg128(Lb + ((size_t)tri(yrow) + P) * 64 + lane * 2);
+                        dmma(acc[kBlk][0], acc[kBlk][1], af.x, bf.x);
+                        dmma(acc[kBlk][0], acc[kBlk][1], af.y, bf.y);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r <= kBlk; ++r)
+                    *reinterpret_cast<double2 *>(s_part + (warp * 9 + r) * 64 + lane * 2) = make_double2(acc[r][0], acc[r][1]);
+                __syncthreads();
+                // ---- the diagonal tile first (row J - g0 when J is a new row): every other row needs W_J --
+                const bool J_new = J >= g0;
+                if (J_new && warp == 0) {
+                    const int r = J - g0;
+                    double c0v = 0.0, c1v = 0.0;
+                    for (int w = 0; w < kWarps; ++w) {
+                        const double2 v = *reinterpret_cast<double2 *>(s_part + (w * 9 + r) * 64 + lane * 2);
+                        c0v += v.x; c1v += v.y;
+                    }
+                    double out[4];
+                    gram_pair(tp, gc, J, J, J, lane, out);
+                    double d0 = out[0] - c0v, d1 = out[1] - c1v, w0, w1, piv[8];
+                    const int bad = chol8_inv(d0, d1, w0, w1, lane, q - J * 8, piv);
+                    if (bad && lane == 0 && !s_info) s_info = J * 8 + bad;
+                    double ld = 0.0;
+#pragma unroll
+                    for (int pp = 0; pp < 8; ++pp) {
+                        const int row = J * 8 + pp;
+                        if (row >= n_old && row < n) ld += 0.5 * log(piv[pp]);
+                    }
+                    if (lane == 0) s_acc[0] += ld;
+                    store_op(Lb + ((size_t)tri(J) + J) * 64, d0, d1, lane);
+                    store_op(Wb + (size_t)J * 64, w0, w1, lane);
+                }
+                if (J_new) { __threadfence_block(); __syncthreads(); }
+                // ---- finish the off-diagonal rows: warp r handles new row r, warp (R % 8 ...) the y row ------
+                const double2 ib = ldg128(Wb + (size_t)J * 64 + lane * 2);
+                for (int r = warp; r <= kBlk; r += kWarps) {
+                    const bool isy = (r == kBlk);
+                    if (isy ? !y_on : !(r < R && g0 + r > J)) continue;
+                    double c0v = 0.0, c1v = 0.0;
+                    for (int w = 0; w < kWarps; ++w) {
+                        const double2 v = *reinterpret_cast<double2 *>(s_part + (w * 9 + r) * 64 + lane * 2);
+                        c0v += v.x; c1v += v.y;
+                    }
+                    double g0v, g1v;
+                    if (isy) {
+                        y_tile(a, 0, 0, J, n, lane, g0v, g1v);
+                    } else {
+                        double out[4];
+                        gram_pair(tp, gc, g0 + r, J, J, lane, out);
+                        g0v = out[0]; g1v = out[1];
+                    }
+                    const double2 fr = acc_to_frag(g0v - c0v, g1v - c1v, lane);
+                    double x0 = 0.0, x1 = 0.0;
+                    dmma(x0, x1, fr.x, ib.x);
+                    dmma(x0, x1, fr.y, ib.y);
+                    const int I = isy ? yrow : g0 + r;
+                    store_op(Lb + ((size_t)tri(I) + J) * 64, x0, x1, lane);
+                    if (isy && (lane >> 2) == 0) {
+                        // new z entries: columns J*8 + 2*lj, +1
+                        double zz = 0.0;
+                        const int c = J * 8 + (lane & 3) * 2;
+                        if (c >= n_old && c < n) zz = fma(x0, x0, zz);
+                        if (c + 1 >= n_old && c + 1 < n) zz = fma(x1, x1, zz);
+                        zz += __shfl_xor_sync(0x0000000fu, zz, 1);
+                        zz += __shfl_xor_sync(0x0000000fu, zz, 2);
+                        if (lane == 0) s_acc[1] += zz;
+                    }
+                }
+                __threadfence_block();
+                __syncthreads();
+            }
+        }
+        if (tid == 0) {
+            const double log2pi = 1.8378770664093454835606594728112;
+            if (s_info) {
+                a.info[b] = s_info;
+                if (al.dlogml) al.dlogml[b] = nan("");
+                if (al.logml) al.logml[b] = nan("");
+            } else {
+                const double d = -0.5 * ((double)(n - n_old) * log2pi + 2.0 * s_acc[0] + s_acc[1]);
+                a.info[b] = 0;
+                if (al.dlogml) al.dlogml[b] = d;
+                if (al.logml) al.logml[b] += d;
+            }
+        }
+    }
+}
+
+void large_aux_sizes(int Q, int G, int ntheta_cap, int ntab_cap, int ncp_cap, size_t (&sz)[5])
+{
+    auto up = [](size_t x) { return (x + 15) & ~size_t(15); };
+    sz[0] = up((size_t)std::max(ntheta_cap, 1) * sizeof(double));
+    sz[1] = up((size_t)Q * sizeof(int));
+    sz[2] = up((size_t)Q * sizeof(double));
+    sz[3] = up((size_t)ncp_cap * Q * sizeof(double));
+    sz[4] = up((size_t)ntab_cap * (G > 0 ? G : 0) * sizeof(double));
+}
+
+}  // namespace
+
+int large_max_q() { return 4096; }
+
+LargePlan plan_large(int q, int q_cap, int G, int ntheta_cap, int ntab_cap, int ncp_cap, int smem_per_sm, bool append)
+{
+    LargePlan pl{};
+    pl.nt = (q + 7) / 8;
+    pl.ntp = (pl.nt + kBlk - 1) / kBlk * kBlk;
+    const int nt_cap = (std::max(q, q_cap) + 7) / 8;
+    pl.ntp_cap = (nt_cap + kBlk - 1) / kBlk * kBlk;
+    pl.yrow = pl.ntp_cap;
+    pl.L_stride = ((size_t)pl.ntp_cap * (pl.ntp_cap + 1) / 2 + pl.ntp_cap) * 64;
+    const int Q = pl.ntp * 8;
+    size_t base = append ? (size_t)(kWarps * 9) * 64 * sizeof(double) : (size_t)(36 + 36 + kBlk) * 64 * sizeof(double);
+    size_t sz[5];
+    large_aux_sizes(Q, G, ntheta_cap, ntab_cap, ncp_cap, sz);
+    const size_t static_smem = 2048 + 1024;
+    const size_t budget = (size_t)smem_per_sm / 2 - static_smem;   // keep two CTAs per SM
+    size_t s_off = 0, g_off = 0;
+    const int order[5] = {0, 1, 4, 3, 2};
+    for (int oi = 0; oi < 5; ++oi) {
+        int i = order[oi];
+        if (base + s_off + sz[i] <= budget) { pl.aux_smem[i] = 1; pl.aux_off[i] = (int)s_off; s_off += sz[i]; }
+        else { pl.aux_smem[i] = 0; pl.aux_off[i] = (int)g_off; g_off += sz[i]; }
+    }
+    pl.smem_bytes = base + s_off;
+    pl.scratch_stride = (int)((g_off + 255) & ~size_t(255));
+    pl.ok = q <= large_max_q();
+    return pl;
+}
+
+static LargeLayout make_layout(const LargePlan &pl, char *scratch, double *L, int keep, double *W,
+                               unsigned long long *work_counter)
+{
+    LargeLayout lay{};
+    lay.nt = pl.nt; lay.ntp = pl.ntp; lay.yrow = pl.yrow;
+    for (int i = 0; i < 5; ++i) { lay.aux_off[i] = pl.aux_off[i]; lay.aux_smem[i] = pl.aux_smem[i]; }
+    lay.scratch_stride = pl.scratch_stride;
+    lay.scratch = scratch;
+    lay.L = L; lay.L_stride = pl.L_stride; lay.keep = keep;
+    lay.W = W; lay.W_stride = (size_t)pl.ntp_cap * 64;
+    lay.work_counter = work_counter;
+    return lay;
+}
+
+int large_grid(const LargePlan &pl, int64_t B, int num_sms, bool append)
+{
+    int per_sm = 0;
+    const void *fn = append ? (const void *)rank_append_kernel : (const void *)chol_large_kernel;
+    cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, pl.smem_bytes) != cudaSuccess || per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 1;
+    }
+    return (int)std::min<int64_t>((int64_t)per_sm * num_sms, B);
+}
+
+cudaError_t launch_chol_large(const FusedArgs &a, const LargePlan &pl, char *scratch, double *L, int keep, double *W,
+                              unsigned long long *work_counter, int grid, cudaStream_t stream)
+{
+    cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return e;
+    LargeLayout lay = make_layout(pl, scratch, L, keep, W, work_counter);
+    e = cudaFuncSetAttribute(chol_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
+    if (e != cudaSuccess) return e;
+    chol_large_kernel<<<grid, kThreads, pl.smem_bytes, stream>>>(a, lay);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rank_append(const FusedArgs &a, const LargePlan &pl, char *scratch, double *L, double *W,
+                               int n_old, double *logml, double *dlogml, int grid, cudaStream_t stream)
+{
+    AppendLayout al{};
+    al.base = make_layout(pl, scratch, L, 1, W, nullptr);
+    al.n_old = n_old; al.logml = logml; al.dlogml = dlogml;
+    cudaError_t e = cudaFuncSetAttribute(rank_append_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
+    if (e != cudaSuccess) return e;
+    rank_append_kernel<<<grid, kThreads, pl.smem_bytes, stream>>>(a, al);
+    return cudaGetLastError();
+}
+
+}  // namespace nagp

@@ -151,6 +151,39 @@ class Engine:
         self._check(rc, raise_posdef=check)
         return f
 
+    def factor_store_large(self, ens: FlatEnsemble, t, y, capacity=None, g=None, step=0.0,
+                           check: bool = True) -> "Factor":
+        """Appendable whole-factor store for long series (`nagp_factor_store_large`)."""
+        P = ens.size
+        n = len(t)
+        capacity = n if capacity is None else int(capacity)
+        logml = np.empty(P)
+        info = np.zeros(P, np.int32)
+        keep = [_ptr(ens.prog), _ptr(ens.prog_off), _ptr(ens.theta), _ptr(ens.theta_off), _ptr(ens.noise),
+                _ptr(np.asarray(t), np.float64), _ptr(None if g is None else np.asarray(g), np.int32),
+                _ptr(np.asarray(y), np.float64)]
+        p = [x[0] for x in keep]
+        handle = C.c_void_p()
+        rc = self._lib.nagp_factor_store_large(self._ctx, P, p[0], p[1], p[2], p[3], p[4], n, capacity, p[5], p[6],
+                                               step, p[7], C.byref(handle), logml.ctypes.data, info.ctypes.data)
+        f = Factor(self, handle, P, n, 0, 0, logml, info)
+        self._check(rc, raise_posdef=check)
+        return f
+
+    def factor_append(self, factor: "Factor", t_new, y_new, g_new=None, check: bool = True):
+        """Rank-append `len(t_new)` points in place; returns (dlogml[P], logml[P], info[P])."""
+        kn_ = len(t_new)
+        dl, lm = np.empty(factor.P), np.empty(factor.P)
+        info = np.zeros(factor.P, np.int32)
+        keep = [_ptr(np.asarray(t_new), np.float64), _ptr(None if g_new is None else np.asarray(g_new), np.int32),
+                _ptr(np.asarray(y_new), np.float64)]
+        rc = self._lib.nagp_factor_append(self._ctx, factor._h, kn_, keep[0][0], keep[1][0], keep[2][0],
+                                          dl.ctypes.data, lm.ctypes.data, info.ctypes.data)
+        self._check(rc, raise_posdef=check)
+        factor.n = int(self._lib.nagp_factor_size(factor._h))
+        factor.logml_n = lm
+        return dl, lm, info
+
     def append(self, factor: "Factor", y2, logw=None, mu=None, want_mu: bool = True):
         K = y2.shape[0]
         logw = np.empty((K, factor.P)) if logw is None else logw
