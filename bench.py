@@ -139,6 +139,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-sanity", action="store_true", help="timing experiments with deliberately wrong kernels")
     ap.add_argument("--only-value", action="store_true", help="time only the device-resident step")
+    ap.add_argument("--no-micro", action="store_true", help="skip the configs[2]/configs[4] micro-benchmarks")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -291,6 +292,63 @@ def main():
     ms_fast = timed(step_fast_device, args.steps, args.warmup)
     ms_fast_e2e = timed(step_fast_e2e, args.steps, args.warmup)
 
+    # ---- secondary metric (BASELINE configs[2]): batched logML evals/sec, 1024 particles x n=512 ----------
+    def micro_logml():
+        from nowcastautogp_b200 import synthetic as syn
+        Bm, nm = 1024, 512
+        wm = syn.make_workload(nm, 0, 0, 1, Bm, seed=20261018 + 3 + 1000 * rank, max_depth=4, period=365.0)
+        ens_m = FlatEnsemble(wm.ens.prog, wm.ens.prog_off, to_dev(wm.ens.theta), wm.ens.theta_off, to_dev(wm.ens.noise))
+        d_y, d_lm = to_dev(wm.y1), torch.empty(Bm, dtype=torch.float64, device=dev)
+        d_inf = torch.zeros(Bm, dtype=torch.int32, device=dev)
+        tm, gm = wm.t[:nm], wm.g[:nm]
+
+        def run():
+            eng.logml_batch(ens_m, tm, d_y, g=gm, step=wm.step, logml=d_lm, info=d_inf)
+        ms = timed(run, max(3, args.steps // 2), 3)
+        ok_ = int(d_inf.abs().max().item()) == 0 and bool(torch.isfinite(d_lm).all().item())
+        fl_ = Bm * (nm ** 3 / 3.0 + 2.0 * nm * nm)
+        return {"what": "BASELINE configs[2]: 1024 particles, compositional kernels, n=512, Gram+Cholesky+logdet "
+                        "(chol_large_kernel, factor in HBM/L2, Gram never stored)",
+                "value": Bm * world / (ms * 1e-3), "unit": "logML evals/s", "ms_per_step": ms, "ok": ok_,
+                "roofline": {"bound": "tensor", "achieved": fl_ / (ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+                             "flops_per_launch": fl_}}
+
+    # ---- BASELINE configs[4]: daily series n=2048, 256 particles, incremental add_data! (rank-append) -------
+    def micro_append():
+        from nowcastautogp_b200 import synthetic as syn
+        Pa, na, ka = 256, 2048, 1
+        wa = syn.make_workload(na + 8 * ka, 0, 0, 1, Pa, seed=20261018 + 5 + 1000 * rank, max_depth=4, period=365.0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        f = eng.factor_store_large(wa.ens, wa.t[:na], wa.y1[:na], capacity=na + 8 * ka, g=wa.g[:na], step=wa.step,
+                                   check=False)
+        e1.record(stream); e1.synchronize()
+        ms_store = e0.elapsed_time(e1)
+        ok_ = bool((f.info == 0).all())
+        tms = []
+        cur = na
+        for i in range(8):
+            flush.fill_(1)
+            e0.record(stream)
+            eng.factor_append(f, wa.t[cur:cur + ka], wa.y1[cur:cur + ka], g_new=wa.g[cur:cur + ka], check=False)
+            e1.record(stream); e1.synchronize()
+            tms.append(e0.elapsed_time(e1)); cur += ka
+        f.free()
+        ms_app = float(np.median(tms[1:]))
+        bytes_ = Pa * 4.0 * na * (na + 1)          # the stored factor read once
+        fl_ = Pa * (na ** 3 / 3.0 + 2.0 * na * na)
+        return {"what": "BASELINE configs[4]: daily series n=2048, 256 particles; factor_store_large then in-place "
+                        "rank-append of k=1 point (times include the blocking C-ABI call, host->device of the new point "
+                        "and device->host of dlogml/logml/info)",
+                "ok": ok_, "store_ms": ms_store,
+                "store_roofline": {"bound": "tensor", "achieved": fl_ / (ms_store * 1e-3) / 1e12, "unit": "TFLOP/s"},
+                "append_ms": ms_app, "appends_per_s": Pa * world / (ms_app * 1e-3),
+                "append_roofline": {"bound": "hbm", "achieved": bytes_ / (ms_app * 1e-3) / 1e9, "unit": "GB/s",
+                                    "bytes_per_launch": bytes_}}
+
+    micro = None if args.no_micro else {"logml": micro_logml(), "append": micro_append()}
+
     # sanity: the step produced finite draws and no factorisation failed
     step_device()
     torch.cuda.synchronize()
@@ -329,6 +387,18 @@ def main():
                           "e2e": {"value": draws / (ms_fast_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_fast_e2e,
                                   "h2d_bytes_per_step": int(h2d_fast), "d2h_bytes_per_step": int(d2h)}},
         }
+        if micro is not None:
+            hbm_peak = 6541.8
+            try:
+                hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+            except (OSError, KeyError, ValueError):
+                pass
+            micro["logml"]["roofline"].update(peak=peak_tf, frac=micro["logml"]["roofline"]["achieved"] / peak_tf)
+            micro["append"]["store_roofline"].update(peak=peak_tf, frac=micro["append"]["store_roofline"]["achieved"] / peak_tf)
+            micro["append"]["append_roofline"].update(peak=hbm_peak, peak_source="MEASURED_PEAKS.json hbm_gbs",
+                                                      frac=micro["append"]["append_roofline"]["achieved"] / hbm_peak)
+            line["logml_microbench"] = micro["logml"]
+            line["append_microbench"] = micro["append"]
         if world == 1 and not args.no_cpu_baseline:
             cb, _, _ = cpu_reference(w, theta_k, noise_k, zeta, u, steps=1, warmup=0)
             line["cpu_baseline"] = cb

@@ -1,4 +1,4 @@
-// nagp_fused_v2.cu — tile kernel (variant 2): fused Gram -> blocked Cholesky -> forward solve ->
+// nagp_fused_v3.cu — dataflow tile kernel (variant 3): fused Gram -> blocked Cholesky -> forward solve ->
 // logML / predictive moments, one persistent CTA stream of (scenario, particle) instances.
 //
 // Layout: the lower triangle of the joint q x q Gram lives in shared memory as 8x8 FP64 tiles
@@ -27,7 +27,7 @@
 #include "nagp_tree.cuh"
 #include "nagp_tile.cuh"
 
-#if NAGP_EXP == 8
+#if NAGP_EXP == 9
 __device__ long long g_nagp_dbg[8192];
 extern "C" int nagp_debug_read(long long *out, int count)
 {
@@ -45,6 +45,11 @@ namespace nagp {
 namespace {
 
 constexpr int kMaxTilesPerWarp = 4;   // ceil(nt / kWarps), nt <= 29
+constexpr int kChunk = 4;             // lookahead terms between two polls of the W flag
+#ifndef NAGP_QUIET_SIBLING
+#define NAGP_QUIET_SIBLING 1
+#endif
+constexpr bool kQuietSibling = NAGP_QUIET_SIBLING;   // the warp sharing the owner's scheduler skips lookahead
 
 // DMMA inner loop of the left-looking update for NA tile rows of one warp: per P one 16-byte LDS for
 // the shared B fragment (tile (Jc, P)), and per row one 16-byte LDS + two DMMAs (one per k-chunk, on
@@ -66,7 +71,7 @@ __device__ __forceinline__ void kloop(double (&acc)[kMaxTilesPerWarp][2][2], uin
     }
 }
 
-struct V2Layout {
+struct V3Layout {
     int nt;            // tile rows/cols of the matrix (rows padded to Q = 8 nt)
     int aux_off[5];    // byte offsets of th, gg, tt, sig, tab inside their home
     int aux_smem[5];   // 1: shared memory (offset from aux base), 0: per-CTA global scratch
@@ -75,13 +80,15 @@ struct V2Layout {
     unsigned long long *work_counter;   // dynamic instance scheduler (zeroed before the launch)
 };
 
-__global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a, const V2Layout lay)
+__global__ void __launch_bounds__(kThreads, 2) fused_v3_kernel(const FusedArgs a, const V3Layout lay)
 {
     extern __shared__ __align__(16) double smem[];
     __shared__ TreeProgram tp;
     __shared__ int s_info;
     __shared__ long long s_next;
     __shared__ double s_red[4][kWarps];
+    __shared__ volatile int s_fW;               // number of published inverse diagonal tiles
+    __shared__ volatile int s_fwarp[kWarps];    // per warp: its rows are final through this many tile columns
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = a.n, k = a.k, h = a.h, m = n + k, q = m + h;
@@ -93,7 +100,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
     double *tiles = smem;
     double *yv = tiles + ntiles * 64;
     double *invL = yv + Q;
-    char *aux_s = reinterpret_cast<char *>(invL + 64);
+    char *aux_s = reinterpret_cast<char *>(invL + kWarps * 64);   // invL: ring of 8 inverse tiles
     char *aux_g = lay.scratch + (size_t)blockIdx.x * lay.scratch_stride;
     auto aux = [&](int i) { return (lay.aux_smem[i] ? aux_s : aux_g) + lay.aux_off[i]; };
     double *th = reinterpret_cast<double *>(aux(0));
@@ -123,11 +130,12 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
 
         DBG_G(0);
         if (tid == 0) {
-            s_info = 0;
+            s_info = 0; s_fW = 0;
             if (ntheta > MAX_THETA) tp.error = -3;
             else tree_compile(tp, a.prog + po, (int)plen, (int)ntheta, G > 0 ? a.ntab_cap : 0, a.ncp_cap);
         }
         for (int i = tid; i < ntheta && i < MAX_THETA; i += kThreads) th[i] = theta_g[i];
+        if (tid < kWarps) s_fwarp[tid] = 0;
         __syncthreads();
         if (tp.error) {
             if (tid == 0) {
@@ -278,11 +286,21 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
             }
         };
 
+        // Dataflow schedule: no CTA-wide barrier inside the factorisation. Cross-warp dependencies are
+        //   W_J (inverse of diagonal tile J, ring slot J & 7)      -> s_fW   >= J + 1
+        //   row R final through tile column c (owner warp R & 7)  -> s_fwarp[R & 7] >= c + 1
+        // Each warp walks the columns in order: the owner of J finishes its diagonal tile, factors it and
+        // publishes W_J; everybody else first completes the column-J sums of its own rows, then runs ahead on
+        // column J+1 while polling for W_J, then solves its tiles of column J and publishes its rows.
         for (int J = 0; J < nt; ++J) {
             const bool owner = (warp == (J & (kWarps - 1)));
             const int NA = Ilast >= J ? (Ilast - J) / kWarps + 1 : 0;   // active regular rows (I >= J)
-            // (1) remaining terms of column J, (2) C = A_IJ - sum
             DBG_T(J, 0);
+            // (B) remaining terms of column J: needs row J final through column J-1
+            if (!owner && J > 0) {
+                while (s_fwarp[J & (kWarps - 1)] < J) { }
+                __threadfence_block();
+            }
             accumulate(J, pre_done, J);
             double c[kMaxTilesPerWarp][2], cy[2] = {0.0, 0.0}, d0 = 0.0, d1 = 0.0;
             const uint32_t joff = (uint32_t)J * 512u;
@@ -305,55 +323,55 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
                 yacc[0][0] = yacc[0][1] = yacc[1][0] = yacc[1][1] = 0.0;
             }
             DBG_T(J, 1);
+            const uint32_t wslot = invL_a + (uint32_t)(J & (kWarps - 1)) * 512u;
             if (owner) {
-                // (3) diagonal tile (slot NA-1): factor + invert in registers, publish, release the others
+                // (A) diagonal tile (slot NA-1): factor + invert in registers, publish W_J
                 double w0, w1, piv[8];
-#if NAGP_EXP == 1
-                const int bad = 0; w0 = (lr == 2 * lj) ? 1.0 : 0.0; w1 = (lr == 2 * lj + 1) ? 1.0 : 0.0; (void)piv;
-#else
                 const int bad = chol8_inv(d0, d1, w0, w1, lane, q - J * 8, piv);
-#endif
                 const uint32_t dt = tiles_a + (uint32_t)((tri(J) + J) * 512);
                 sts64(dt + oi0 * 8, d0);
                 sts64(dt + oi1 * 8, d1);
-                sts64(invL_a + oi0 * 8, w0);
-                sts64(invL_a + oi1 * 8, w1);
-                if (bad && lane == 0 && NAGP_EXP == 0) s_info = J * 8 + bad;
+                sts64(wslot + oi0 * 8, w0);
+                sts64(wslot + oi1 * 8, w1);
+                if (bad && lane == 0 && !s_info) s_info = J * 8 + bad;
                 __syncwarp();
-                DBG_T(J, 2);
-                asm volatile("bar.arrive 1, %0;" ::"n"(kThreads) : "memory");
-                pre_done = 0;   // its own lookahead is deferred to the next column (hidden behind that owner)
-            } else if ((warp & 3) == (J & 3)) {
-                // shares its scheduler (and FP64 pipe) with the owner: leave the pipe to the serial
-                // diagonal factorisation and catch up at the top of the next column
+                if (lane == 0) { __threadfence_block(); s_fW = J + 1; }
                 pre_done = 0;
                 DBG_T(J, 2);
-                asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
             } else {
-                // (4) lookahead: column J+1 over P < J
-                if (J + 1 < nt) accumulate(J + 1, 0, J);
-                pre_done = J;
+                // (C) lookahead: column J+1 over the terms that are already final, polling for W_J
+                int la = 0;
+                if (J + 1 < nt && !(kQuietSibling && (warp & 3) == (J & 3))) {
+                    while (la < J && s_fW < J + 1) {
+                        int lim = s_fwarp[(J + 1) & (kWarps - 1)];
+                        lim = lim < J ? lim : J;
+                        if (la >= lim) continue;
+                        __threadfence_block();
+                        const int hi = la + kChunk < lim ? la + kChunk : lim;
+                        accumulate(J + 1, la, hi);
+                        la = hi;
+                    }
+                }
+                pre_done = la;
                 DBG_T(J, 2);
-                asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+                // (D)
+                while (s_fW < J + 1) { }
+                __threadfence_block();
             }
-            // (5) triangular solve of the column: X = C * invL^T, stored in operand layout
+            // (E) triangular solve of the column: X = C * W_J^T, stored in operand layout
             DBG_T(J, 3);
-#if NAGP_EXP == 4
-            if (false) {
-#else
-            if (!s_info) {
-#endif
-                const double2 ib = lds128(invL_a + lane * 16);
+            {
+                const double2 ib = lds128(wslot + lane * 16);
                 const int nsolve = owner ? NA - 1 : NA;   // rows strictly below the diagonal
 #pragma unroll
-                for (int u = 0; u < kMaxTilesPerWarp; ++u) {
-                    if (u < nsolve) {
-                        const double v00 = shfl(c[u][0], cv0), v01 = shfl(c[u][1], cv0);
-                        const double v10 = shfl(c[u][0], cv1), v11 = shfl(c[u][1], cv1);
+                for (int uu = kMaxTilesPerWarp - 1; uu >= 0; --uu) {   // increasing row index: row J+1 first
+                    if (uu < nsolve) {
+                        const double v00 = shfl(c[uu][0], cv0), v01 = shfl(c[uu][1], cv0);
+                        const double v10 = shfl(c[uu][0], cv1), v11 = shfl(c[uu][1], cv1);
                         double x0 = 0.0, x1 = 0.0;
                         dmma(x0, x1, odd ? v01 : v00, ib.x);
                         dmma(x0, x1, odd ? v11 : v10, ib.y);
-                        const uint32_t dt = rowa[u] - lane * 16 + joff;
+                        const uint32_t dt = rowa[uu] - lane * 16 + joff;
                         sts64(dt + oi0 * 8, x0);
                         sts64(dt + oi1 * 8, x1);
                     }
@@ -369,12 +387,13 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
                         sts64(yv_a + (J * 8 + 2 * lj + 1) * 8, x1);
                     }
                 }
+                __syncwarp();
+                if (lane == 0) { __threadfence_block(); s_fwarp[warp] = J + 1; }
             }
             DBG_T(J, 4);
-            __syncthreads();
             DBG_T(J, 5);
-            if (s_info) break;
         }
+        __syncthreads();
         DBG_G(4);
 
         if (s_info) {
@@ -464,17 +483,17 @@ void aux_sizes(int Q, int G, int ntheta_cap, int ntab_cap, int ncp_cap, size_t (
 
 }  // namespace
 
-int fused_v2_max_q() { return 8 * (kMaxTilesPerWarp * kWarps - 1); }
+int fused_v3_max_q() { return 8 * (kMaxTilesPerWarp * kWarps - 1); }
 
 // Plans shared memory for the tile kernel: the tiles, yv and invL are mandatory; the aux arrays go
 // to shared memory in priority order while the CTA stays within `budget` bytes, else to global
 // scratch (L1-resident: a few KB per CTA).
-V2Plan plan_fused_v2(int q, int G, int ntheta_cap, int ntab_cap, int ncp_cap, int smem_optin, int smem_per_sm)
+V2Plan plan_fused_v3(int q, int G, int ntheta_cap, int ntab_cap, int ncp_cap, int smem_optin, int smem_per_sm)
 {
     V2Plan pl{};
     const int nt = (q + 7) / 8, Q = nt * 8;
     pl.nt = nt;
-    size_t base = ((size_t)(nt * (nt + 1) / 2) * 64 + Q + 64) * sizeof(double);
+    size_t base = ((size_t)(nt * (nt + 1) / 2) * 64 + Q + kWarps * 64) * sizeof(double);
     size_t sz[5];
     aux_sizes(Q, G, ntheta_cap, ntab_cap, ncp_cap, sz);
     size_t total_aux = sz[0] + sz[1] + sz[2] + sz[3] + sz[4];
@@ -497,11 +516,11 @@ V2Plan plan_fused_v2(int q, int G, int ntheta_cap, int ntab_cap, int ncp_cap, in
     return pl;
 }
 
-int fused_v2_grid(const V2Plan &pl, int64_t B, int num_sms)
+int fused_v3_grid(const V2Plan &pl, int64_t B, int num_sms)
 {
     int per_sm = 0;
-    cudaFuncSetAttribute(fused_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_v2_kernel, kThreads, pl.smem_bytes) != cudaSuccess ||
+    cudaFuncSetAttribute(fused_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_v3_kernel, kThreads, pl.smem_bytes) != cudaSuccess ||
         per_sm < 1) {
         cudaGetLastError();
         per_sm = 1;
@@ -510,10 +529,10 @@ int fused_v2_grid(const V2Plan &pl, int64_t B, int num_sms)
     return (int)std::min<int64_t>(g, B);
 }
 
-cudaError_t launch_fused_v2(const FusedArgs &a, const V2Plan &pl, char *scratch, unsigned long long *work_counter,
+cudaError_t launch_fused_v3(const FusedArgs &a, const V2Plan &pl, char *scratch, unsigned long long *work_counter,
                             int grid, cudaStream_t stream)
 {
-    V2Layout lay{};
+    V3Layout lay{};
     lay.work_counter = work_counter;
     cudaError_t e0 = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
     if (e0 != cudaSuccess) return e0;
@@ -521,9 +540,9 @@ cudaError_t launch_fused_v2(const FusedArgs &a, const V2Plan &pl, char *scratch,
     for (int i = 0; i < 5; ++i) { lay.aux_off[i] = pl.aux_off[i]; lay.aux_smem[i] = pl.aux_smem[i]; }
     lay.scratch_stride = pl.scratch_stride;
     lay.scratch = scratch;
-    cudaError_t e = cudaFuncSetAttribute(fused_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(fused_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (e != cudaSuccess) return e;
-    fused_v2_kernel<<<grid, kThreads, pl.smem_bytes, stream>>>(a, lay);
+    fused_v3_kernel<<<grid, kThreads, pl.smem_bytes, stream>>>(a, lay);
     return cudaGetLastError();
 }
 

@@ -1,4 +1,4 @@
-// nagp_fused_v2.cu — tile kernel (variant 2): fused Gram -> blocked Cholesky -> forward solve ->
+// nagp_fused_v4.cu — panel-warp dataflow tile kernel (variant 4): fused Gram -> blocked Cholesky -> forward solve ->
 // logML / predictive moments, one persistent CTA stream of (scenario, particle) instances.
 //
 // Layout: the lower triangle of the joint q x q Gram lives in shared memory as 8x8 FP64 tiles
@@ -27,7 +27,7 @@
 #include "nagp_tree.cuh"
 #include "nagp_tile.cuh"
 
-#if NAGP_EXP == 8
+#if NAGP_EXP == 10
 __device__ long long g_nagp_dbg[8192];
 extern "C" int nagp_debug_read(long long *out, int count)
 {
@@ -44,7 +44,17 @@ namespace nagp {
 
 namespace {
 
-constexpr int kMaxTilesPerWarp = 4;   // ceil(nt / kWarps), nt <= 29
+constexpr int kRing = 2;              // inverse-diagonal-tile ring (W_J lives in slot J & 3)
+constexpr int kBulk = 6;              // bulk warps (tile rows are owned I mod 6)
+constexpr int kMaxTilesPerWarp = 5;   // ceil(nt / kBulk), nt <= 29
+constexpr int kChunk = 4;             // lookahead terms between two polls of the W flag
+#ifndef NAGP_CHOL8_SHFL
+#define NAGP_CHOL8_SHFL 0   // 1: shuffle-based diagonal factorisation (chol8_inv) in the panel warp
+#endif
+#ifndef NAGP_QUIET_SIBLING
+#define NAGP_QUIET_SIBLING 1
+#endif
+constexpr bool kQuietSibling = NAGP_QUIET_SIBLING;   // the warp sharing the owner's scheduler skips lookahead
 
 // DMMA inner loop of the left-looking update for NA tile rows of one warp: per P one 16-byte LDS for
 // the shared B fragment (tile (Jc, P)), and per row one 16-byte LDS + two DMMAs (one per k-chunk, on
@@ -66,7 +76,7 @@ __device__ __forceinline__ void kloop(double (&acc)[kMaxTilesPerWarp][2][2], uin
     }
 }
 
-struct V2Layout {
+struct V4Layout {
     int nt;            // tile rows/cols of the matrix (rows padded to Q = 8 nt)
     int aux_off[5];    // byte offsets of th, gg, tt, sig, tab inside their home
     int aux_smem[5];   // 1: shared memory (offset from aux base), 0: per-CTA global scratch
@@ -75,13 +85,17 @@ struct V2Layout {
     unsigned long long *work_counter;   // dynamic instance scheduler (zeroed before the launch)
 };
 
-__global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a, const V2Layout lay)
+__global__ void __launch_bounds__(kThreads, 2) fused_v4_kernel(const FusedArgs a, const V4Layout lay)
 {
     extern __shared__ __align__(16) double smem[];
     __shared__ TreeProgram tp;
     __shared__ int s_info;
     __shared__ long long s_next;
     __shared__ double s_red[4][kWarps];
+    __shared__ volatile int s_fW;               // number of published inverse diagonal tiles
+    __shared__ volatile int s_fwarp[kWarps];    // per warp: its rows are final through this many tile columns
+    __shared__ volatile int s_frow, s_faux;
+    __shared__ volatile int s_fpre[32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = a.n, k = a.k, h = a.h, m = n + k, q = m + h;
@@ -93,7 +107,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
     double *tiles = smem;
     double *yv = tiles + ntiles * 64;
     double *invL = yv + Q;
-    char *aux_s = reinterpret_cast<char *>(invL + 64);
+    char *aux_s = reinterpret_cast<char *>(invL + kRing * 64);   // invL: ring of inverse diagonal tiles
     char *aux_g = lay.scratch + (size_t)blockIdx.x * lay.scratch_stride;
     auto aux = [&](int i) { return (lay.aux_smem[i] ? aux_s : aux_g) + lay.aux_off[i]; };
     double *th = reinterpret_cast<double *>(aux(0));
@@ -123,11 +137,13 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
 
         DBG_G(0);
         if (tid == 0) {
-            s_info = 0;
+            s_info = 0; s_fW = 0; s_frow = 0; s_faux = 0;
             if (ntheta > MAX_THETA) tp.error = -3;
             else tree_compile(tp, a.prog + po, (int)plen, (int)ntheta, G > 0 ? a.ntab_cap : 0, a.ncp_cap);
         }
         for (int i = tid; i < ntheta && i < MAX_THETA; i += kThreads) th[i] = theta_g[i];
+        if (tid < kWarps) s_fwarp[tid] = 0;
+        if (tid < 32) s_fpre[tid] = 0;
         __syncthreads();
         if (tp.error) {
             if (tid == 0) {
@@ -224,157 +240,238 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
         __syncthreads();
 
         DBG_G(3);
-        // ---- left-looking tile-column Cholesky with one column of lookahead ---------------------------
-        // A warp owns the tile rows I == warp (mod 8). Slot u counts them from the bottom (u = 0 is the
-        // last row below nt), so the rows still active in column J are always the prefix u < NA and the
-        // DMMA loop is instantiated per NA without predicates. The observation vector is one more row
-        // (index nt) owned by warp nt mod 8. While the owner of diagonal tile J factors it, the other
-        // warps already accumulate column J+1 over P < J (every term that does not need column J).
+        // ---- left-looking tile Cholesky as a dataflow of three warp roles (no CTA barrier inside) ---------
+        // The latency chain of a small Cholesky is: diagonal tile J (8 dependent pivots) -> sub-diagonal tile
+        // (J+1, J) -> diagonal tile J+1. ONE warp (warp 0, the only factorisation-critical warp on its
+        // scheduler) runs that whole chain in registers; the six bulk warps 1,2,3,5,6,7 (schedulers 1-3) own the
+        // tile rows I mod 6 and do every DMMA-heavy sum, including the two partial sums the panel warp needs
+        // next ("pre" tiles); warp 4 carries the observation row z = L^-1 y.
+        //   s_fW      number of published W_J = L_JJ^-1 (ring slot J & 7)          panel -> bulk, aux
+        //   s_frow    rows <= s_frow are final (sub-diagonal tile stored)         panel -> bulk
+        //   s_fpre[I] pre tiles of row I are in shared memory                     bulk  -> panel
+        //   s_fwarp[w] bulk warp w's rows are final through this many tile columns  bulk  -> bulk
+        //   s_faux    columns solved by the observation-row warp                   aux   -> panel (W ring reuse)
         const int lr = lane >> 2, lj = lane & 3;
         const int oi0 = op_idx(lr, 2 * lj), oi1 = op_idx(lr, 2 * lj + 1);
         const int cv0 = (lane & ~3) + (lj >> 1), cv1 = cv0 + 2;
         const bool odd = lane & 1;
-        const int nreg = warp < nt ? (nt - 1 - warp) / kWarps + 1 : 0;   // regular rows of this warp
-        const int Ilast = warp + (nreg - 1) * kWarps;
-        const bool has_y = ((nt - warp) & (kWarps - 1)) == 0;
         const uint32_t tiles_a = smem_addr(tiles), yv_a = smem_addr(yv), invL_a = smem_addr(invL);
-        uint32_t rowa[kMaxTilesPerWarp];        // shared address of this lane's fragment in tile (I_u, 0)
-#pragma unroll
-        for (int u = 0; u < kMaxTilesPerWarp; ++u) {
-            const int I = Ilast - u * kWarps;
-            rowa[u] = tiles_a + (uint32_t)(tri(I > 0 ? I : 0) * 512 + lane * 16);
-        }
-        double accn[kMaxTilesPerWarp][2][2];   // [slot][k-chunk chain][acc regs] partial sums of the current column
-        double yacc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-#pragma unroll
-        for (int u = 0; u < kMaxTilesPerWarp; ++u) { accn[u][0][0] = accn[u][0][1] = accn[u][1][0] = accn[u][1][1] = 0.0; }
-        int pre_done = 0;                       // terms P < pre_done are already in accn / yacc
+        auto to_frag = [&](double c0, double c1) {
+            const double v00 = shfl(c0, cv0), v01 = shfl(c1, cv0);
+            const double v10 = shfl(c0, cv1), v11 = shfl(c1, cv1);
+            return make_double2(odd ? v01 : v00, odd ? v11 : v10);
+        };
 
-        // accumulate sum_{P0 <= P < P1} L_IP L_{Jc,P}^T for the owned rows I >= Jc (and the observation row)
-        auto accumulate = [&](int Jc, int P0, int P1) {
-#if NAGP_EXP == 2
-            return;
+        if (warp == 0) {
+            // ================= panel warp =================
+            for (int J = 0; J < nt; ++J) {
+                const uint32_t dtile = tiles_a + (uint32_t)((tri(J) + J) * 512);
+                double d0, d1;
+                DBG_T(J, 0);
+                if (J == 0) {
+                    const double2 g2 = lds128(dtile + lane * 16);
+                    d0 = g2.x; d1 = g2.y;
+                } else {
+                    while (s_fpre[J] == 0) { }
+                    __threadfence_block();
+                    DBG_T(J, 1);
+                    const uint32_t ctile = dtile - 512u;
+                    const double2 cpre = lds128(ctile + lane * 16);
+                    const double2 dpre = lds128(dtile + lane * 16);
+                    const double2 ib = lds128(invL_a + (uint32_t)((J - 1) & (kRing - 1)) * 512u + lane * 16);
+                    const double2 fr = to_frag(cpre.x, cpre.y);
+                    double x0 = 0.0, x1 = 0.0;
+                    dmma(x0, x1, fr.x, ib.x);
+                    dmma(x0, x1, fr.y, ib.y);
+                    __syncwarp();
+                    sts64(ctile + oi0 * 8, x0);
+                    sts64(ctile + oi1 * 8, x1);
+                    const double2 xf = to_frag(x0, x1);
+                    d0 = dpre.x; d1 = dpre.y;
+                    dmma(d0, d1, -xf.x, xf.x);
+                    dmma(d0, d1, -xf.y, xf.y);
+                    __syncwarp();
+                    if (lane == 0) { __threadfence_block(); s_frow = J; }
+                }
+                DBG_T(J, 2);
+                if (J >= kRing) {
+                    // slot J & 3 still holds W_{J-4}: every consumer must have solved column J-4
+                    const int need = J - (kRing - 1);
+                    for (;;) {
+                        const int v = lane < kWarps ? ((lane & 3) == 0 ? (lane == 0 ? need : s_faux) : s_fwarp[lane]) : need;
+                        if (__all_sync(kFull, v >= need)) break;
+                    }
+                }
+                const uint32_t wslot = invL_a + (uint32_t)(J & (kRing - 1)) * 512u;
+#if NAGP_CHOL8_SHFL
+                double w0, w1, piv[8];
+                const int bad = chol8_inv(d0, d1, w0, w1, lane, q - J * 8, piv);
+                sts64(dtile + oi0 * 8, d0);
+                sts64(dtile + oi1 * 8, d1);
+                sts64(wslot + oi0 * 8, w0);
+                sts64(wslot + oi1 * 8, w1);
+#else
+                if (J > 0) { __syncwarp(); sts128(dtile + lane * 16, d0, d1); __syncwarp(); }
+                const int bad = chol8_red(dtile, dtile, wslot, lane, q - J * 8);
 #endif
-            if (P0 >= P1) return;
-            const int NA = Ilast >= Jc ? (Ilast - Jc) / kWarps + 1 : 0;
-            const uint32_t bp = tiles_a + (uint32_t)(tri(Jc) * 512 + lane * 16);
-            switch (NA) {
-            case 1: kloop<1>(accn, bp, rowa, P0, P1); break;
-            case 2: kloop<2>(accn, bp, rowa, P0, P1); break;
-            case 3: kloop<3>(accn, bp, rowa, P0, P1); break;
-            case 4: kloop<4>(accn, bp, rowa, P0, P1); break;
-            default: break;
+                if (bad && lane == 0 && !s_info) s_info = J * 8 + bad;
+                __syncwarp();
+                if (lane == 0) { __threadfence_block(); s_fW = J + 1; }
+                DBG_T(J, 3);
             }
-            if (has_y) {
+        } else if (warp == 4) {
+            // ================= observation row: z_J = (y_J - sum_P z_P L_JP^T) W_J^T =================
+            for (int J = 0; J < nt; ++J) {
+                while (s_fW < J + 1) __nanosleep(100);
+                __threadfence_block();
+                double ya0 = 0.0, ya1 = 0.0, yb0 = 0.0, yb1 = 0.0;
+                const uint32_t bp = tiles_a + (uint32_t)(tri(J) * 512 + lane * 16);
                 const uint32_t yp = yv_a + lj * 8;
 #pragma unroll 2
-                for (int P = P0; P < P1; ++P) {
+                for (int P = 0; P < J; ++P) {
                     const double2 bf = lds128(bp + (uint32_t)P * 512u);
                     const double a0 = lr == 0 ? lds64(yp + P * 64) : 0.0;
                     const double a1 = lr == 0 ? lds64(yp + P * 64 + 32) : 0.0;
-                    dmma(yacc[0][0], yacc[0][1], a0, bf.x);
-                    dmma(yacc[1][0], yacc[1][1], a1, bf.y);
+                    dmma(ya0, ya1, a0, bf.x);
+                    dmma(yb0, yb1, a1, bf.y);
                 }
-            }
-        };
-
-        for (int J = 0; J < nt; ++J) {
-            const bool owner = (warp == (J & (kWarps - 1)));
-            const int NA = Ilast >= J ? (Ilast - J) / kWarps + 1 : 0;   // active regular rows (I >= J)
-            // (1) remaining terms of column J, (2) C = A_IJ - sum
-            DBG_T(J, 0);
-            accumulate(J, pre_done, J);
-            double c[kMaxTilesPerWarp][2], cy[2] = {0.0, 0.0}, d0 = 0.0, d1 = 0.0;
-            const uint32_t joff = (uint32_t)J * 512u;
-#pragma unroll
-            for (int u = 0; u < kMaxTilesPerWarp; ++u) {
-                c[u][0] = 0.0; c[u][1] = 0.0;
-                if (u < NA) {
-                    const double2 g2 = lds128(rowa[u] + joff);
-                    c[u][0] = g2.x - (accn[u][0][0] + accn[u][1][0]);
-                    c[u][1] = g2.y - (accn[u][0][1] + accn[u][1][1]);
-                    d0 = c[u][0]; d1 = c[u][1];   // ends up holding slot NA-1: the diagonal tile of its owner
-                }
-                accn[u][0][0] = accn[u][0][1] = accn[u][1][0] = accn[u][1][1] = 0.0;
-            }
-            if (has_y) {
                 const double y0 = lr == 0 ? lds64(yv_a + (J * 8 + 2 * lj) * 8) : 0.0;
                 const double y1v = lr == 0 ? lds64(yv_a + (J * 8 + 2 * lj + 1) * 8) : 0.0;
-                cy[0] = y0 - (yacc[0][0] + yacc[1][0]);
-                cy[1] = y1v - (yacc[0][1] + yacc[1][1]);
-                yacc[0][0] = yacc[0][1] = yacc[1][0] = yacc[1][1] = 0.0;
-            }
-            DBG_T(J, 1);
-            if (owner) {
-                // (3) diagonal tile (slot NA-1): factor + invert in registers, publish, release the others
-                double w0, w1, piv[8];
-#if NAGP_EXP == 1
-                const int bad = 0; w0 = (lr == 2 * lj) ? 1.0 : 0.0; w1 = (lr == 2 * lj + 1) ? 1.0 : 0.0; (void)piv;
-#else
-                const int bad = chol8_inv(d0, d1, w0, w1, lane, q - J * 8, piv);
-#endif
-                const uint32_t dt = tiles_a + (uint32_t)((tri(J) + J) * 512);
-                sts64(dt + oi0 * 8, d0);
-                sts64(dt + oi1 * 8, d1);
-                sts64(invL_a + oi0 * 8, w0);
-                sts64(invL_a + oi1 * 8, w1);
-                if (bad && lane == 0 && NAGP_EXP == 0) s_info = J * 8 + bad;
+                const double2 fr = to_frag(y0 - (ya0 + yb0), y1v - (ya1 + yb1));
+                const double2 ib = lds128(invL_a + (uint32_t)(J & (kRing - 1)) * 512u + lane * 16);
+                double x0 = 0.0, x1 = 0.0;
+                dmma(x0, x1, fr.x, ib.x);
+                dmma(x0, x1, fr.y, ib.y);
+                if (lr == 0) {
+                    sts64(yv_a + (J * 8 + 2 * lj) * 8, x0);
+                    sts64(yv_a + (J * 8 + 2 * lj + 1) * 8, x1);
+                }
                 __syncwarp();
-                DBG_T(J, 2);
-                asm volatile("bar.arrive 1, %0;" ::"n"(kThreads) : "memory");
-                pre_done = 0;   // its own lookahead is deferred to the next column (hidden behind that owner)
-            } else if ((warp & 3) == (J & 3)) {
-                // shares its scheduler (and FP64 pipe) with the owner: leave the pipe to the serial
-                // diagonal factorisation and catch up at the top of the next column
-                pre_done = 0;
-                DBG_T(J, 2);
-                asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
-            } else {
-                // (4) lookahead: column J+1 over P < J
-                if (J + 1 < nt) accumulate(J + 1, 0, J);
-                pre_done = J;
-                DBG_T(J, 2);
-                asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+                if (lane == 0) { __threadfence_block(); s_faux = J + 1; }
             }
-            // (5) triangular solve of the column: X = C * invL^T, stored in operand layout
-            DBG_T(J, 3);
-#if NAGP_EXP == 4
-            if (false) {
-#else
-            if (!s_info) {
-#endif
-                const double2 ib = lds128(invL_a + lane * 16);
-                const int nsolve = owner ? NA - 1 : NA;   // rows strictly below the diagonal
+        } else {
+            // ================= bulk warps: tile rows I == bi (mod 6) =================
+            const int bi = warp < 4 ? warp - 1 : warp - 2;
+            const int nreg = bi < nt ? (nt - 1 - bi) / kBulk + 1 : 0;
+            const int Ilast = bi + (nreg - 1) * kBulk;
+            uint32_t rowa[kMaxTilesPerWarp];        // shared address of this lane's fragment in tile (I_u, 0)
+#pragma unroll
+            for (int u = 0; u < kMaxTilesPerWarp; ++u) {
+                const int I = Ilast - u * kBulk;
+                rowa[u] = tiles_a + (uint32_t)(tri(I > 0 ? I : 0) * 512 + lane * 16);
+            }
+            double accn[kMaxTilesPerWarp][2][2];
+#pragma unroll
+            for (int u = 0; u < kMaxTilesPerWarp; ++u) { accn[u][0][0] = accn[u][0][1] = accn[u][1][0] = accn[u][1][1] = 0.0; }
+            int pre_done = 0;
+            double dn00 = 0.0, dn01 = 0.0, dn10 = 0.0, dn11 = 0.0;   // sum_P L_RP L_RP^T of the warp's next diagonal row R
+            // sum_{P0 <= P < P1} L_IP L_{Jc,P}^T for the owned rows I >= Jc + 1
+            auto accumulate = [&](int Jc, int P0, int P1) {
+                if (P0 >= P1) return;
+                const int NAc = Ilast >= Jc + 1 ? (Ilast - Jc - 1) / kBulk + 1 : 0;
+                const uint32_t bp = tiles_a + (uint32_t)(tri(Jc) * 512 + lane * 16);
+                switch (NAc) {
+                case 1: kloop<1>(accn, bp, rowa, P0, P1); break;
+                case 2: kloop<2>(accn, bp, rowa, P0, P1); break;
+                case 3: kloop<3>(accn, bp, rowa, P0, P1); break;
+                case 4: kloop<4>(accn, bp, rowa, P0, P1); break;
+                case 5: kloop<5>(accn, bp, rowa, P0, P1); break;
+                default: break;
+                }
+            };
+            for (int J = 0; J < nt; ++J) {
+                const int NA = Ilast >= J + 1 ? (Ilast - J - 1) / kBulk + 1 : 0;   // own rows I >= J+1
+                if (NA == 0) break;
+                // (B) finish the column-J sums: needs row J final
+                if (J > 0) {
+                    while (s_frow < J) { }
+                    __threadfence_block();
+                }
+                accumulate(J, pre_done, J);
+                double c[kMaxTilesPerWarp][2];
+                const uint32_t joff = (uint32_t)J * 512u;
 #pragma unroll
                 for (int u = 0; u < kMaxTilesPerWarp; ++u) {
-                    if (u < nsolve) {
-                        const double v00 = shfl(c[u][0], cv0), v01 = shfl(c[u][1], cv0);
-                        const double v10 = shfl(c[u][0], cv1), v11 = shfl(c[u][1], cv1);
+                    c[u][0] = 0.0; c[u][1] = 0.0;
+                    if (u < NA) {
+                        const double2 g2 = lds128(rowa[u] + joff);
+                        c[u][0] = g2.x - (accn[u][0][0] + accn[u][1][0]);
+                        c[u][1] = g2.y - (accn[u][0][1] + accn[u][1][1]);
+                    }
+                    accn[u][0][0] = accn[u][0][1] = accn[u][1][0] = accn[u][1][1] = 0.0;
+                }
+                // the smallest active row is J+1: hand its two pre tiles to the panel warp
+                const bool has_next = (Ilast - (NA - 1) * kBulk) == J + 1;
+                if (has_next) {
+                    double pc0 = 0.0, pc1 = 0.0;
+                    uint32_t ra = 0, ra2 = 0;
+#pragma unroll
+                    for (int u = 0; u < kMaxTilesPerWarp; ++u) {
+                        if (u == NA - 1) { pc0 = c[u][0]; pc1 = c[u][1]; ra = rowa[u]; }
+                        if (u == NA - 2) ra2 = rowa[u];
+                    }
+                    const double2 g2 = lds128(ra + joff + 512u);
+                    __syncwarp();
+                    sts128(ra + joff, pc0, pc1);
+                    sts128(ra + joff + 512u, g2.x - (dn00 + dn10), g2.y - (dn01 + dn11));
+                    __syncwarp();
+                    if (lane == 0) { __threadfence_block(); s_fpre[J + 1] = 1; }
+                    // the next own row (J+7) becomes the warp's next diagonal row: catch up on its final tiles
+                    dn00 = dn01 = dn10 = dn11 = 0.0;
+                    if (NA >= 2) {
+#pragma unroll 2
+                        for (int P = 0; P < J; ++P) {
+                            const double2 f = lds128(ra2 + (uint32_t)P * 512u);
+                            dmma(dn00, dn01, f.x, f.x);
+                            dmma(dn10, dn11, f.y, f.y);
+                        }
+                    }
+                }
+                const int nsolve = has_next ? NA - 1 : NA;      // rows >= J+2
+                // (C) lookahead on column J+1 (rows >= J+2) over the terms already final, polling for W_J
+                int la = 0;
+                if (J + 1 < nt && nsolve > 0) {
+                    const int ow = ((J + 1) % kBulk) < 3 ? ((J + 1) % kBulk) + 1 : ((J + 1) % kBulk) + 2;   // bulk owner of row J+1
+                    while (la < J && s_fW < J + 1) {
+                        int lim = s_fwarp[ow];
+                        lim = lim < J ? lim : J;
+                        if (la >= lim) continue;
+                        __threadfence_block();
+                        const int hi = la + kChunk < lim ? la + kChunk : lim;
+                        accumulate(J + 1, la, hi);
+                        la = hi;
+                    }
+                }
+                pre_done = la;
+                // (D)
+                while (s_fW < J + 1) { }
+                __threadfence_block();
+                // (E) X = C W_J^T for rows >= J+2, stored in operand layout
+                const double2 ib = lds128(invL_a + (uint32_t)(J & (kRing - 1)) * 512u + lane * 16);
+#pragma unroll
+                for (int uu = kMaxTilesPerWarp - 1; uu >= 0; --uu) {
+                    if (uu < nsolve) {
+                        const double2 fr = to_frag(c[uu][0], c[uu][1]);
                         double x0 = 0.0, x1 = 0.0;
-                        dmma(x0, x1, odd ? v01 : v00, ib.x);
-                        dmma(x0, x1, odd ? v11 : v10, ib.y);
-                        const uint32_t dt = rowa[u] - lane * 16 + joff;
+                        dmma(x0, x1, fr.x, ib.x);
+                        dmma(x0, x1, fr.y, ib.y);
+                        const uint32_t dt = rowa[uu] - lane * 16 + joff;
                         sts64(dt + oi0 * 8, x0);
                         sts64(dt + oi1 * 8, x1);
+                        if (uu == nsolve - 1) {   // the warp's next diagonal row: keep its diagonal sum current
+                            const double2 xf = to_frag(x0, x1);
+                            dmma(dn00, dn01, xf.x, xf.x);
+                            dmma(dn10, dn11, xf.y, xf.y);
+                        }
                     }
                 }
-                if (has_y) {
-                    const double v00 = shfl(cy[0], cv0), v01 = shfl(cy[1], cv0);
-                    const double v10 = shfl(cy[0], cv1), v11 = shfl(cy[1], cv1);
-                    double x0 = 0.0, x1 = 0.0;
-                    dmma(x0, x1, odd ? v01 : v00, ib.x);
-                    dmma(x0, x1, odd ? v11 : v10, ib.y);
-                    if (lr == 0) {
-                        sts64(yv_a + (J * 8 + 2 * lj) * 8, x0);
-                        sts64(yv_a + (J * 8 + 2 * lj + 1) * 8, x1);
-                    }
-                }
+                __syncwarp();
+                if (lane == 0) { __threadfence_block(); s_fwarp[warp] = J + 1; }
             }
-            DBG_T(J, 4);
-            __syncthreads();
-            DBG_T(J, 5);
-            if (s_info) break;
+            __syncwarp();
+            if (lane == 0) s_fwarp[warp] = nt;   // nothing left to read: never hold up the W ring
         }
+        __syncthreads();
         DBG_G(4);
 
         if (s_info) {
@@ -464,21 +561,21 @@ void aux_sizes(int Q, int G, int ntheta_cap, int ntab_cap, int ncp_cap, size_t (
 
 }  // namespace
 
-int fused_v2_max_q() { return 8 * (kMaxTilesPerWarp * kWarps - 1); }
+int fused_v4_max_q() { return 8 * 29; }
 
 // Plans shared memory for the tile kernel: the tiles, yv and invL are mandatory; the aux arrays go
 // to shared memory in priority order while the CTA stays within `budget` bytes, else to global
 // scratch (L1-resident: a few KB per CTA).
-V2Plan plan_fused_v2(int q, int G, int ntheta_cap, int ntab_cap, int ncp_cap, int smem_optin, int smem_per_sm)
+V2Plan plan_fused_v4(int q, int G, int ntheta_cap, int ntab_cap, int ncp_cap, int smem_optin, int smem_per_sm)
 {
     V2Plan pl{};
     const int nt = (q + 7) / 8, Q = nt * 8;
     pl.nt = nt;
-    size_t base = ((size_t)(nt * (nt + 1) / 2) * 64 + Q + 64) * sizeof(double);
+    size_t base = ((size_t)(nt * (nt + 1) / 2) * 64 + Q + kRing * 64) * sizeof(double);
     size_t sz[5];
     aux_sizes(Q, G, ntheta_cap, ntab_cap, ncp_cap, sz);
     size_t total_aux = sz[0] + sz[1] + sz[2] + sz[3] + sz[4];
-    const size_t static_smem = 1536 + 1024;   // TreeProgram + reductions + per-CTA reservation
+    const size_t static_smem = 1216 + 1024;   // static shared memory (ptxas) + per-CTA reservation
     // budget: 2 CTAs/SM if the mandatory part allows it, else everything the opt-in limit gives
     size_t two = (size_t)smem_per_sm / 2;
     size_t budget = (base + static_smem <= two) ? two - static_smem : (size_t)smem_optin - 1536;
@@ -497,11 +594,11 @@ V2Plan plan_fused_v2(int q, int G, int ntheta_cap, int ntab_cap, int ncp_cap, in
     return pl;
 }
 
-int fused_v2_grid(const V2Plan &pl, int64_t B, int num_sms)
+int fused_v4_grid(const V2Plan &pl, int64_t B, int num_sms)
 {
     int per_sm = 0;
-    cudaFuncSetAttribute(fused_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_v2_kernel, kThreads, pl.smem_bytes) != cudaSuccess ||
+    cudaFuncSetAttribute(fused_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_v4_kernel, kThreads, pl.smem_bytes) != cudaSuccess ||
         per_sm < 1) {
         cudaGetLastError();
         per_sm = 1;
@@ -510,10 +607,10 @@ int fused_v2_grid(const V2Plan &pl, int64_t B, int num_sms)
     return (int)std::min<int64_t>(g, B);
 }
 
-cudaError_t launch_fused_v2(const FusedArgs &a, const V2Plan &pl, char *scratch, unsigned long long *work_counter,
+cudaError_t launch_fused_v4(const FusedArgs &a, const V2Plan &pl, char *scratch, unsigned long long *work_counter,
                             int grid, cudaStream_t stream)
 {
-    V2Layout lay{};
+    V4Layout lay{};
     lay.work_counter = work_counter;
     cudaError_t e0 = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
     if (e0 != cudaSuccess) return e0;
@@ -521,9 +618,9 @@ cudaError_t launch_fused_v2(const FusedArgs &a, const V2Plan &pl, char *scratch,
     for (int i = 0; i < 5; ++i) { lay.aux_off[i] = pl.aux_off[i]; lay.aux_smem[i] = pl.aux_smem[i]; }
     lay.scratch_stride = pl.scratch_stride;
     lay.scratch = scratch;
-    cudaError_t e = cudaFuncSetAttribute(fused_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(fused_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (e != cudaSuccess) return e;
-    fused_v2_kernel<<<grid, kThreads, pl.smem_bytes, stream>>>(a, lay);
+    fused_v4_kernel<<<grid, kThreads, pl.smem_bytes, stream>>>(a, lay);
     return cudaGetLastError();
 }
 

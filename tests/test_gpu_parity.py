@@ -14,9 +14,10 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-9
 
 
-@pytest.fixture(params=[1, 2], ids=["column-kernel", "tile-kernel"])
+@pytest.fixture(params=[1, 2, 3, 4], ids=["column-kernel", "tile-kernel", "dataflow-kernel", "panel-kernel"])
 def veng(engine, request):
-    """The engine pinned to one factorisation kernel (1 = shared-memory column, 2 = DMMA tile)."""
+    """The engine pinned to one factorisation kernel (1 = shared-memory column, 2 = DMMA tile with CTA
+    barriers, 3 = DMMA tile with dataflow flags, 4 = panel-warp dataflow)."""
     engine.set_variant(request.param)
     yield engine
     engine.set_variant(0)

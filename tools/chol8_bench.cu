@@ -88,6 +88,97 @@ __device__ __forceinline__ int chol8_v1(double &c0, double &c1, double &w0, doub
     return bad;
 }
 
+
+__device__ __forceinline__ double rcp_fast(double a)
+{
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+    double e = fma(-a, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-a, x, 1.0);
+    x = fma(x, e, x);
+    return x;
+}
+__device__ __forceinline__ int op_idx(int r, int c) { return ((r * 4 + (c & 3)) << 1) + (c >> 2); }
+
+// variant 2: every lane factors the whole tile redundantly in registers (no shuffles on the chain);
+// the reciprocal pivot for the Schur update comes from its own MUFU+Newton chain so the rsqrt is off
+// the critical path; lane c solves column c of the inverse. In/out through shared memory.
+__device__ __forceinline__ int chol8_v2(double *sm_in, double *sm_L, double *sm_W, int lane, int nreal)
+{
+    double s[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) s[i][j] = sm_in[i * 8 + j];
+    double rinv[8];
+    int bad = 0;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+        const double d = s[p][p];
+        if (!(d > 0.0) && p < nreal && bad == 0) bad = p + 1;
+        const double r = rcp_fast(d);
+        const double ri = rsqrt_fast(d);
+        rinv[p] = ri;
+        double t[8];
+#pragma unroll
+        for (int i = p + 1; i < 8; ++i) t[i] = s[i][p] * r;
+#pragma unroll
+        for (int i = p + 1; i < 8; ++i)
+#pragma unroll
+            for (int j = p + 1; j <= i; ++j) s[i][j] = fma(-t[i], s[j][p], s[i][j]);
+#pragma unroll
+        for (int i = p + 1; i < 8; ++i) s[i][p] *= ri;
+        s[p][p] = d * ri;
+    }
+    // column c of W = L^-1 (forward substitution on e_c)
+    const int c = lane & 7;
+    double w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        double acc = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < i; ++k) acc = fma(-s[i][k], w[k], acc);
+        w[i] = acc * rinv[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) sm_L[op_idx(i, j)] = s[i][j];
+    if (lane < 8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sm_W[op_idx(i, c)] = w[i];
+    }
+    return bad;
+}
+
+__global__ void bench2(const double *A, double *L, double *W, long long *cyc, int reps)
+{
+    __shared__ double sm_in[64], sm_L[64], sm_W[64];
+    const int lane = threadIdx.x, r = lane >> 2, j = lane & 3;
+    double a0 = A[r * 8 + 2 * j], a1 = A[r * 8 + 2 * j + 1];
+    double c0 = a0, c1 = a1;
+    int bad = 0;
+    for (int i = lane; i < 64; i += 32) { sm_L[i] = 0; sm_W[i] = 0; }
+    long long t0 = clock64();
+    for (int i = 0; i < reps; ++i) {
+        c0 = a0 + c0 * 1e-300; c1 = a1 + c1 * 1e-300;   // serialise calls
+        *reinterpret_cast<double2 *>(sm_in + lane * 2) = make_double2(c0, c1);
+        __syncwarp();
+        bad += chol8_v2(sm_in, sm_L, sm_W, lane, 8);
+        __syncwarp();
+        double2 v = *reinterpret_cast<double2 *>(sm_W + lane * 2);   // consumer-side fragment load
+        c0 = v.x; c1 = v.y;
+    }
+    long long t1 = clock64();
+    __syncwarp();
+    for (int e = lane; e < 64; e += 32) {
+        int rr = e >> 3, cc = e & 7;
+        L[e] = sm_L[op_idx(rr, cc)]; W[e] = sm_W[op_idx(rr, cc)];
+    }
+    if (lane == 0) { cyc[0] = (t1 - t0) / reps; cyc[1] = bad; }
+}
+
 template <int V>
 __global__ void bench(const double *A, double *L, double *W, long long *cyc, int reps)
 {
@@ -113,8 +204,8 @@ int main()
     double *A, *L, *W; long long *cyc, hc[2];
     cudaMalloc(&A, 512); cudaMalloc(&L, 512); cudaMalloc(&W, 512); cudaMalloc(&cyc, 16);
     cudaMemcpy(A, hA, 512, cudaMemcpyHostToDevice);
-    for (int v = 0; v < 2; ++v) {
-        if (v == 0) bench<0><<<1, 32>>>(A, L, W, cyc, 200); else bench<1><<<1, 32>>>(A, L, W, cyc, 200);
+    for (int v = 0; v < 3; ++v) {
+        if (v == 0) bench<0><<<1, 32>>>(A, L, W, cyc, 200); else if (v == 1) bench<1><<<1, 32>>>(A, L, W, cyc, 200); else bench2<<<1, 32>>>(A, L, W, cyc, 200);
         cudaMemcpy(hL, L, 512, cudaMemcpyDeviceToHost); cudaMemcpy(hW, W, 512, cudaMemcpyDeviceToHost);
         cudaMemcpy(hc, cyc, 16, cudaMemcpyDeviceToHost);
         // check L L^T = A and W L = I

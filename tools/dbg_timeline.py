@@ -22,6 +22,8 @@ print("phases: setup %d tables %d gram %d factor %d logml %d" % tuple(np.diff(g[
 t = d[:20 * 64].reshape(20, 8, 8)[:, :, :6]
 base = t[0, :, 0].min()
 print("col owner | per-warp [top->C, C->pre-bar, bar wait, trsm, sync wait] (owner's row) | column wall")
+starts = [t[J, J % 8, 1] for J in range(20)]
+print("owner C-ready to next owner C-ready (chain period):", np.diff(starts))
 for J in range(20):
     ow = J % 8
     row = t[J, ow]
