@@ -58,8 +58,7 @@ int32_t nagp_set_stream(nagp_ctx *ctx, void *cuda_stream);
 int32_t nagp_set_jitter(nagp_ctx *ctx, double jitter);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t nagp_launch_count(const nagp_ctx *ctx);
-/* Pick the factorisation kernel for q <= 232: 0 = auto, 1 = shared-memory column kernel, 2 = tile kernel
- * (CTA barriers per tile column), 3 = dataflow tile kernel (flags, no barriers inside the factorisation). */
+/* Pick the factorisation kernel for q <= 232: 0 = auto, 1 = shared-memory column kernel, 2 = tile kernel. */
 int32_t nagp_set_variant(nagp_ctx *ctx, int32_t variant);
 
 /* ---- (a2) batched log marginal likelihood ---------------------------------------------------

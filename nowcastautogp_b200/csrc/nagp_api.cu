@@ -249,24 +249,19 @@ int32_t run_fused(nagp_ctx *ctx, FusedArgs a, const int64_t *theta_off_host)
     if (ctx->variant != 1 && q <= fused_v2_max_q()) {
         int64_t nth = 1;
         for (int64_t p = 0; p < a.P; ++p) nth = std::max(nth, theta_off_host[p + 1] - theta_off_host[p]);
-        const bool v3 = ctx->variant == 3, v4 = ctx->variant == 4;
-        V2Plan pl = v4 ? plan_fused_v4(q, a.G, (int)std::min<int64_t>(nth, MAX_THETA), a.ntab_cap, a.ncp_cap,
-                                       ctx->smem_optin, ctx->smem_per_sm) : v3 ? plan_fused_v3(q, a.G, (int)std::min<int64_t>(nth, MAX_THETA), a.ntab_cap, a.ncp_cap,
-                                       ctx->smem_optin, ctx->smem_per_sm)
-                       : plan_fused_v2(q, a.G, (int)std::min<int64_t>(nth, MAX_THETA), a.ntab_cap, a.ncp_cap,
-                                       ctx->smem_optin, ctx->smem_per_sm);
+        V2Plan pl = plan_fused_v2(q, a.G, (int)std::min<int64_t>(nth, MAX_THETA), a.ntab_cap, a.ncp_cap,
+                                  ctx->smem_optin, ctx->smem_per_sm);
         if (pl.ok) {
-            int grid = v4 ? fused_v4_grid(pl, a.B, ctx->num_sms) : v3 ? fused_v3_grid(pl, a.B, ctx->num_sms) : fused_v2_grid(pl, a.B, ctx->num_sms);
+            int grid = fused_v2_grid(pl, a.B, ctx->num_sms);
             if (getenv("NAGP_DEBUG"))
-                fprintf(stderr, "[nagp] tile kernel v%d: q=%d G=%d caps(tab=%d,cp=%d,theta=%d) smem=%zu B aux_in_smem(th,gg,tt,sig,tab)=%d%d%d%d%d scratch/CTA=%d grid=%d\n",
-                        v4 ? 4 : v3 ? 3 : 2, q, a.G, a.ntab_cap, a.ncp_cap, (int)nth, pl.smem_bytes, pl.aux_smem[0], pl.aux_smem[1],
+                fprintf(stderr, "[nagp] tile kernel: q=%d G=%d caps(tab=%d,cp=%d,theta=%d) smem=%zu B aux_in_smem(th,gg,tt,sig,tab)=%d%d%d%d%d scratch/CTA=%d grid=%d\n",
+                        q, a.G, a.ntab_cap, a.ncp_cap, (int)nth, pl.smem_bytes, pl.aux_smem[0], pl.aux_smem[1],
                         pl.aux_smem[2], pl.aux_smem[3], pl.aux_smem[4], pl.scratch_stride, grid);
             char *scr = nullptr;
             if (pl.scratch_stride) NAGP_TRY(scratch(ctx, (size_t)grid * pl.scratch_stride, &scr));
             unsigned long long *counter = nullptr;
             NAGP_TRY(scratch(ctx, 1, &counter));
-            NAGP_CUDA(ctx, v4 ? launch_fused_v4(a, pl, scr, counter, grid, ctx->stream) : v3 ? launch_fused_v3(a, pl, scr, counter, grid, ctx->stream)
-                              : launch_fused_v2(a, pl, scr, counter, grid, ctx->stream));
+            NAGP_CUDA(ctx, launch_fused_v2(a, pl, scr, counter, grid, ctx->stream));
             ctx->launches += 1;
             return NAGP_OK;
         }
@@ -325,7 +320,6 @@ int32_t nagp_init(int32_t device, nagp_ctx **out)
         return fail(nullptr, NAGP_E_CUDA, std::string("context setup: ") + cudaGetErrorString(e));
     }
     ctx->stream = ctx->own_stream;
-    if (const char *ev = getenv("NAGP_VARIANT")) ctx->variant = atoi(ev);   // experiments only
     *out = ctx;
     return NAGP_OK;
 }
@@ -362,7 +356,7 @@ int64_t nagp_launch_count(const nagp_ctx *ctx) { return ctx ? ctx->launches : 0;
 
 int32_t nagp_set_variant(nagp_ctx *ctx, int32_t variant)
 {
-    if (!ctx || variant < 0 || variant > 4) return NAGP_E_ARG;
+    if (!ctx || variant < 0 || variant > 2) return NAGP_E_ARG;
     ctx->variant = variant;
     return NAGP_OK;
 }

@@ -27,7 +27,7 @@
 #include "nagp_tree.cuh"
 #include "nagp_tile.cuh"
 
-#if NAGP_EXP == 8
+#if NAGP_EXP == 9
 __device__ long long g_nagp_dbg[8192];
 extern "C" int nagp_debug_read(long long *out, int count)
 {

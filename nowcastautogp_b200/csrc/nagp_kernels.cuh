@@ -59,20 +59,6 @@ int fused_v2_grid(const V2Plan &pl, int64_t B, int num_sms);
 cudaError_t launch_fused_v2(const FusedArgs &a, const V2Plan &pl, char *scratch, unsigned long long *work_counter,
                             int grid, cudaStream_t stream);
 
-// Dataflow tile kernel (variant 3): same plan structure, flags instead of CTA barriers inside the factorisation.
-int fused_v3_max_q();
-V2Plan plan_fused_v3(int q, int G, int ntheta_cap, int ntab_cap, int ncp_cap, int smem_optin, int smem_per_sm);
-int fused_v3_grid(const V2Plan &pl, int64_t B, int num_sms);
-cudaError_t launch_fused_v3(const FusedArgs &a, const V2Plan &pl, char *scratch, unsigned long long *work_counter,
-                            int grid, cudaStream_t stream);
-
-// Panel-warp dataflow tile kernel (variant 4): one warp runs the diagonal chain, six bulk warps the sums.
-int fused_v4_max_q();
-V2Plan plan_fused_v4(int q, int G, int ntheta_cap, int ntab_cap, int ncp_cap, int smem_optin, int smem_per_sm);
-int fused_v4_grid(const V2Plan &pl, int64_t B, int num_sms);
-cudaError_t launch_fused_v4(const FusedArgs &a, const V2Plan &pl, char *scratch, unsigned long long *work_counter,
-                            int grid, cudaStream_t stream);
-
 // Large path (q beyond shared memory): factor in HBM as tile-packed operand-layout tiles.
 struct LargePlan {
     int ok;

@@ -500,9 +500,10 @@ __global__ void __launch_bounds__(kThreads, 2) chol_large_kernel(const FusedArgs
 // Extends each particle's stored factor from n_old to n_new = a.n points in place. Tile rows
 // I0 = floor(n_old / 8) .. nt-1 are (re)computed up-looking in groups of <= 8 tile rows:
 //   X_J = (A(I, J) - sum_{P<J} X_P L_JP^T) W_J^T   for J < I,   chol8 of the remainder for J == I,
-// and the same recurrence gives the new entries of z = L^-1 y. The sum over P is split across the 8
-// warps (warp w takes P = w, w+8, ...; each stored tile of L is read exactly once per group, in storage
-// order), reduced through shared memory, and row r of the group is finished by warp r.
+// and the same recurrence gives the new entries of z = L^-1 y. The stored rows J of L are swept in blocks
+// of 8: warp w streams row J0+w (contiguous in storage, 4 KB in flight per warp, read exactly once per
+// group) and sums over the columns P < J0 on its own; the 8x8-tile triangle of the block is then finished
+// row by row, one barrier per row.
 struct AppendLayout {
     LargeLayout base;
     int n_old;
@@ -524,8 +525,8 @@ __global__ void __launch_bounds__(kThreads, 2) rank_append_kernel(const FusedArg
     const int n_old = al.n_old;
     const int I0 = n_old >> 3;
 
-    double *s_part = smem;                               // [kWarps][9] partial tiles, accumulator layout
-    char *aux_s = reinterpret_cast<char *>(s_part + kWarps * 9 * 64);
+    double *s_x = smem;                                   // [8] X tiles of the current block (operand layout)
+    char *aux_s = reinterpret_cast<char *>(s_x + kWarps * 64);
     const Setup su = aux_pointers(lay, aux_s);
 
     for (int i = tid; i < Q; i += kThreads) {
@@ -553,19 +554,133 @@ __global__ void __launch_bounds__(kThreads, 2) rank_append_kernel(const FusedArg
         gc.single_table = (tp.clen == 1 && tp.cop[0] == OP_TABLE);
 
         for (int g0 = I0; g0 < nt && !s_info; g0 += kBlk) {
-            const int R = min(kBlk, nt - g0);           // new tile rows g0 .. g0+R-1; row index R = the y row
-            const int Jend = g0 + R;                    // sweep J = 0 .. Jend-1
-            for (int J = 0; J < Jend; ++J) {
-                // rows active at this J: new rows r with g0 + r >= J, and the y row once J >= g0
-                const int r_lo = J > g0 ? J - g0 : 0;
-                const bool y_on = J >= g0;   // z of this group's rows
-                // ---- split-K partial sums ------------------------------------------------------------
+            const int R = min(kBlk, nt - g0);           // new tile rows g0 .. g0+R-1 (+ the y row)
+            const int Jend = g0 + R;                    // rows J = 0 .. Jend-1 of L are swept
+            if (R == 1) {
+                // ---- one new tile row (appends of <= 8 points): the HBM-bound case ------------------------
+                // Row J of the stored factor contributes X_J = (A(g0,J) - sum_{P<J} X_P L_JP^T) W_J^T. Warp w
+                // streams row J0+w (4 tiles = 2 KB in flight per warp, next to the matching tiles of the new
+                // row from L1/L2) for the columns P < J0; the last <= 7 terms use the X tiles of this block,
+                // handed from warp to warp through shared memory.
+                const double *xrow = Lb + (size_t)tri(g0) * 64 + lane * 2;      // the new row (A operand)
+                const double *zrow = Lb + (size_t)tri(yrow) * 64 + lane * 2;    // z = L^-1 y
+                for (int J0 = 0; J0 <= g0; J0 += kWarps) {
+                    const int J = J0 + warp;
+                    const bool rowv = J <= g0;
+                    const bool last = J == g0;                                   // the new row itself
+                    const double *lrow = Lb + (size_t)tri(rowv ? J : 0) * 64 + lane * 2;
+                    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;               // two chains of the row sum
+                    double y0 = 0.0, y1 = 0.0;                                   // z_g0 sum (last row only)
+                    if (rowv) {
+                        int P = 0;
+                        for (; P + 4 <= J0; P += 4) {
+                            double2 bf[4], af[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) bf[i] = ldg128_stream(lrow + (size_t)(P + i) * 64);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) af[i] = ldg128(xrow + (size_t)(P + i) * 64);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                dmma(a0, a1, af[i].x, bf[i].x);
+                                dmma(b0, b1, af[i].y, bf[i].y);
+                            }
+                            if (last) {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const double2 zf = ldg128(zrow + (size_t)(P + i) * 64);
+                                    dmma(y0, y1, zf.x, bf[i].x);
+                                    dmma(y0, y1, zf.y, bf[i].y);
+                                }
+                            }
+                        }
+                    }
+                    // operands of the in-block terms that do not depend on this block: L_JP (old rows), W_J, A(g0,J)
+                    double2 bfb[kWarps - 1];
+                    double2 ib = make_double2(0.0, 0.0);
+                    double gt0 = 0.0, gt1 = 0.0;
+                    if (rowv) {
+#pragma unroll
+                        for (int i = 0; i < kWarps - 1; ++i)
+                            bfb[i] = (!last && i < warp) ? ldg128_stream(lrow + (size_t)(J0 + i) * 64) : make_double2(0.0, 0.0);
+                        if (!last) ib = ldg128(Wb + (size_t)J * 64 + lane * 2);
+                        double out[4];
+                        gram_pair(tp, gc, g0, J, J, lane, out);
+                        gt0 = out[0]; gt1 = out[1];
+                    }
+                    for (int j = 0; j < kWarps; ++j) {
+                        if (warp == j && rowv) {
+#pragma unroll
+                            for (int i = 0; i < kWarps - 1; ++i) {
+                                if (i < j) {
+                                    const double2 af = *reinterpret_cast<const double2 *>(s_x + i * 64 + lane * 2);
+                                    const double2 bf = last ? af : bfb[i];
+                                    dmma(a0, a1, af.x, bf.x);
+                                    dmma(b0, b1, af.y, bf.y);
+                                    if (last) {
+                                        const double2 zf = ldg128(zrow + (size_t)(J0 + i) * 64);
+                                        dmma(y0, y1, zf.x, bf.x);
+                                        dmma(y0, y1, zf.y, bf.y);
+                                    }
+                                }
+                            }
+                            const double c0v = gt0 - (a0 + b0), c1v = gt1 - (a1 + b1);
+                            if (!last) {
+                                const double2 fr = acc_to_frag(c0v, c1v, lane);
+                                double x0 = 0.0, x1 = 0.0;
+                                dmma(x0, x1, fr.x, ib.x);
+                                dmma(x0, x1, fr.y, ib.y);
+                                store_op(s_x + j * 64, x0, x1, lane);
+                                store_op(Lb + ((size_t)tri(g0) + J) * 64, x0, x1, lane);
+                            } else {
+                                double d0 = c0v, d1 = c1v, w0, w1, piv[8];
+                                const int bad = chol8_inv(d0, d1, w0, w1, lane, q - J * 8, piv);
+                                if (bad && lane == 0 && !s_info) s_info = J * 8 + bad;
+                                double ld = 0.0;
+#pragma unroll
+                                for (int pp = 0; pp < 8; ++pp) {
+                                    const int row = J * 8 + pp;
+                                    if (row >= n_old && row < n) ld += 0.5 * log(piv[pp]);
+                                }
+                                store_op(Lb + ((size_t)tri(J) + J) * 64, d0, d1, lane);
+                                store_op(Wb + (size_t)J * 64, w0, w1, lane);
+                                store_op(s_x + j * 64, w0, w1, lane);      // W_g0 as a B operand for the z tile
+                                __syncwarp();
+                                const double2 iw = *reinterpret_cast<const double2 *>(s_x + j * 64 + lane * 2);
+                                double yg0, yg1;
+                                y_tile(a, 0, 0, J, n, lane, yg0, yg1);
+                                const double2 fr = acc_to_frag(yg0 - y0, yg1 - y1, lane);
+                                double x0 = 0.0, x1 = 0.0;
+                                dmma(x0, x1, fr.x, iw.x);
+                                dmma(x0, x1, fr.y, iw.y);
+                                store_op(Lb + ((size_t)tri(yrow) + J) * 64, x0, x1, lane);
+                                double zz = 0.0;
+                                if ((lane >> 2) == 0) {
+                                    const int c = J * 8 + (lane & 3) * 2;
+                                    if (c >= n_old && c < n) zz = fma(x0, x0, zz);
+                                    if (c + 1 >= n_old && c + 1 < n) zz = fma(x1, x1, zz);
+                                }
+                                zz = warp_sum(zz);
+                                if (lane == 0) { s_acc[0] += ld; s_acc[1] += zz; }
+                            }
+                        }
+                        if (J0 + j + 1 <= g0) __syncthreads();
+                        else break;
+                    }
+                    __syncthreads();
+                }
+                continue;
+            }
+            for (int J0 = 0; J0 < Jend; J0 += kWarps) {
+                // ---- streaming part: warp w owns row J = J0 + w of L and sums over the columns P < J0 ------
+                const int J = J0 + warp;
+                const bool rowv = J < Jend;
+                const int r_lo = J > g0 ? J - g0 : 0;   // new rows r >= r_lo still need column J
+                const bool y_on = J >= g0;              // z of this group's rows
                 double acc[kBlk + 1][2];
 #pragma unroll
                 for (int r = 0; r <= kBlk; ++r) { acc[r][0] = 0.0; acc[r][1] = 0.0; }
-                const double *lrow = Lb + (size_t)tri(J) * 64 + lane * 2;
-                for (int P = warp; P < J; P += kWarps) {
-                    const double2 bf = ldg128_stream(lrow + (size_t)P * 64);
+                const double *lrow = Lb + (size_t)tri(rowv ? J : 0) * 64 + lane * 2;
+                auto terms = [&](int P, const double2 bf) {
 #pragma unroll
                     for (int r = 0; r < kBlk; ++r) {
                         if (r >= r_lo && r < R) {
@@ -579,72 +694,77 @@ __global__ void __launch_bounds__(kThreads, 2) rank_append_kernel(const FusedArg
                         dmma(acc[kBlk][0], acc[kBlk][1], af.x, bf.x);
                         dmma(acc[kBlk][0], acc[kBlk][1], af.y, bf.y);
                     }
-                }
+                };
+                if (rowv) {
+                    int P = 0;
+                    for (; P + 8 <= J0; P += 8) {      // 4 KB of the row in flight per warp
+                        double2 bf[8];
 #pragma unroll
-                for (int r = 0; r <= kBlk; ++r)
-                    *reinterpret_cast<double2 *>(s_part + (warp * 9 + r) * 64 + lane * 2) = make_double2(acc[r][0], acc[r][1]);
-                __syncthreads();
-                // ---- the diagonal tile first (row J - g0 when J is a new row): every other row needs W_J --
-                const bool J_new = J >= g0;
-                if (J_new && warp == 0) {
-                    const int r = J - g0;
-                    double c0v = 0.0, c1v = 0.0;
-                    for (int w = 0; w < kWarps; ++w) {
-                        const double2 v = *reinterpret_cast<double2 *>(s_part + (w * 9 + r) * 64 + lane * 2);
-                        c0v += v.x; c1v += v.y;
-                    }
-                    double out[4];
-                    gram_pair(tp, gc, J, J, J, lane, out);
-                    double d0 = out[0] - c0v, d1 = out[1] - c1v, w0, w1, piv[8];
-                    const int bad = chol8_inv(d0, d1, w0, w1, lane, q - J * 8, piv);
-                    if (bad && lane == 0 && !s_info) s_info = J * 8 + bad;
-                    double ld = 0.0;
+                        for (int i = 0; i < 8; ++i) bf[i] = ldg128_stream(lrow + (size_t)(P + i) * 64);
 #pragma unroll
-                    for (int pp = 0; pp < 8; ++pp) {
-                        const int row = J * 8 + pp;
-                        if (row >= n_old && row < n) ld += 0.5 * log(piv[pp]);
+                        for (int i = 0; i < 8; ++i) terms(P + i, bf[i]);
                     }
-                    if (lane == 0) s_acc[0] += ld;
-                    store_op(Lb + ((size_t)tri(J) + J) * 64, d0, d1, lane);
-                    store_op(Wb + (size_t)J * 64, w0, w1, lane);
+                    for (; P < J0; ++P) terms(P, ldg128_stream(lrow + (size_t)P * 64));
                 }
-                if (J_new) { __threadfence_block(); __syncthreads(); }
-                // ---- finish the off-diagonal rows: warp r handles new row r, warp (R % 8 ...) the y row ------
-                const double2 ib = ldg128(Wb + (size_t)J * 64 + lane * 2);
-                for (int r = warp; r <= kBlk; r += kWarps) {
-                    const bool isy = (r == kBlk);
-                    if (isy ? !y_on : !(r < R && g0 + r > J)) continue;
-                    double c0v = 0.0, c1v = 0.0;
-                    for (int w = 0; w < kWarps; ++w) {
-                        const double2 v = *reinterpret_cast<double2 *>(s_part + (w * 9 + r) * 64 + lane * 2);
-                        c0v += v.x; c1v += v.y;
+                // ---- the 8 x 8-tile triangle of this block: row J0+j needs the tiles finished by rows < J0+j --
+                for (int j = 0; j < kWarps; ++j) {
+                    if (warp == j && rowv) {
+                        for (int P = J0; P < J; ++P) terms(P, ldg128(lrow + (size_t)P * 64));
+                        double2 ib;
+                        if (J >= g0) {
+                            // J is a new row: its diagonal tile (new row r = J - g0)
+                            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                            for (int r = 0; r < kBlk; ++r) if (r == J - g0) { s0 = acc[r][0]; s1 = acc[r][1]; }
+                            double out[4];
+                            gram_pair(tp, gc, J, J, J, lane, out);
+                            double d0 = out[0] - s0, d1 = out[1] - s1, w0, w1, piv[8];
+                            const int bad = chol8_inv(d0, d1, w0, w1, lane, q - J * 8, piv);
+                            if (bad && lane == 0 && !s_info) s_info = J * 8 + bad;
+                            double ld = 0.0;
+#pragma unroll
+                            for (int pp = 0; pp < 8; ++pp) {
+                                const int row = J * 8 + pp;
+                                if (row >= n_old && row < n) ld += 0.5 * log(piv[pp]);
+                            }
+                            if (lane == 0) s_acc[0] += ld;
+                            store_op(Lb + ((size_t)tri(J) + J) * 64, d0, d1, lane);
+                            store_op(Wb + (size_t)J * 64, w0, w1, lane);
+                            __syncwarp();
+                        }
+                        ib = ldg128(Wb + (size_t)J * 64 + lane * 2);
+#pragma unroll
+                        for (int r = 0; r <= kBlk; ++r) {
+                            const bool isy = (r == kBlk);
+                            if (isy ? !y_on : !(r < R && g0 + r > J)) continue;
+                            double g0v, g1v;
+                            if (isy) {
+                                y_tile(a, 0, 0, J, n, lane, g0v, g1v);
+                            } else {
+                                double out[4];
+                                gram_pair(tp, gc, g0 + r, J, J, lane, out);
+                                g0v = out[0]; g1v = out[1];
+                            }
+                            const double2 fr = acc_to_frag(g0v - acc[r][0], g1v - acc[r][1], lane);
+                            double x0 = 0.0, x1 = 0.0;
+                            dmma(x0, x1, fr.x, ib.x);
+                            dmma(x0, x1, fr.y, ib.y);
+                            const int I = isy ? yrow : g0 + r;
+                            store_op(Lb + ((size_t)tri(I) + J) * 64, x0, x1, lane);
+                            if (isy && (lane >> 2) == 0) {
+                                double zz = 0.0;
+                                const int c = J * 8 + (lane & 3) * 2;
+                                if (c >= n_old && c < n) zz = fma(x0, x0, zz);
+                                if (c + 1 >= n_old && c + 1 < n) zz = fma(x1, x1, zz);
+                                zz += __shfl_xor_sync(0x0000000fu, zz, 1);
+                                zz += __shfl_xor_sync(0x0000000fu, zz, 2);
+                                if (lane == 0) s_acc[1] += zz;
+                            }
+                        }
                     }
-                    double g0v, g1v;
-                    if (isy) {
-                        y_tile(a, 0, 0, J, n, lane, g0v, g1v);
-                    } else {
-                        double out[4];
-                        gram_pair(tp, gc, g0 + r, J, J, lane, out);
-                        g0v = out[0]; g1v = out[1];
-                    }
-                    const double2 fr = acc_to_frag(g0v - c0v, g1v - c1v, lane);
-                    double x0 = 0.0, x1 = 0.0;
-                    dmma(x0, x1, fr.x, ib.x);
-                    dmma(x0, x1, fr.y, ib.y);
-                    const int I = isy ? yrow : g0 + r;
-                    store_op(Lb + ((size_t)tri(I) + J) * 64, x0, x1, lane);
-                    if (isy && (lane >> 2) == 0) {
-                        // new z entries: columns J*8 + 2*lj, +1
-                        double zz = 0.0;
-                        const int c = J * 8 + (lane & 3) * 2;
-                        if (c >= n_old && c < n) zz = fma(x0, x0, zz);
-                        if (c + 1 >= n_old && c + 1 < n) zz = fma(x1, x1, zz);
-                        zz += __shfl_xor_sync(0x0000000fu, zz, 1);
-                        zz += __shfl_xor_sync(0x0000000fu, zz, 2);
-                        if (lane == 0) s_acc[1] += zz;
-                    }
+                    if (J0 + j + 1 < Jend) { __threadfence_block(); __syncthreads(); }
+                    else break;
                 }
-                __threadfence_block();
                 __syncthreads();
             }
         }
@@ -688,7 +808,7 @@ LargePlan plan_large(int q, int q_cap, int G, int ntheta_cap, int ntab_cap, int 
     pl.yrow = pl.ntp_cap;
     pl.L_stride = ((size_t)pl.ntp_cap * (pl.ntp_cap + 1) / 2 + pl.ntp_cap) * 64;
     const int Q = pl.ntp * 8;
-    size_t base = append ? (size_t)(kWarps * 9) * 64 * sizeof(double) : (size_t)(36 + 36 + kBlk) * 64 * sizeof(double);
+    size_t base = append ? (size_t)kWarps * 64 * sizeof(double) : (size_t)(36 + 36 + kBlk) * 64 * sizeof(double);
     size_t sz[5];
     large_aux_sizes(Q, G, ntheta_cap, ntab_cap, ncp_cap, sz);
     const size_t static_smem = 2048 + 1024;

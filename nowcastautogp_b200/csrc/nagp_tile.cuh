@@ -144,89 +144,6 @@ __device__ __forceinline__ void tree_eval4(const TreeProgram &tp, const EvalCtx 
 }
 
 
-// MUFU seed + Newton: full double accuracy for positive normal inputs (pivots); failures are flagged by the caller
-__device__ __forceinline__ double rsqrt_fast(double a)
-{
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-    double e = fma(-(y * y), a, 1.0);
-    double t = fma(e, 0.375, 0.5);
-    double ye = y * e;
-    y = fma(t, ye, y);
-    e = fma(-(y * y), a, 1.0);
-    y = fma(0.5 * y, e, y);
-    return y;
-}
-__device__ __forceinline__ double rcp_fast(double a)
-{
-    double x;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
-    double e = fma(-a, x, 1.0);
-    x = fma(x, e, x);
-    e = fma(-a, x, 1.0);
-    x = fma(x, e, x);
-    return x;
-}
-
-// 8x8 Cholesky + inverse with NO cross-lane traffic: every lane factors the whole tile redundantly in
-// registers (the shuffle network and shared memory are saturated by the bulk warps' operand loads, which
-// is what makes the shuffle-based chol8_inv slow inside the kernel). The Schur update uses the reciprocal
-// pivot from its own MUFU+Newton chain, so the rsqrt that scales column p is off the critical path. Lane c
-// solves column c of W = L^-1. Input: tile at `in_a` in accumulator (row-major) layout; outputs L at `L_a`
-// and W at `W_a` in operand layout (`in_a` may equal `L_a`). Returns 0 or 1 + index of the first bad pivot.
-__device__ __forceinline__ int chol8_red(uint32_t in_a, uint32_t L_a, uint32_t W_a, int lane, int nreal)
-{
-    double s[8][8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j <= i; j += 2) {
-            const double2 v = lds128(in_a + (uint32_t)(i * 8 + j) * 8u);
-            s[i][j] = v.x;
-            if (j + 1 <= i) s[i][j + 1] = v.y;
-        }
-    double rinv[8];
-    int bad = 0;
-#pragma unroll
-    for (int p = 0; p < 8; ++p) {
-        const double d = s[p][p];
-        if (!(d > 0.0) && p < nreal && bad == 0) bad = p + 1;
-        const double r = rcp_fast(d);
-        const double ri = rsqrt_fast(d);
-        rinv[p] = ri;
-        double t[8];
-#pragma unroll
-        for (int i = p + 1; i < 8; ++i) t[i] = s[i][p] * r;
-#pragma unroll
-        for (int i = p + 1; i < 8; ++i)
-#pragma unroll
-            for (int j = p + 1; j <= i; ++j) s[i][j] = fma(-t[i], s[j][p], s[i][j]);
-#pragma unroll
-        for (int i = p + 1; i < 8; ++i) s[i][p] *= ri;
-        s[p][p] = d * ri;
-    }
-    const int c = lane & 7;
-    double w[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        double acc = (i == c) ? 1.0 : 0.0;
-#pragma unroll
-        for (int k = 0; k < i; ++k) acc = fma(-s[i][k], w[k], acc);
-        w[i] = acc * rinv[i];
-    }
-    __syncwarp();   // every lane has read the input tile before it is overwritten
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4 && j <= i; ++j)
-            sts128(L_a + (uint32_t)op_idx(i, j) * 8u, s[i][j], (j + 4 <= i) ? s[i][j + 4] : 0.0);
-    if (lane < 8) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) sts64(W_a + (uint32_t)op_idx(i, c) * 8u, w[i]);
-    }
-    return bad;
-}
-
 // In-register Cholesky of an 8x8 tile held in DMMA accumulator layout (lane (r = l>>2, j = l&3)
 // holds columns 2j, 2j+1 of row r), together with its inverse built by the same row operations
 // (L^-1 A = L^T, so the operations that reduce A to L^T turn I into L^-1).

@@ -14,10 +14,9 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-9
 
 
-@pytest.fixture(params=[1, 2, 3, 4], ids=["column-kernel", "tile-kernel", "dataflow-kernel", "panel-kernel"])
+@pytest.fixture(params=[1, 2], ids=["column-kernel", "tile-kernel"])
 def veng(engine, request):
-    """The engine pinned to one factorisation kernel (1 = shared-memory column, 2 = DMMA tile with CTA
-    barriers, 3 = DMMA tile with dataflow flags, 4 = panel-warp dataflow)."""
+    """The engine pinned to one factorisation kernel (1 = shared-memory column, 2 = DMMA tile)."""
     engine.set_variant(request.param)
     yield engine
     engine.set_variant(0)
