@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(kThreads, 2) rank_append_kernel(const FusedArg
             if (R == 1) {
                 // ---- one new tile row (appends of <= 8 points): the HBM-bound case ------------------------
                 // Row J of the stored factor contributes X_J = (A(g0,J) - sum_{P<J} X_P L_JP^T) W_J^T. Warp w
-                // streams row J0+w (4 tiles = 2 KB in flight per warp, next to the matching tiles of the new
+                // streams row J0+w (8 tiles = 4 KB in flight per warp, next to the matching tiles of the new
                 // row from L1/L2) for the columns P < J0; the last <= 7 terms use the X tiles of this block,
                 // handed from warp to warp through shared memory.
                 const double *xrow = Lb + (size_t)tri(g0) * 64 + lane * 2;      // the new row (A operand)
@@ -573,20 +573,23 @@ __global__ void __launch_bounds__(kThreads, 2) rank_append_kernel(const FusedArg
                     double y0 = 0.0, y1 = 0.0;                                   // z_g0 sum (last row only)
                     if (rowv) {
                         int P = 0;
-                        for (; P + 4 <= J0; P += 4) {
-                            double2 bf[4], af[4];
+                        for (; P + 8 <= J0; P += 8) {      // 4 KB of the stored row in flight per warp
+                            double2 bf[8], af[4];
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) bf[i] = ldg128_stream(lrow + (size_t)(P + i) * 64);
+                            for (int i = 0; i < 8; ++i) bf[i] = ldg128_stream(lrow + (size_t)(P + i) * 64);
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) af[i] = ldg128(xrow + (size_t)(P + i) * 64);
+                            for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                dmma(a0, a1, af[i].x, bf[i].x);
-                                dmma(b0, b1, af[i].y, bf[i].y);
+                                for (int i = 0; i < 4; ++i) af[i] = ldg128(xrow + (size_t)(P + hh * 4 + i) * 64);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    dmma(a0, a1, af[i].x, bf[hh * 4 + i].x);
+                                    dmma(b0, b1, af[i].y, bf[hh * 4 + i].y);
+                                }
                             }
                             if (last) {
 #pragma unroll
-                                for (int i = 0; i < 4; ++i) {
+                                for (int i = 0; i < 8; ++i) {
                                     const double2 zf = ldg128(zrow + (size_t)(P + i) * 64);
                                     dmma(y0, y1, zf.x, bf[i].x);
                                     dmma(y0, y1, zf.y, bf[i].y);
