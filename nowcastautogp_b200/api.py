@@ -204,6 +204,17 @@ def _forecast_with_nowcasts(base_model: GPModel, nowcasts: Sequence[TData], fore
     y2 = np.ascontiguousarray(np.stack([yt.apply(np.asarray(nc.y, np.float64)) for nc in nowcasts]))
     ens = m.ensemble()
 
+    if n_hmc == 0 and forecast_n_hmc is None and k > 16:
+        # more nowcast points than the scenario-append kernel keeps in registers: one fused factorisation per
+        # (scenario, particle) with the shared hyperparameters, then the same ESS/resample/draw kernel
+        zeta = rng.standard_normal((K, D, h))
+        u = rng.uniform(size=(K, D))
+        u_res = rng.uniform(size=(K, P)) if ess_threshold > 0.0 else None
+        r = eng.forecast_instances(ens, n, k, h, t, y1, y2, m.log_weights, yt.slope, yt.intercept, g=g, step=step,
+                                   check=True)
+        x, _, _ = eng.draw(r["logw"], r["mu"], r["L"], zeta, u=u, u_res=u_res, ess_thr=ess_threshold)
+        return np.ascontiguousarray(x), r["logw"]
+
     if n_hmc == 0 and forecast_n_hmc is None:
         # default path: factor once per particle, append K scenarios, ESS/resample, draw — one call
         zeta = rng.standard_normal((K, D, h))

@@ -653,6 +653,7 @@ int32_t nagp_append(nagp_ctx *ctx, const nagp_factor *f, int64_t K, const double
     if (!f || K <= 0 || !logw || (f->k > 0 && !y2)) return fail(ctx, NAGP_E_ARG, "nagp_append: null or empty argument");
     if (f->appendable) return fail(ctx, NAGP_E_ARG, "nagp_append: factor was created by nagp_factor_store_large (use nagp_factor_append)");
     if (f->device != ctx->device) return fail(ctx, NAGP_E_ARG, "factor lives on another device");
+    if (f->k > 16) return fail(ctx, NAGP_E_SIZE, "nagp_append: more than 16 nowcast points (use nagp_forecast_instances)");
     NAGP_CUDA(ctx, cudaSetDevice(ctx->device));
     NAGP_TRY(arena_reset(ctx));
     AppendArgs a{};
@@ -755,6 +756,7 @@ int32_t nagp_forecast_with_nowcasts(nagp_ctx *ctx, int64_t K, int64_t P, int64_t
         !y1 || (k > 0 && !y2) || !zeta || !x || !info || (!comp && !u) || ya == 0.0)
         return fail(ctx, NAGP_E_ARG, "nagp_forecast_with_nowcasts: null or empty argument");
     if (u_res && !u) return fail(ctx, NAGP_E_ARG, "nagp_forecast_with_nowcasts: resampling needs u");
+    if (k > 16) return fail(ctx, NAGP_E_SIZE, "nagp_forecast_with_nowcasts: more than 16 nowcast points (use nagp_forecast_instances + nagp_draw)");
     NAGP_TRY(check_dims(ctx, n, k, h));
     if (on_device(prog_off) || on_device(theta_off))
         return fail(ctx, NAGP_E_ARG, "prog_off/theta_off must be host arrays");

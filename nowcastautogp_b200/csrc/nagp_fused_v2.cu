@@ -44,7 +44,12 @@ namespace nagp {
 
 namespace {
 
-constexpr int kMaxTilesPerWarp = 4;   // ceil(nt / kWarps), nt <= 29
+#ifndef NAGP_V2_WARPS
+#define NAGP_V2_WARPS 8
+#endif
+constexpr int kW2 = NAGP_V2_WARPS;      // warps per CTA of the tile kernel
+constexpr int kT2 = kW2 * 32;
+constexpr int kMaxTilesPerWarp = (29 + kW2 - 1) / kW2;   // ceil(nt / kW2), nt <= 29
 
 // DMMA inner loop of the left-looking update for NA tile rows of one warp: per P one 16-byte LDS for
 // the shared B fragment (tile (Jc, P)), and per row one 16-byte LDS + two DMMAs (one per k-chunk, on
@@ -75,13 +80,13 @@ struct V2Layout {
     unsigned long long *work_counter;   // dynamic instance scheduler (zeroed before the launch)
 };
 
-__global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a, const V2Layout lay)
+__global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, const V2Layout lay)
 {
     extern __shared__ __align__(16) double smem[];
     __shared__ TreeProgram tp;
     __shared__ int s_info;
     __shared__ long long s_next;
-    __shared__ double s_red[4][kWarps];
+    __shared__ double s_red[4][kW2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = a.n, k = a.k, h = a.h, m = n + k, q = m + h;
@@ -103,7 +108,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
     double *tab = reinterpret_cast<double *>(aux(4));
 
     // times are common to every instance of the launch
-    for (int i = tid; i < Q; i += kThreads) {
+    for (int i = tid; i < Q; i += kT2) {
         tt[i] = i < q ? a.t[i] : 0.0;
         gg[i] = (a.g && i < q) ? a.g[i] : 0;
     }
@@ -127,7 +132,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
             if (ntheta > MAX_THETA) tp.error = -3;
             else tree_compile(tp, a.prog + po, (int)plen, (int)ntheta, G > 0 ? a.ntab_cap : 0, a.ncp_cap);
         }
-        for (int i = tid; i < ntheta && i < MAX_THETA; i += kThreads) th[i] = theta_g[i];
+        for (int i = tid; i < ntheta && i < MAX_THETA; i += kT2) th[i] = theta_g[i];
         __syncthreads();
         if (tp.error) {
             if (tid == 0) {
@@ -142,13 +147,13 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
 
         DBG_G(1);
         // ---- lag tables and changepoint sigma tables ------------------------------------------------
-        for (int e = tid; e < ntab * G; e += kThreads) {
+        for (int e = tid; e < ntab * G; e += kT2) {
             int id = e / G, lg = e - id * G;
             int s0 = tp.tab_src0[id], s1 = tp.tab_src1[id];
             tab[e] = tree_eval(tp.sop + s0, tp.sarg + s0, nullptr, s1 - s0, th, 0.0, 0.0,
                                (double)lg * a.step, 0, nullptr, 0, nullptr, 0, 0, 0);
         }
-        for (int e = tid; e < ncp * Q; e += kThreads) {
+        for (int e = tid; e < ncp * Q; e += kT2) {
             int id = e / Q, i = e - id * Q;
             const double *cp = th + tp.cp_theta[id];
             sig[e] = 0.5 * (1.0 + tanh((tt[i] - cp[0]) / cp[1]));
@@ -167,7 +172,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
         cx.step = a.step; cx.G = G; cx.Q = Q; cx.grid = a.g != nullptr;
         {
             const int gr = lane >> 2, gc = (lane & 3) * 2;
-            for (int t0 = warp * 2; t0 < ntiles; t0 += kWarps * 2) {
+            for (int t0 = warp * 2; t0 < ntiles; t0 += kW2 * 2) {
                 int ii[4], jj[4], lag[4], tixs[2];
                 bool real[4];
 #pragma unroll
@@ -214,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
         }
         {
             const double *y1 = a.y1 + b * a.y1_stride;
-            for (int jx = tid; jx < Q; jx += kThreads) {
+            for (int jx = tid; jx < Q; jx += kT2) {
                 double v = 0.0;
                 if (jx < n) v = y1[jx];
                 else if (jx < ny) v = a.y2 ? a.y2[s * k + (jx - n)] : y1[jx];
@@ -234,14 +239,14 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
         const int oi0 = op_idx(lr, 2 * lj), oi1 = op_idx(lr, 2 * lj + 1);
         const int cv0 = (lane & ~3) + (lj >> 1), cv1 = cv0 + 2;
         const bool odd = lane & 1;
-        const int nreg = warp < nt ? (nt - 1 - warp) / kWarps + 1 : 0;   // regular rows of this warp
-        const int Ilast = warp + (nreg - 1) * kWarps;
-        const bool has_y = ((nt - warp) & (kWarps - 1)) == 0;
+        const int nreg = warp < nt ? (nt - 1 - warp) / kW2 + 1 : 0;   // regular rows of this warp
+        const int Ilast = warp + (nreg - 1) * kW2;
+        const bool has_y = (warp == nt % kW2);
         const uint32_t tiles_a = smem_addr(tiles), yv_a = smem_addr(yv), invL_a = smem_addr(invL);
         uint32_t rowa[kMaxTilesPerWarp];        // shared address of this lane's fragment in tile (I_u, 0)
 #pragma unroll
         for (int u = 0; u < kMaxTilesPerWarp; ++u) {
-            const int I = Ilast - u * kWarps;
+            const int I = Ilast - u * kW2;
             rowa[u] = tiles_a + (uint32_t)(tri(I > 0 ? I : 0) * 512 + lane * 16);
         }
         double accn[kMaxTilesPerWarp][2][2];   // [slot][k-chunk chain][acc regs] partial sums of the current column
@@ -256,13 +261,17 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
             return;
 #endif
             if (P0 >= P1) return;
-            const int NA = Ilast >= Jc ? (Ilast - Jc) / kWarps + 1 : 0;
+            const int NA = Ilast >= Jc ? (Ilast - Jc) / kW2 + 1 : 0;
             const uint32_t bp = tiles_a + (uint32_t)(tri(Jc) * 512 + lane * 16);
             switch (NA) {
-            case 1: kloop<1>(accn, bp, rowa, P0, P1); break;
-            case 2: kloop<2>(accn, bp, rowa, P0, P1); break;
-            case 3: kloop<3>(accn, bp, rowa, P0, P1); break;
-            case 4: kloop<4>(accn, bp, rowa, P0, P1); break;
+            case 1: kloop<(kMaxTilesPerWarp >= 1 ? 1 : 1)>(accn, bp, rowa, P0, P1); break;
+            case 2: kloop<(kMaxTilesPerWarp >= 2 ? 2 : 1)>(accn, bp, rowa, P0, P1); break;
+            case 3: kloop<(kMaxTilesPerWarp >= 3 ? 3 : 1)>(accn, bp, rowa, P0, P1); break;
+            case 4: kloop<(kMaxTilesPerWarp >= 4 ? 4 : 1)>(accn, bp, rowa, P0, P1); break;
+            case 5: kloop<(kMaxTilesPerWarp >= 5 ? 5 : 1)>(accn, bp, rowa, P0, P1); break;
+            case 6: kloop<(kMaxTilesPerWarp >= 6 ? 6 : 1)>(accn, bp, rowa, P0, P1); break;
+            case 7: kloop<(kMaxTilesPerWarp >= 7 ? 7 : 1)>(accn, bp, rowa, P0, P1); break;
+            case 8: kloop<(kMaxTilesPerWarp >= 8 ? 8 : 1)>(accn, bp, rowa, P0, P1); break;
             default: break;
             }
             if (has_y) {
@@ -279,8 +288,8 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
         };
 
         for (int J = 0; J < nt; ++J) {
-            const bool owner = (warp == (J & (kWarps - 1)));
-            const int NA = Ilast >= J ? (Ilast - J) / kWarps + 1 : 0;   // active regular rows (I >= J)
+            const bool owner = (warp == (J % kW2));
+            const int NA = Ilast >= J ? (Ilast - J) / kW2 + 1 : 0;   // active regular rows (I >= J)
             // (1) remaining terms of column J, (2) C = A_IJ - sum
             DBG_T(J, 0);
             accumulate(J, pre_done, J);
@@ -321,20 +330,20 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
                 if (bad && lane == 0 && NAGP_EXP == 0) s_info = J * 8 + bad;
                 __syncwarp();
                 DBG_T(J, 2);
-                asm volatile("bar.arrive 1, %0;" ::"n"(kThreads) : "memory");
+                asm volatile("bar.arrive 1, %0;" ::"n"(kT2) : "memory");
                 pre_done = 0;   // its own lookahead is deferred to the next column (hidden behind that owner)
             } else if ((warp & 3) == (J & 3)) {
                 // shares its scheduler (and FP64 pipe) with the owner: leave the pipe to the serial
                 // diagonal factorisation and catch up at the top of the next column
                 pre_done = 0;
                 DBG_T(J, 2);
-                asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(kT2) : "memory");
             } else {
                 // (4) lookahead: column J+1 over P < J
                 if (J + 1 < nt) accumulate(J + 1, 0, J);
                 pre_done = J;
                 DBG_T(J, 2);
-                asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(kT2) : "memory");
             }
             // (5) triangular solve of the column: X = C * invL^T, stored in operand layout
             DBG_T(J, 3);
@@ -395,7 +404,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
         // ---- logML(n), logML(m) ----------------------------------------------------------------------
         const double *z = yv;
         double ld_n = 0, ld_m = 0, qd_n = 0, qd_m = 0;
-        for (int r = tid; r < m; r += kThreads) {
+        for (int r = tid; r < m; r += kT2) {
             double l = log(Lel(r, r));
             double zz = r < ny ? z[r] * z[r] : 0.0;
             ld_m += l; qd_m += zz;
@@ -406,7 +415,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
         __syncthreads();
         if (tid == 0) {
             double r0 = 0, r1 = 0, r2 = 0, r3 = 0;
-            for (int w = 0; w < kWarps; ++w) { r0 += s_red[0][w]; r1 += s_red[1][w]; r2 += s_red[2][w]; r3 += s_red[3][w]; }
+            for (int w = 0; w < kW2; ++w) { r0 += s_red[0][w]; r1 += s_red[1][w]; r2 += s_red[2][w]; r3 += s_red[3][w]; }
             const double log2pi = 1.8378770664093454835606594728112;
             double lmn = -0.5 * ((double)n * log2pi + 2.0 * r0 + r2);
             double lmm = have_y2 ? -0.5 * ((double)m * log2pi + 2.0 * r1 + r3) : nan("");
@@ -421,7 +430,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
         const int kh = k + h;
         if (a.mu && have_y2) {
             // one warp per forecast row: lanes stride the m columns, then reduce
-            for (int r = warp; r < h; r += kWarps) {
+            for (int r = warp; r < h; r += kW2) {
                 double accv = 0.0;
                 for (int cix = lane; cix < m; cix += 32) accv = fma(Lel(m + r, cix), z[cix], accv);
                 accv = warp_sum(accv);
@@ -429,13 +438,13 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
             }
         }
         if (a.L33) {
-            for (int e = tid; e < h * h; e += kThreads) {
+            for (int e = tid; e < h * h; e += kT2) {
                 int r = e / h, cix = e - r * h;
                 a.L33[b * h * h + e] = cix <= r ? Lel(m + r, m + cix) / a.ya : 0.0;
             }
         }
         if (a.proj) {
-            for (int r = warp; r < kh; r += kWarps) {
+            for (int r = warp; r < kh; r += kW2) {
                 double accv = 0.0;
                 for (int cix = lane; cix < n; cix += 32) accv = fma(Lel(n + r, cix), z[cix], accv);
                 accv = warp_sum(accv);
@@ -443,7 +452,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_v2_kernel(const FusedArgs a
             }
         }
         if (a.Ltail) {
-            for (int e = tid; e < kh * kh; e += kThreads) {
+            for (int e = tid; e < kh * kh; e += kT2) {
                 int r = e / kh, cix = e - r * kh;
                 a.Ltail[b * kh * kh + e] = cix <= r ? Lel(n + r, n + cix) : 0.0;
             }
@@ -464,7 +473,7 @@ void aux_sizes(int Q, int G, int ntheta_cap, int ntab_cap, int ncp_cap, size_t (
 
 }  // namespace
 
-int fused_v2_max_q() { return 8 * (kMaxTilesPerWarp * kWarps - 1); }
+int fused_v2_max_q() { return 8 * (kMaxTilesPerWarp * kW2 - 1); }
 
 // Plans shared memory for the tile kernel: the tiles, yv and invL are mandatory; the aux arrays go
 // to shared memory in priority order while the CTA stays within `budget` bytes, else to global
@@ -501,7 +510,7 @@ int fused_v2_grid(const V2Plan &pl, int64_t B, int num_sms)
 {
     int per_sm = 0;
     cudaFuncSetAttribute(fused_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_v2_kernel, kThreads, pl.smem_bytes) != cudaSuccess ||
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_v2_kernel, kT2, pl.smem_bytes) != cudaSuccess ||
         per_sm < 1) {
         cudaGetLastError();
         per_sm = 1;
@@ -523,7 +532,7 @@ cudaError_t launch_fused_v2(const FusedArgs &a, const V2Plan &pl, char *scratch,
     lay.scratch = scratch;
     cudaError_t e = cudaFuncSetAttribute(fused_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (e != cudaSuccess) return e;
-    fused_v2_kernel<<<grid, kThreads, pl.smem_bytes, stream>>>(a, lay);
+    fused_v2_kernel<<<grid, kT2, pl.smem_bytes, stream>>>(a, lay);
     return cudaGetLastError();
 }
 
