@@ -249,25 +249,6 @@ int32_t run_fused(nagp_ctx *ctx, FusedArgs a, const int64_t *theta_off_host)
     if (ctx->variant != 1 && q <= fused_v2_max_q()) {
         int64_t nth = 1;
         for (int64_t p = 0; p < a.P; ++p) nth = std::max(nth, theta_off_host[p + 1] - theta_off_host[p]);
-        if (ctx->variant == 3) {
-            const bool need_tail = a.mu || a.L33 || a.proj || a.Ltail;
-            SqPlan sp = plan_fused_sq(q, a.n, need_tail, a.G, (int)std::min<int64_t>(nth, MAX_THETA), a.ntab_cap,
-                                      a.ncp_cap, ctx->smem_per_sm);
-            if (sp.ok) {
-                const int grid = fused_sq_grid(sp, a.B, ctx->num_sms);
-                if (getenv("NAGP_DEBUG"))
-                    fprintf(stderr, "[nagp] recycled-tile kernel: q=%d H=%d Tt=%d smem=%zu B aux_in_smem=%d%d%d%d%d scratch/CTA=%d grid=%d\n",
-                            q, sp.H, sp.Tt, sp.smem_bytes, sp.aux_smem[0], sp.aux_smem[1], sp.aux_smem[2], sp.aux_smem[3],
-                            sp.aux_smem[4], sp.scratch_stride, grid);
-                char *scr = nullptr;
-                if (sp.scratch_stride) NAGP_TRY(scratch(ctx, (size_t)grid * sp.scratch_stride, &scr));
-                unsigned long long *counter = nullptr;
-                NAGP_TRY(scratch(ctx, 1, &counter));
-                NAGP_CUDA(ctx, launch_fused_sq(a, sp, scr, counter, grid, ctx->stream));
-                ctx->launches += 1;
-                return NAGP_OK;
-            }
-        }
         V2Plan pl = plan_fused_v2(q, a.G, (int)std::min<int64_t>(nth, MAX_THETA), a.ntab_cap, a.ncp_cap,
                                   ctx->smem_optin, ctx->smem_per_sm);
         if (pl.ok) {
@@ -339,7 +320,6 @@ int32_t nagp_init(int32_t device, nagp_ctx **out)
         return fail(nullptr, NAGP_E_CUDA, std::string("context setup: ") + cudaGetErrorString(e));
     }
     ctx->stream = ctx->own_stream;
-    if (const char *ev = getenv("NAGP_VARIANT")) ctx->variant = atoi(ev);   // kernel-selection experiments
     *out = ctx;
     return NAGP_OK;
 }
@@ -376,7 +356,7 @@ int64_t nagp_launch_count(const nagp_ctx *ctx) { return ctx ? ctx->launches : 0;
 
 int32_t nagp_set_variant(nagp_ctx *ctx, int32_t variant)
 {
-    if (!ctx || variant < 0 || variant > 3) return NAGP_E_ARG;
+    if (!ctx || variant < 0 || variant > 2) return NAGP_E_ARG;
     ctx->variant = variant;
     return NAGP_OK;
 }

@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
     __shared__ int s_info;
     __shared__ long long s_next;
     __shared__ double s_red[4][kW2];
+    __shared__ unsigned char s_ti[436];         // packed tile index -> tile row I (J = index - tri(I)), nt <= 29
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = a.n, k = a.k, h = a.h, m = n + k, q = m + h;
@@ -107,6 +108,8 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
     double *sig = reinterpret_cast<double *>(aux(3));
     double *tab = reinterpret_cast<double *>(aux(4));
 
+    for (int I = tid; I < nt; I += kT2)
+        for (int J = 0; J <= I; ++J) s_ti[tri(I) + J] = (unsigned char)I;
     // times are common to every instance of the launch
     for (int i = tid; i < Q; i += kT2) {
         tt[i] = i < q ? a.t[i] : 0.0;
@@ -175,14 +178,13 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
             for (int t0 = warp * 2; t0 < ntiles; t0 += kW2 * 2) {
                 int ii[4], jj[4], lag[4], tixs[2];
                 bool real[4];
+                bool interior = true;      // both tiles strictly below the diagonal and free of padding
 #pragma unroll
                 for (int h2 = 0; h2 < 2; ++h2) {
                     const int tix = min(t0 + h2, ntiles - 1);
                     tixs[h2] = tix;
-                    int I = (int)((sqrtf(8.0f * (float)tix + 1.0f) - 1.0f) * 0.5f);
-                    I += (tri(I + 1) <= tix);
-                    I -= (tri(I) > tix);
-                    const int J = tix - tri(I);
+                    const int I = s_ti[tix], J = tix - tri(I);
+                    interior = interior && I > J && I * 8 + 7 < q;
                     const int gi = gg[I * 8 + gr];
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
@@ -207,10 +209,12 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                 } else {
                     tree_eval4(tp, cx, ii, jj, lag, out);
                 }
+                if (!interior) {
 #pragma unroll
-                for (int x = 0; x < 4; ++x) {
-                    if (!real[x]) out[x] = (ii[x] == jj[x]) ? 1.0 : 0.0;
-                    else if (ii[x] == jj[x]) out[x] += (ii[x] < m) ? d_lo : d_hi;
+                    for (int x = 0; x < 4; ++x) {
+                        if (!real[x]) out[x] = (ii[x] == jj[x]) ? 1.0 : 0.0;
+                        else if (ii[x] == jj[x]) out[x] += (ii[x] < m) ? d_lo : d_hi;
+                    }
                 }
                 *reinterpret_cast<double2 *>(tiles + tixs[0] * 64 + lane * 2) = make_double2(out[0], out[1]);
                 if (t0 + 1 < ntiles)
@@ -487,7 +491,10 @@ V2Plan plan_fused_v2(int q, int G, int ntheta_cap, int ntab_cap, int ncp_cap, in
     size_t sz[5];
     aux_sizes(Q, G, ntheta_cap, ntab_cap, ncp_cap, sz);
     size_t total_aux = sz[0] + sz[1] + sz[2] + sz[3] + sz[4];
-    const size_t static_smem = 1536 + 1024;   // TreeProgram + reductions + per-CTA reservation
+    cudaFuncAttributes fa{};
+    size_t static_smem = 2560 + 1024;
+    if (cudaFuncGetAttributes(&fa, fused_v2_kernel) == cudaSuccess) static_smem = fa.sharedSizeBytes + 1024;   // + per-CTA reservation
+    else cudaGetLastError();
     // budget: 2 CTAs/SM if the mandatory part allows it, else everything the opt-in limit gives
     size_t two = (size_t)smem_per_sm / 2;
     size_t budget = (base + static_smem <= two) ? two - static_smem : (size_t)smem_optin - 1536;

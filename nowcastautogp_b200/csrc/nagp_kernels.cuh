@@ -59,21 +59,6 @@ int fused_v2_grid(const V2Plan &pl, int64_t B, int num_sms);
 cudaError_t launch_fused_v2(const FusedArgs &a, const V2Plan &pl, char *scratch, unsigned long long *work_counter,
                             int grid, cudaStream_t stream);
 
-// Recycled-tile kernel (variant 3): factor in an H x H square of tiles, Gram one column ahead; 3 CTAs per SM.
-struct SqPlan {
-    int ok;
-    int nt, H, Tt, ntail;
-    int off_tail, off_gbuf, off_yv, off_invL, off_aux;
-    int aux_off[5];
-    int aux_smem[5];
-    int scratch_stride;
-    size_t smem_bytes;
-};
-SqPlan plan_fused_sq(int q, int n, bool need_tail, int G, int ntheta_cap, int ntab_cap, int ncp_cap, int smem_per_sm);
-int fused_sq_grid(const SqPlan &pl, int64_t B, int num_sms);
-cudaError_t launch_fused_sq(const FusedArgs &a, const SqPlan &pl, char *scratch, unsigned long long *work_counter,
-                            int grid, cudaStream_t stream);
-
 // Large path (q beyond shared memory): factor in HBM as tile-packed operand-layout tiles.
 struct LargePlan {
     int ok;

@@ -14,10 +14,9 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-9
 
 
-@pytest.fixture(params=[1, 2, 3], ids=["column-kernel", "tile-kernel", "recycled-tile-kernel"])
+@pytest.fixture(params=[1, 2], ids=["column-kernel", "tile-kernel"])
 def veng(engine, request):
-    """The engine pinned to one factorisation kernel (1 = shared-memory column, 2 = DMMA tile, 3 = DMMA tile
-    with recycled shared-memory tiles; 3 falls back to 2 where its plan does not apply)."""
+    """The engine pinned to one factorisation kernel (1 = shared-memory column, 2 = DMMA tile)."""
     engine.set_variant(request.param)
     yield engine
     engine.set_variant(0)
