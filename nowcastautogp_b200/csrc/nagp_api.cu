@@ -36,6 +36,7 @@ struct nagp_ctx {
     std::vector<Chunk> chunks;
     size_t chunk_off = 0;          // bump offset in chunks.back()
     std::vector<PendingOut> outs;
+    std::vector<nagp::TreeProgram> compiled;   // host-compiled programs of the current call (empty: compile on device)
 };
 
 struct nagp_factor {
@@ -216,6 +217,14 @@ int32_t plan_tables(nagp_ctx *ctx, int64_t P, const uint8_t *prog, const int64_t
         }
     }
     *ntab_cap = ntab; *ncp_cap = ncp;
+    ctx->compiled.clear();
+    if (prog && !on_device(prog) && !on_device(prog_off) && !on_device(theta_off)) {
+        // the programs as the device would compile them with the final capacities: uploaded once per call
+        ctx->compiled.resize((size_t)P);
+        for (int64_t p = 0; p < P; ++p)
+            tree_compile(ctx->compiled[p], prog + prog_off[p], (int)(prog_off[p + 1] - prog_off[p]),
+                         (int)(theta_off[p + 1] - theta_off[p]), G > 0 ? ntab : 0, ncp);
+    }
     return NAGP_OK;
 }
 
@@ -252,6 +261,8 @@ int32_t run_fused(nagp_ctx *ctx, FusedArgs a, const int64_t *theta_off_host)
         V2Plan pl = plan_fused_v2(q, a.G, (int)std::min<int64_t>(nth, MAX_THETA), a.ntab_cap, a.ncp_cap,
                                   ctx->smem_optin, ctx->smem_per_sm);
         if (pl.ok) {
+            if ((int64_t)ctx->compiled.size() == a.P)
+                NAGP_TRY(stage_in(ctx, ctx->compiled.data(), ctx->compiled.size(), &a.compiled));
             int grid = fused_v2_grid(pl, a.B, ctx->num_sms);
             if (getenv("NAGP_DEBUG"))
                 fprintf(stderr, "[nagp] tile kernel: q=%d G=%d caps(tab=%d,cp=%d,theta=%d) smem=%zu B aux_in_smem(th,gg,tt,sig,tab)=%d%d%d%d%d scratch/CTA=%d grid=%d\n",

@@ -130,8 +130,13 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
         const double *theta_g = a.theta + s * a.theta_stride_k + to;
 
         DBG_G(0);
-        if (tid == 0) {
-            s_info = 0;
+        if (tid == 0) s_info = 0;
+        if (a.compiled) {
+            // compiled once per particle on the host: every (scenario, particle) instance just copies it
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(a.compiled + p);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(&tp);
+            for (int i = tid; i < (int)(sizeof(TreeProgram) / 4); i += kT2) dst[i] = src[i];
+        } else if (tid == 0) {
             if (ntheta > MAX_THETA) tp.error = -3;
             else tree_compile(tp, a.prog + po, (int)plen, (int)ntheta, G > 0 ? a.ntab_cap : 0, a.ncp_cap);
         }

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "nagp_tree.cuh"
+
 namespace nagp {
 
 // One fused Gram -> Cholesky -> solve problem per instance b in [0, B). Instance b belongs to
@@ -39,6 +41,7 @@ struct FusedArgs {
     double *Ltail;               // [B,k+h,k+h]: L[n+r][n+c] (scaled space, zeros above diagonal)
     int32_t *info;               // [B]
     int ntab_cap, ncp_cap;       // shared-memory table slots per CTA
+    const TreeProgram *compiled; // [P] programs compiled on the host with these capacities (nullable: compile on device)
 };
 
 size_t fused_smem_bytes_v1(int q, int G, int ntab_cap, int ncp_cap);
