@@ -19,6 +19,9 @@
 // Arithmetic contract: docs/KERNEL_SPEC.md §3-§6.
 #include <algorithm>
 
+#ifndef NAGP_QUIET_SIBLING
+#define NAGP_QUIET_SIBLING 0   // 1: the warp sharing the owner's scheduler skips the lookahead (measured neutral)
+#endif
 #ifndef NAGP_EXP
 #define NAGP_EXP 0   // timing-attribution experiments (tools/exp_build.sh); 0 in every product build
 #endif
@@ -341,7 +344,7 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                 DBG_T(J, 2);
                 asm volatile("bar.arrive 1, %0;" ::"n"(kT2) : "memory");
                 pre_done = 0;   // its own lookahead is deferred to the next column (hidden behind that owner)
-            } else if ((warp & 3) == (J & 3)) {
+            } else if (NAGP_QUIET_SIBLING && (warp & 3) == ((J % kW2) & 3)) {
                 // shares its scheduler (and FP64 pipe) with the owner: leave the pipe to the serial
                 // diagonal factorisation and catch up at the top of the next column
                 pre_done = 0;
