@@ -108,6 +108,10 @@ def cpu_reference(w, theta_k, noise_k, zeta, u, steps, warmup, target_s=12.0):
     """Reference schedule on the host cores (oracle port), bounded sample of the same workload."""
     from oracle.oracle import Oracle
     o = Oracle()
+    try:     # all host cores this process may use, whatever OMP_NUM_THREADS the launcher exported (torchrun sets 1)
+        o.set_num_threads(len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        o.set_num_threads(os.cpu_count() or 1)
     c = CFG
 
     def run(Ks):

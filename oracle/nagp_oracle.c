@@ -550,6 +550,16 @@ int32_t nagp_o_logml_batch(int64_t B, const uint8_t *prog, const int64_t *prog_o
     return worst;
 }
 
+/* bench.py's CPU arm: use every host core even when the launcher (torchrun) exported OMP_NUM_THREADS=1 */
+void nagp_o_set_num_threads(int32_t n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int32_t nagp_o_num_threads(void)
 {
 #ifdef _OPENMP

@@ -215,6 +215,9 @@ class Oracle:
           y.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), info.ctypes.data_as(C.c_void_p))
         return out, info
 
+    def set_num_threads(self, n: int) -> None:
+        self.lib.nagp_o_set_num_threads(int(n))
+
     def num_threads(self) -> int:
         return int(self.lib.nagp_o_num_threads())
 
