@@ -110,6 +110,24 @@ int32_t nagp_factor_store(nagp_ctx *ctx, int64_t P,
                           nagp_factor **out, double *logml_n, int32_t *info);
 void nagp_factor_free(nagp_factor *f);
 
+/* ---- (f1) gradient of the log marginal likelihood: what HMC on the hyperparameters differentiates ----
+ * AutoGP.mcmc_parameters! (/root/reference/src/forecasting.jl:148 and :65) and fit_smc!'s n_hmc steps
+ * (/root/reference/src/make_and_fit_model.jl:91) run HMC on each particle's hyperparameters; the gradient of
+ * the MVN log density is the expensive part. For K scenarios x P particles over the n + k observed points
+ * (y = [y1 | y2[s]]; theta/noise shared or per scenario as in nagp_forecast_instances):
+ *   logml[K*P]           log marginal likelihood over all n + k points
+ *   grad_theta[K*total]  d logML / d theta for every theta slot, same CSR layout as theta (per scenario)
+ *   grad_noise[K*P]      d logML / d noise
+ * Constrained-space derivatives; the caller applies its own chain rule to the unconstrained parameters.
+ * n + k <= 232 in this version (NAGP_E_SIZE beyond). */
+int32_t nagp_logml_grad(nagp_ctx *ctx, int64_t K, int64_t P,
+                        const uint8_t *prog, const int64_t *prog_off,
+                        const double *theta, const int64_t *theta_off, int64_t theta_stride_k,
+                        const double *noise, int64_t noise_stride_k,
+                        int64_t n, int64_t k, const double *t, const int32_t *g, double step,
+                        const double *y1, const double *y2,
+                        double *logml, double *grad_theta, double *grad_noise, int32_t *info);
+
 /* ---- (a2/a4) appendable factor for long series: SMC data annealing, rank-append Cholesky ---------
  * AutoGP.fit_smc! walks a schedule of growing observation counts (/root/reference/src/make_and_fit_model.jl:
  * 89-91, linear_schedule) and re-scores every particle from scratch at each step; add_data! does the same

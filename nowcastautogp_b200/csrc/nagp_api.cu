@@ -538,6 +538,71 @@ void nagp_factor_free(nagp_factor *f)
 }
 
 
+// ---- (f1) gradient of the log marginal likelihood: the HMC primitive --------------------------------------
+int32_t nagp_logml_grad(nagp_ctx *ctx, int64_t K, int64_t P, const uint8_t *prog, const int64_t *prog_off,
+                        const double *theta, const int64_t *theta_off, int64_t theta_stride_k,
+                        const double *noise, int64_t noise_stride_k, int64_t n, int64_t k, const double *t,
+                        const int32_t *g, double step, const double *y1, const double *y2,
+                        double *logml, double *grad_theta, double *grad_noise, int32_t *info)
+{
+    if (!ctx) return NAGP_E_ARG;
+    if (K <= 0 || P <= 0 || !prog || !prog_off || !theta || !theta_off || !noise || !t || !y1 || !logml ||
+        !grad_theta || !grad_noise || !info || (k > 0 && !y2) || n <= 0 || k < 0)
+        return fail(ctx, NAGP_E_ARG, "nagp_logml_grad: null or empty argument");
+    if (n + k > fused_v2_max_q()) return fail(ctx, NAGP_E_SIZE, "nagp_logml_grad: n + k > 232 not supported yet");
+    if (on_device(prog_off) || on_device(theta_off))
+        return fail(ctx, NAGP_E_ARG, "prog_off/theta_off must be host arrays");
+    NAGP_CUDA(ctx, cudaSetDevice(ctx->device));
+    NAGP_TRY(arena_reset(ctx));
+    const int64_t m = n + k, B = K * P, ntheta = theta_off[P];
+    const int nt = (int)((m + 7) / 8);
+    FusedArgs a{};
+    NAGP_TRY(grid_extent(ctx, g, m, &a.G));
+    NAGP_TRY(plan_tables(ctx, P, prog, prog_off, theta_off, (int)m, a.G, &a.ntab_cap, &a.ncp_cap));
+    a.B = B; a.P = P;
+    NAGP_TRY(stage_in(ctx, prog, (size_t)prog_off[P], &a.prog));
+    NAGP_TRY(stage_in(ctx, prog_off, (size_t)P + 1, &a.prog_off));
+    NAGP_TRY(stage_in(ctx, theta, (size_t)(theta_stride_k ? (K - 1) * theta_stride_k + ntheta : ntheta), &a.theta));
+    NAGP_TRY(stage_in(ctx, theta_off, (size_t)P + 1, &a.theta_off));
+    a.theta_stride_k = theta_stride_k;
+    NAGP_TRY(stage_in(ctx, noise, (size_t)(noise_stride_k ? (K - 1) * noise_stride_k + P : P), &a.noise));
+    a.noise_stride_k = noise_stride_k;
+    a.jitter = ctx->jitter; a.noise_pred = -1.0;
+    a.n = (int)n; a.k = (int)k; a.h = 0;
+    NAGP_TRY(stage_in(ctx, t, (size_t)m, &a.t));
+    NAGP_TRY(stage_in(ctx, g, (size_t)m, &a.g));
+    a.step = step;
+    NAGP_TRY(stage_in(ctx, y1, (size_t)n, &a.y1));
+    NAGP_TRY(stage_in(ctx, y2, (size_t)(K * k), &a.y2));
+    a.ya = 1.0; a.yb = 0.0;
+    NAGP_TRY(stage_out(ctx, logml, (size_t)B, &a.logml_m));
+    int32_t *d_info = nullptr;
+    NAGP_TRY(stage_out(ctx, info, (size_t)B, &d_info));
+    a.info = d_info;
+    NAGP_TRY(scratch(ctx, (size_t)B * (size_t)(nt * (nt + 1) / 2) * 64, &a.Lkeep));
+    NAGP_TRY(scratch(ctx, (size_t)B * nt * 8, &a.zkeep));
+    const int saved_variant = ctx->variant;
+    ctx->variant = 2;                                   // the tile kernel is the one that keeps the factor
+    const int32_t rc = run_fused(ctx, a, theta_off);
+    ctx->variant = saved_variant;
+    NAGP_TRY(rc);
+
+    GradArgs ga{};
+    ga.B = B; ga.P = P; ga.prog = a.prog; ga.prog_off = a.prog_off; ga.theta = a.theta; ga.theta_off = a.theta_off;
+    ga.theta_stride_k = theta_stride_k; ga.n = (int)m; ga.t = a.t; ga.g = a.g; ga.step = step;
+    ga.L = a.Lkeep; ga.z = a.zkeep; ga.info = d_info;
+    NAGP_TRY(stage_out(ctx, grad_theta, (size_t)(K * ntheta), &ga.grad_theta));
+    NAGP_TRY(stage_out(ctx, grad_noise, (size_t)B, &ga.grad_noise));
+    bool s_in_smem = true;
+    const size_t smem = grad_smem_bytes((int)m, ctx->smem_optin, &s_in_smem);
+    const int grid = (int)std::min<int64_t>(B, ctx->num_sms);
+    if (!s_in_smem) NAGP_TRY(scratch(ctx, (size_t)grid * m * m, &ga.S));
+    NAGP_CUDA(ctx, launch_grad(ga, grid, smem, ctx->stream));
+    ctx->launches += 1;
+    NAGP_TRY(finish(ctx));
+    return on_device(info) ? NAGP_OK : worst_info(info, B);
+}
+
 // ---- appendable factor store for long series (SMC data annealing, BASELINE config 5) -----------------
 int32_t nagp_factor_store_large(nagp_ctx *ctx, int64_t P, const uint8_t *prog, const int64_t *prog_off,
                                 const double *theta, const int64_t *theta_off, const double *noise,

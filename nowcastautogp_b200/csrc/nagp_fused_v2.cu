@@ -398,6 +398,15 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
         }
         DBG_G(4);
 
+        if (a.Lkeep && !s_info) {
+            // keep the factor for the gradient kernel: tiles as they are (operand layout), z padded to Q
+            double *Lo = a.Lkeep + (size_t)b * ((size_t)ntiles * 64);
+            for (int i = tid; i < ntiles * 32; i += kT2)
+                reinterpret_cast<double2 *>(Lo)[i] = reinterpret_cast<const double2 *>(tiles)[i];
+            double *zo = a.zkeep + (size_t)b * Q;
+            for (int i = tid; i < Q; i += kT2) zo[i] = yv[i];
+        }
+
         if (s_info) {
             if (tid == 0) {
                 a.info[b] = s_info;

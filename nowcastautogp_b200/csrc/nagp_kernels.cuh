@@ -42,6 +42,8 @@ struct FusedArgs {
     int32_t *info;               // [B]
     int ntab_cap, ncp_cap;       // shared-memory table slots per CTA
     const TreeProgram *compiled; // [P] programs compiled on the host with these capacities (nullable: compile on device)
+    double *Lkeep;               // nullable: the factor of every instance, tile-packed operand layout [B, tri(nt)*64]
+    double *zkeep;               // nullable (with Lkeep): z = L^-1 y per instance [B, 8*nt]
 };
 
 size_t fused_smem_bytes_v1(int q, int G, int ntab_cap, int ncp_cap);
@@ -84,6 +86,23 @@ cudaError_t launch_chol_large(const FusedArgs &a, const LargePlan &pl, char *scr
 // Extend the stored factors (slots 0..B-1) from n_old to a.n points in place; a.t/a.g/a.y1 cover all a.n points.
 cudaError_t launch_rank_append(const FusedArgs &a, const LargePlan &pl, char *scratch, double *L, double *W,
                                int n_old, double *logml, double *dlogml, int grid, cudaStream_t stream);
+
+// Gradient of the log marginal likelihood: consumes the factors kept by the tile kernel.
+struct GradArgs {
+    int64_t B, P;
+    const uint8_t *prog; const int64_t *prog_off;
+    const double *theta; const int64_t *theta_off; int64_t theta_stride_k;
+    int n;                       // observed points (k = h = 0)
+    const double *t; const int32_t *g; double step;
+    const double *L;             // [B, tri(nt)*64] kept factors
+    const double *z;             // [B, 8*nt]
+    double *grad_theta;          // [B/P scenarios][theta total]: d logML / d theta slot
+    double *grad_noise;          // [B]
+    double *S;                   // nullable global scratch [grid][n*n] when n*n doubles do not fit shared memory
+    const int32_t *info;         // [B] from the factorisation: instances with info != 0 get NaN gradients
+};
+size_t grad_smem_bytes(int n, int smem_optin, bool *s_in_smem);
+cudaError_t launch_grad(const GradArgs &a, int grid, size_t smem_bytes, cudaStream_t stream);
 
 // Scenario-shared fast path: per (scenario, particle) O(k^2 + hk) tail of the forward solve.
 struct AppendArgs {

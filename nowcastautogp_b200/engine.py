@@ -134,6 +134,33 @@ class Engine:
         self._check(rc, raise_posdef=check)
         return dict(logw=logw, mu=mu, L=L, info=info, logml_n=logml_n, logml_m=logml_m)
 
+    # ---- (f1) gradient of the log marginal likelihood -----------------------------------------------
+    def logml_grad(self, ens: FlatEnsemble, t, y1, y2=None, g=None, step: float = 0.0, theta=None, noise=None,
+                   K: int = 1, check: bool = False):
+        """logML over the n + k points [y1 | y2[s]] and its gradient w.r.t. every theta slot and the noise.
+        Returns (logml [K,P], grad_theta [K,total], grad_noise [K,P], info [K,P])."""
+        P = ens.size
+        n = len(y1)
+        k = 0 if y2 is None else int(np.asarray(y2).shape[-1])
+        if y2 is not None:
+            K = int(np.asarray(y2).shape[0])
+        elif theta is not None:
+            K = int(np.asarray(theta).shape[0])
+        total = int(ens.theta_off[-1])
+        logml, gth = np.empty((K, P)), np.empty((K, total))
+        gnz, info = np.empty((K, P)), np.zeros((K, P), np.int32)
+        th = ens.theta if theta is None else theta
+        nz = ens.noise if noise is None else noise
+        keep = [_ptr(ens.prog), _ptr(ens.prog_off), _ptr(th, np.float64), _ptr(ens.theta_off), _ptr(nz, np.float64),
+                _ptr(t, np.float64), _ptr(g, np.int32), _ptr(y1, np.float64), _ptr(y2, np.float64),
+                _ptr(logml), _ptr(gth), _ptr(gnz), _ptr(info)]
+        p = [x[0] for x in keep]
+        rc = self._lib.nagp_logml_grad(self._ctx, K, P, p[0], p[1], p[2], p[3], 0 if theta is None else total,
+                                       p[4], 0 if noise is None else P, n, k, p[5], p[6], step, p[7], p[8],
+                                       p[9], p[10], p[11], p[12])
+        self._check(rc, raise_posdef=check)
+        return logml, gth, gnz, info
+
     # ---- (a3)/(a4)/(a7) ----------------------------------------------------------------------------
     def factor_store(self, ens: FlatEnsemble, n, k, h, t, y1, logw0=None, ya=1.0, yb=0.0, g=None, step=0.0,
                      noise_pred=-1.0, check: bool = True) -> "Factor":
