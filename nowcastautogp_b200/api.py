@@ -4,8 +4,8 @@ same names, keyword arguments, assertion behaviour and return shapes.
 Mirrors `/root/reference/src/make_and_fit_model.jl:17-27,78-93` and
 `/root/reference/src/forecasting.jl:29-75,117-167`. Where the reference spawns one task per nowcast
 scenario and rebuilds the particle ensemble inside each (`forecasting.jl:131-133`), this module
-issues ONE batched device call over all (scenario, particle) instances; kernel-structure and
-parameter proposals stay on the CPU, every likelihood / factorisation / moment / draw is in libnagp.
+issues ONE batched device call over all (scenario, particle) instances; kernel-structure proposals and the
+HMC integrator stay on the CPU, every likelihood, gradient, factorisation, moment and draw is in libnagp.
 Random numbers come from a NumPy `Generator` (the reference uses Julia's task-local Xoshiro), so
 outputs agree with the reference in distribution, not draw by draw.
 """
@@ -16,7 +16,7 @@ from typing import Callable, List, Optional, Sequence
 
 import numpy as np
 
-from .gpmodel import GPConfig, GPModel, pack_particles, slot_transform
+from .gpmodel import GPConfig, GPModel, HMC_DEFAULT, pack_particles, slot_dtheta_dz, slot_transform
 from .tdata import TData
 from . import kernels as kn
 
@@ -118,6 +118,18 @@ class _ScenarioParams:
         else:
             nz = np.vectorize(lambda v: slot_transform("noise", v, cfg))(noise_z)
         return np.ascontiguousarray(th), np.ascontiguousarray(nz)
+
+    def jacobian(self, z, th, noise_z, nz):
+        """d theta / d z per slot [K, total] and d noise / d noise_z [K, P]."""
+        cfg = self.m.config
+        jz = np.empty_like(z)
+        for j, nm in enumerate(self.names):
+            jz[:, j] = [slot_dtheta_dz(nm, a, b, cfg) for a, b in zip(z[:, j], th[:, j])]
+        if cfg.noise is not None:
+            jn = np.zeros_like(noise_z)
+        else:
+            jn = np.vectorize(lambda a, b: slot_dtheta_dz("noise", a, b, cfg))(noise_z, nz)
+        return jz, jn
 
     def log_prior(self, z, noise_z):
         lp = np.zeros((self.K, self.P))
@@ -269,8 +281,53 @@ def _forecast_with_nowcasts(base_model: GPModel, nowcasts: Sequence[TData], fore
             sp.noise_z = np.where(acc, nzp, sp.noise_z)
             lm = np.where(acc, lmp, lm)
 
+    learn_noise = m.config.noise is None
+
+    def logpost_grad(z, noise_z):
+        """Per (scenario, particle): logML over [train | nowcast] + log N(z; 0, I), and d/dz — one device call."""
+        th_, nz_ = sp.theta(z, noise_z)
+        lmg, gth, gnz, info = eng.logml_grad(ens, t[:n + k], y1, y2=y2 if k else None, g=None if g is None else g[:n + k],
+                                             step=step, theta=th_, noise=nz_, K=K)
+        jz, jn = sp.jacobian(z, th_, noise_z, nz_)
+        lml = np.where(info == 0, lmg, -np.inf)
+        dz = np.where(np.isfinite(gth), gth, 0.0) * jz - z
+        dn = (np.where(np.isfinite(gnz), gnz, 0.0) * jn - noise_z) if learn_noise else np.zeros_like(noise_z)
+        return lml, lml + sp.log_prior(z, noise_z if learn_noise else np.zeros_like(noise_z)), dz, dn
+
+    def hmc(n_steps):
+        """`n_steps` HMC steps on all K x P chains at once (mcmc_parameters! on every scenario's model copy,
+        forecasting.jl:148 and :65): each leapfrog stage is one `nagp_logml_grad` call."""
+        nonlocal lm
+        from .engine import NagpError
+        L, eps = int(HMC_DEFAULT["n_leapfrog"]), float(HMC_DEFAULT["eps"])
+        try:
+            lml, lp, dz, dn = logpost_grad(sp.z, sp.noise_z)
+        except NagpError as e:
+            if e.code != -4:
+                raise
+            return metropolis(n_steps)
+        for _ in range(n_steps):
+            pz = rng.standard_normal(sp.z.shape)
+            pn = rng.standard_normal(sp.noise_z.shape) if learn_noise else np.zeros_like(sp.noise_z)
+            kin0 = np.zeros((K, P)); np.add.at(kin0.T, sp.owner, 0.5 * (pz * pz).T); kin0 += 0.5 * pn * pn
+            zq, nq, gz, gn, lp_q, lml_q = sp.z.copy(), sp.noise_z.copy(), dz, dn, lp, lml
+            for _l in range(L):
+                pz = pz + 0.5 * eps * gz; pn = pn + 0.5 * eps * gn
+                zq = zq + eps * pz; nq = nq + eps * pn
+                lml_q, lp_q, gz, gn = logpost_grad(zq, nq)
+                pz = pz + 0.5 * eps * gz; pn = pn + 0.5 * eps * gn
+            kin1 = np.zeros((K, P)); np.add.at(kin1.T, sp.owner, 0.5 * (pz * pz).T); kin1 += 0.5 * pn * pn
+            with np.errstate(invalid="ignore"):
+                dH = (lp_q - kin1) - (lp - kin0)
+            acc = np.log(rng.uniform(size=(K, P))) < np.where(np.isfinite(dH), dH, -np.inf)
+            slot_acc = acc[:, sp.owner]
+            sp.z = np.where(slot_acc, zq, sp.z); sp.noise_z = np.where(acc, nq, sp.noise_z)
+            dz = np.where(slot_acc, gz, dz); dn = np.where(acc, gn, dn)
+            lp = np.where(acc, lp_q, lp); lml = np.where(acc, lml_q, lml)
+        lm = lml
+
     if n_hmc > 0:
-        metropolis(n_hmc)                                              # mcmc_parameters!: forecasting.jl:148
+        hmc(n_hmc)                                              # mcmc_parameters!: forecasting.jl:148
 
     def draw_block(Dn):
         th_, nz_ = sp.theta(sp.z, sp.noise_z)
@@ -285,6 +342,6 @@ def _forecast_with_nowcasts(base_model: GPModel, nowcasts: Sequence[TData], fore
     else:
         x = np.empty((h, K * D))
         for i in range(D):                                             # forecasting.jl:63-68
-            metropolis(forecast_n_hmc)
+            hmc(forecast_n_hmc)
             x[:, i::D] = draw_block(1)
     return x, logw

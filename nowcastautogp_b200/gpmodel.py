@@ -117,6 +117,7 @@ def _norm_cdf(x):
 
 def slot_transform(name: str, z: float, config: GPConfig) -> float:
     pr = config.prior
+    z = float(min(max(z, -60.0), 60.0))      # a diverging HMC trajectory must not overflow exp(); it is rejected anyway
     if name == "period":
         return float(np.exp(pr["period"]["mu"] + pr["period"]["sigma"] * z))
     if name == "gamma":
@@ -128,6 +129,25 @@ def slot_transform(name: str, z: float, config: GPConfig) -> float:
     if name == "scale":
         return float(config.cp_scale)
     return float(np.exp(pr["wildcard"]["mu"] + pr["wildcard"]["sigma"] * z))
+
+
+def slot_dtheta_dz(name: str, z: float, theta: float, config: GPConfig) -> float:
+    """d theta / d z of `slot_transform` (chain rule from the device's constrained-space gradient)."""
+    pr = config.prior
+    if name == "period":
+        return pr["period"]["sigma"] * theta
+    if name == "gamma":
+        return pr["gamma"]["sigma"] * theta * (1.0 - 0.5 * theta)
+    if name == "intercept":
+        return 1.0
+    if name == "location":
+        return float(np.exp(-0.5 * z * z) / np.sqrt(2.0 * np.pi))
+    if name == "scale":
+        return 0.0
+    return pr["wildcard"]["sigma"] * theta
+
+
+HMC_DEFAULT = {"n_leapfrog": 10, "eps": 0.02}     # Gen.hmc's L = 10 [R]; step sized for N(0,1)-scaled z
 
 
 @dataclass
@@ -322,6 +342,7 @@ class GPModel:
         174-175`), then rejuvenate with `n_mcmc` structure moves × `n_hmc` parameter steps.
         `n_mcmc` and `n_hmc` are required keywords, as in AutoGP (`test/test_gpconfig.jl:37-43`)."""
         n = len(self.y)
+        self._hmc_config = hmc_config
         self.obs_order = self.rng.permutation(n) if shuffle else np.arange(n)
         for step in schedule:
             step = int(min(step, n))
@@ -374,15 +395,89 @@ class GPModel:
     def _obs_idx(self) -> np.ndarray:
         return np.sort(self.obs_order[:self.n_obs])
 
-    def mcmc_parameters(self, n_hmc: int, step_size: float = 0.15) -> float:
-        """`AutoGP.mcmc_parameters!(model, n_hmc)` (`src/forecasting.jl:148,65`). Round-1 stand-in for
-        HMC: `n_hmc` Gaussian random-walk Metropolis steps on all unconstrained hyperparameters of
-        every particle at once (N(0,1) prior on z [R]); SURVEY §8 f1 replaces it with gradient HMC.
-        Returns the acceptance rate."""
+    def _logpost_grad(self, particles: Sequence[Particle], idx: np.ndarray):
+        """log p(y[idx] | particle) + log N(z; 0, I) and its gradient in unconstrained space, all particles in
+        one `nagp_logml_grad` call. Returns (lp [P], list of dz arrays, dnoise_z [P])."""
+        cfg = self.config
+        t, g, step = self._times(self.ds[idx])
+        ens = pack_particles(particles, cfg)
+        lm, gth, gnz, info = self._engine().logml_grad(ens, t, self.y_transform.apply(self.y[idx]), g=g, step=step)
+        lm, gth, gnz, info = lm[0], gth[0], gnz[0], info[0]
+        lp = np.where(info == 0, lm, -np.inf)
+        dzs, dnz = [], np.zeros(len(particles))
+        for i, p in enumerate(particles):
+            names = kn.theta_slot_names(p.prog)
+            th = ens.theta[ens.theta_off[i]:ens.theta_off[i + 1]]
+            jac = np.array([slot_dtheta_dz(nm, zz, tv, cfg) for nm, zz, tv in zip(names, p.z, th)])
+            dz = np.nan_to_num(gth[ens.theta_off[i]:ens.theta_off[i + 1]], nan=0.0, posinf=0.0, neginf=0.0) * jac - p.z
+            lp[i] += -0.5 * float(p.z @ p.z)
+            if cfg.noise is None:
+                dnz[i] = (gnz[i] if np.isfinite(gnz[i]) else 0.0) * slot_dtheta_dz("noise", p.noise_z, ens.noise[i], cfg) - p.noise_z
+                lp[i] += -0.5 * p.noise_z ** 2
+            dzs.append(np.where(np.isfinite(dz), dz, 0.0))
+        return lp, dzs, np.where(np.isfinite(dnz), dnz, 0.0)
+
+    def mcmc_parameters(self, n_hmc: int, hmc_config: Optional[dict] = None) -> float:
+        """`AutoGP.mcmc_parameters!(model, n_hmc)` (`src/forecasting.jl:148,65`): `n_hmc` Hamiltonian Monte
+        Carlo steps on the unconstrained hyperparameters of every particle (N(0,1) prior on z [R]), all
+        particles advanced together: each leapfrog stage is ONE device call giving every particle's log
+        marginal likelihood and its gradient (`nagp_logml_grad`). Beyond the gradient kernel's size limit the
+        move degrades to random-walk Metropolis on the same target. Returns the acceptance rate."""
+        from .engine import NagpError
+        hc = dict(HMC_DEFAULT, **(hmc_config or getattr(self, "_hmc_config", None) or {}))
+        L, eps = int(hc["n_leapfrog"]), float(hc["eps"])
+        idx = self._obs_idx()
+        P = len(self.particles)
+        if len(idx) == 0 or n_hmc <= 0:
+            return 0.0
+        learn_noise = self.config.noise is None
+        try:
+            lp, dzs, dnz = self._logpost_grad(self.particles, idx)
+        except NagpError as e:
+            if e.code != -4:
+                raise
+            return self._metropolis_parameters(n_hmc)
+        acc = 0
+        for _ in range(n_hmc):
+            cur = [p.copy() for p in self.particles]
+            mom = [self.rng.standard_normal(len(p.z)) for p in cur]
+            mnz = self.rng.standard_normal(P) if learn_noise else np.zeros(P)
+            h0 = -lp + np.array([0.5 * float(m @ m) for m in mom]) + 0.5 * mnz ** 2
+            prop = [p.copy() for p in cur]
+            g_z, g_n, lp_new = dzs, dnz, lp
+            for _l in range(L):
+                for i, q in enumerate(prop):
+                    mom[i] = mom[i] + 0.5 * eps * g_z[i]
+                    q.z = q.z + eps * mom[i]
+                    if learn_noise:
+                        mnz[i] += 0.5 * eps * g_n[i]
+                        q.noise_z = float(q.noise_z + eps * mnz[i])
+                lp_new, g_z, g_n = self._logpost_grad(prop, idx)
+                for i in range(P):
+                    mom[i] = mom[i] + 0.5 * eps * g_z[i]
+                    if learn_noise:
+                        mnz[i] += 0.5 * eps * g_n[i]
+            h1 = -lp_new + np.array([0.5 * float(m @ m) for m in mom]) + 0.5 * mnz ** 2
+            accept = np.log(self.rng.uniform(size=P)) < np.where(np.isfinite(h1), h0 - h1, -np.inf)
+            new_dzs, new_dnz, new_lp = [], dnz.copy(), lp.copy()
+            for i in range(P):
+                if accept[i]:
+                    self.particles[i] = prop[i]
+                    new_dzs.append(g_z[i]); new_dnz[i] = g_n[i]; new_lp[i] = lp_new[i]
+                    prior = -0.5 * float(prop[i].z @ prop[i].z) - (0.5 * prop[i].noise_z ** 2 if learn_noise else 0.0)
+                    self._logml[i] = lp_new[i] - prior
+                    acc += 1
+                else:
+                    new_dzs.append(dzs[i])
+            dzs, dnz, lp = new_dzs, new_dnz, new_lp
+        return acc / max(1, n_hmc * P)
+
+    def _metropolis_parameters(self, n_steps: int, step_size: float = 0.15) -> float:
+        """Gaussian random-walk Metropolis on all unconstrained hyperparameters (same target as the HMC move)."""
         idx = self._obs_idx()
         P = len(self.particles)
         acc = 0
-        for _ in range(n_hmc):
+        for _ in range(n_steps):
             props = []
             for p in self.particles:
                 q = p.copy()
@@ -397,7 +492,7 @@ class GPModel:
                     self.particles[i] = q
                     self._logml[i] = lm_new[i]
                     acc += 1
-        return acc / max(1, n_hmc * P)
+        return acc / max(1, n_steps * P)
 
     def mcmc_structure(self, n_mcmc: int, n_hmc: int) -> float:
         """`AutoGP.mcmc_structure!(model, n_mcmc, n_hmc)` (`src/forecasting.jl:146`): `n_mcmc` rounds of

@@ -107,3 +107,22 @@ def test_grad_vignette_size_is_consistent(engine):
     an = np.array([gth[0, w.ens.theta_off[p]:w.ens.theta_off[p + 1]] @ d[w.ens.theta_off[p]:w.ens.theta_off[p + 1]]
                    for p in range(P)])
     assert np.abs(fd - an).max() < 1e-5 * max(np.abs(an).max(), 1.0)
+
+
+def test_hmc_parameter_move(engine):
+    """mcmc_parameters! as gradient HMC on every particle at once: accepts, stays finite, conserves the
+    Hamiltonian well enough for a healthy acceptance rate, and improves a deliberately poor start."""
+    import nowcastautogp_b200 as ng
+    rng = np.random.default_rng(3)
+    dates = np.arange(np.datetime64("2024-01-01"), np.datetime64("2024-03-01"))
+    vals = 10 + 2 * np.sin(np.arange(len(dates)) / 4.0) + 0.1 * rng.standard_normal(len(dates))
+    m = ng.GPModel(dates, vals, n_particles=6, rng=np.random.default_rng(5), engine=engine)
+    m.n_obs = len(vals)
+    m._logml = m.logml(m.particles, m._obs_idx())
+    before = m._logml.copy()
+    rate = m.mcmc_parameters(10)
+    assert 0.3 < rate <= 1.0
+    after = m.logml(m.particles, m._obs_idx())
+    assert np.isfinite(after).all() and np.allclose(after, m._logml, rtol=1e-9, atol=1e-9)
+    prior = lambda ps: np.array([-0.5 * (p.z @ p.z + p.noise_z ** 2) for p in ps])
+    assert np.median(after) > np.median(before)          # prior draws are far from the posterior mode
