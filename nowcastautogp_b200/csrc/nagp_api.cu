@@ -581,6 +581,23 @@ int32_t nagp_logml_grad(nagp_ctx *ctx, int64_t K, int64_t P, const uint8_t *prog
     a.info = d_info;
     NAGP_TRY(scratch(ctx, (size_t)B * (size_t)(nt * (nt + 1) / 2) * 64, &a.Lkeep));
     NAGP_TRY(scratch(ctx, (size_t)B * nt * 8, &a.zkeep));
+    // tile version of the gradient kernel: needs a strictly increasing lag grid (one point per grid index) or
+    // pairwise times, one lag per thread, and the factor resident in shared memory
+    bool increasing = true;
+    if (g) {
+        std::vector<int32_t> gh((size_t)m);
+        if (on_device(g)) {
+            NAGP_CUDA(ctx, cudaMemcpyAsync(gh.data(), g, m * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            NAGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        } else {
+            std::memcpy(gh.data(), g, m * sizeof(int32_t));
+        }
+        for (int64_t i = 1; i < m; ++i) increasing = increasing && gh[i] > gh[i - 1];
+    }
+    GradTilePlan gpl{};
+    if (increasing && ctx->variant != 1)
+        gpl = plan_grad_tile((int)m, a.G, a.ntab_cap, a.ncp_cap, ctx->smem_optin, ctx->smem_per_sm);
+    if (gpl.ok) NAGP_TRY(scratch(ctx, (size_t)B * nt * 64, &a.Wkeep));
     const int saved_variant = ctx->variant;
     ctx->variant = 2;                                   // the tile kernel is the one that keeps the factor
     const int32_t rc = run_fused(ctx, a, theta_off);
@@ -593,11 +610,25 @@ int32_t nagp_logml_grad(nagp_ctx *ctx, int64_t K, int64_t P, const uint8_t *prog
     ga.L = a.Lkeep; ga.z = a.zkeep; ga.info = d_info;
     NAGP_TRY(stage_out(ctx, grad_theta, (size_t)(K * ntheta), &ga.grad_theta));
     NAGP_TRY(stage_out(ctx, grad_noise, (size_t)B, &ga.grad_noise));
-    bool s_in_smem = true;
-    const size_t smem = grad_smem_bytes((int)m, ctx->smem_optin, &s_in_smem);
-    const int grid = (int)std::min<int64_t>(B, ctx->num_sms);
-    if (!s_in_smem) NAGP_TRY(scratch(ctx, (size_t)grid * m * m, &ga.S));
-    NAGP_CUDA(ctx, launch_grad(ga, grid, smem, ctx->stream));
+    if (gpl.ok) {
+        ga.Winv = a.Wkeep; ga.G = a.G; ga.ntab_cap = a.ntab_cap; ga.ncp_cap = a.ncp_cap;
+        if ((int64_t)ctx->compiled.size() == P) NAGP_TRY(stage_in(ctx, ctx->compiled.data(), ctx->compiled.size(), &ga.compiled));
+        const int grid = grad_tile_grid(gpl, B, ctx->num_sms);
+        if (getenv("NAGP_DEBUG"))
+            fprintf(stderr, "[nagp] grad tile kernel: n=%d G=%d Gd=%d nsec=%d smem=%zu B region=%d scratch/CTA=%d grid=%d\n",
+                    (int)m, a.G, gpl.Gd, gpl.nsec, gpl.smem_bytes, gpl.region_bytes, gpl.scratch_stride, grid);
+        char *scr = nullptr;
+        NAGP_TRY(scratch(ctx, (size_t)grid * gpl.scratch_stride, &scr));
+        unsigned long long *counter = nullptr;
+        NAGP_TRY(scratch(ctx, 1, &counter));
+        NAGP_CUDA(ctx, launch_grad_tile(ga, gpl, scr, counter, grid, ctx->stream));
+    } else {
+        bool s_in_smem = true;
+        const size_t smem = grad_smem_bytes((int)m, ctx->smem_optin, &s_in_smem);
+        const int grid = (int)std::min<int64_t>(B, ctx->num_sms);
+        if (!s_in_smem) NAGP_TRY(scratch(ctx, (size_t)grid * m * m, &ga.S));
+        NAGP_CUDA(ctx, launch_grad(ga, grid, smem, ctx->stream));
+    }
     ctx->launches += 1;
     NAGP_TRY(finish(ctx));
     return on_device(info) ? NAGP_OK : worst_info(info, B);

@@ -339,6 +339,10 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                 sts64(dt + oi1 * 8, d1);
                 sts64(invL_a + oi0 * 8, w0);
                 sts64(invL_a + oi1 * 8, w1);
+                if (a.Wkeep) {
+                    double *wk = a.Wkeep + ((size_t)b * nt + J) * 64;
+                    wk[oi0] = w0; wk[oi1] = w1;
+                }
                 if (bad && lane == 0 && NAGP_EXP == 0) s_info = J * 8 + bad;
                 __syncwarp();
                 DBG_T(J, 2);

@@ -84,7 +84,9 @@ __global__ void __launch_bounds__(kGT, 1) grad_kernel(const GradArgs a, const in
     double *S = s_in_smem ? gsm : a.S + (size_t)blockIdx.x * n * n;
     double *alpha = s_in_smem ? gsm + (size_t)n * n : gsm;      // [Q]
     double *tt = alpha + Q;                                    // [Q]
-    int *gg = reinterpret_cast<int *>(tt + Q);                 // [Q]
+    double *lcol = tt + Q;                                     // [Q] current column of L
+    double *s_part = lcol + Q;                                 // [8][n] partial sums of a row step
+    int *gg = reinterpret_cast<int *>(s_part + 8 * (size_t)n); // [Q]
 
     for (int i = tid; i < Q; i += kGT) {
         tt[i] = i < n ? a.t[i] : 0.0;
@@ -130,11 +132,29 @@ __global__ void __launch_bounds__(kGT, 1) grad_kernel(const GradArgs a, const in
         // ---- 2. S = K^-1 by rows from the bottom ---------------------------------------------------------
         for (int i = n - 1; i >= 0; --i) {
             __syncthreads();
-            const double lii = Lel(i, i);
-            // off-diagonal entries of row i first (they use rows > i only) ...
-            for (int j = i + 1 + tid; j < n; j += kGT) {
-                double acc = 0.0;
-                for (int k = i + 1; k < n; ++k) acc = fma(Lel(k, i), S[(size_t)k * n + j], acc);
+            for (int k = i + tid; k < n; k += kGT) lcol[k] = Lel(k, i);     // column i of L, read once per step
+            __syncthreads();
+            const double lii = lcol[i];
+            // off-diagonal entries of row i first (they use rows > i only): `parts` threads share one j
+            const int nj = n - 1 - i;
+            int parts = 1;
+            while (parts < 8 && nj * parts * 2 <= kGT) parts *= 2;
+            const int jj = tid % (nj > 0 ? nj : 1), part = tid / (nj > 0 ? nj : 1);
+            double acc = 0.0;
+            if (nj > 0 && part < parts) {
+                const int j = i + 1 + jj;
+                for (int k = i + 1 + part; k < n; k += parts) acc = fma(lcol[k], S[(size_t)k * n + j], acc);
+                if (parts > 1) s_part[part * n + jj] = acc;
+            }
+            if (parts > 1) {
+                __syncthreads();
+                if (nj > 0 && part == 0) {
+                    acc = 0.0;
+                    for (int q2 = 0; q2 < parts; ++q2) acc += s_part[q2 * n + jj];
+                }
+            }
+            if (nj > 0 && part == 0) {
+                const int j = i + 1 + jj;
                 const double v = -acc / lii;
                 S[(size_t)i * n + j] = v;
                 S[(size_t)j * n + i] = v;
@@ -142,10 +162,10 @@ __global__ void __launch_bounds__(kGT, 1) grad_kernel(const GradArgs a, const in
             __syncthreads();
             // ... then the diagonal, which needs the column just written
             if (warp == 0) {
-                double acc = 0.0;
-                for (int k = i + 1 + lane; k < n; k += 32) acc = fma(Lel(k, i), S[(size_t)k * n + i], acc);
-                acc = g_warp_sum(acc);
-                if (lane == 0) S[(size_t)i * n + i] = (1.0 / lii - acc) / lii;
+                double acc2 = 0.0;
+                for (int k = i + 1 + lane; k < n; k += 32) acc2 = fma(lcol[k], S[(size_t)k * n + i], acc2);
+                acc2 = g_warp_sum(acc2);
+                if (lane == 0) S[(size_t)i * n + i] = (1.0 / lii - acc2) / lii;
             }
         }
         __syncthreads();
@@ -273,7 +293,7 @@ __global__ void __launch_bounds__(kGT, 1) grad_kernel(const GradArgs a, const in
 size_t grad_smem_bytes(int n, int smem_optin, bool *s_in_smem)
 {
     const int Q = (n + 7) / 8 * 8;
-    const size_t small = (size_t)Q * (8 + 8 + 4) + 64;
+    const size_t small = (size_t)Q * (8 + 8 + 8 + 4) + (size_t)8 * n * 8 + 64;
     const size_t full = (size_t)n * n * 8 + small;
     const size_t limit = (size_t)smem_optin - 8192;     // static shared memory (program, theta) + reservation
     *s_in_smem = full <= limit;

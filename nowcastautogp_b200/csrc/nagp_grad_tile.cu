@@ -1,0 +1,503 @@
+// nagp_grad_tile.cu — gradient of the log marginal likelihood, tile (DMMA) version.
+//
+// What it replaces: AutoGP's HMC on the hyperparameters differentiates the MVN log density of each particle
+// through Gen on the CPU (mcmc_parameters!, /root/reference/src/forecasting.jl:148 and :65; fit_smc!'s n_hmc,
+// /root/reference/src/make_and_fit_model.jl:91). One launch gives d logML / d theta for all B instances.
+//
+//   d logML / d theta_j = sum_{a,b} W_ab dK_ab / d theta_j,   W = 1/2 (alpha alpha^T - K^-1),  alpha = K^-1 y
+//
+// One CTA per instance, two CTAs per SM at the vignette size. The CTA loads the factor L (8x8 tiles, operand
+// layout, kept by the tile kernel together with the inverses of its diagonal tiles and z = L^-1 y) into shared
+// memory and overwrites it IN PLACE with S = K^-1, tile column by tile column from the right:
+//
+//   T_J  = sum_{K>I} S_JK L_KI                (J > I; S symmetric, S_JK = S_KJ^T read transposed when K > J)
+//   S_JI = -T_J L_II^-1
+//   S_II = (L_II^-T - sum_{K>I} S_KI^T L_KI) L_II^-1
+//   alpha_I^T = (z_I^T - sum_{K>I} alpha_K^T L_KI) L_II^-1      (alpha rides along as one more row)
+//
+// Column I of L is dead once column I of S exists, so no second matrix is needed; a transposed copy of the
+// column (operand layout of L_KI^T) is staged per step so every DMMA operand but the mirrored S_JK is one
+// 16-byte LDS. 2 q^3/3 FLOP, all on the FP64 tensor pipe (mma.sync m8n8k4 f64: there is no tcgen05 kind for f64).
+//
+// The tree is then differentiated in reverse mode per matrix entry over the COMPILED program (stationary
+// sub-trees folded into lag tables, ChangePoint sigmoids tabulated per point, as in the Gram pass of the tile
+// kernel). A thread owns one lag d and walks the rows a with b = ginv[g_a - d]: the adjoint that reaches a lag
+// table is summed per (table, lag) in a register — no atomics, fixed order, bit-reproducible — and only
+// afterwards pushed through the stationary sub-tree once per (table, lag): G transcendental evaluations per
+// table instead of n^2/2. Low lags (long diagonals) are split between two threads.
+// Formulas: docs/KERNEL_SPEC.md §3, §8.
+#include <algorithm>
+
+#include "nagp_kernels.cuh"
+#include "nagp_tree.cuh"
+#include "nagp_tile.cuh"
+
+namespace nagp {
+
+namespace {
+
+constexpr int kGW = 8;              // warps per CTA
+constexpr int kGT2 = kGW * 32;
+constexpr int kMaxRows = (29 + kGW - 1) / kGW;
+
+struct RevProgram {
+    int8_t cleft[MAX_PROG];    // compiled program: root index of the left child of a binary node
+    int8_t sleft[MAX_PROG];    // source program: same
+};
+
+// left-child roots of a post-order program (leaf: opcode <= OP_PERIODIC or OP_TABLE)
+__device__ void left_roots(const uint8_t *op, int len, int8_t *left)
+{
+    int8_t stack[MAX_STACK];
+    int sp = 0;
+    for (int i = 0; i < len; ++i) {
+        const int o = op[i];
+        left[i] = -1;
+        if (o <= OP_PERIODIC || o == OP_TABLE) { if (sp < MAX_STACK) stack[sp++] = (int8_t)i; }
+        else if (sp >= 2) { left[i] = stack[sp - 2]; sp -= 2; stack[sp++] = (int8_t)i; }
+    }
+}
+
+// Reverse-mode sweep of ops [i0, i1) for one pair: forward values, then the adjoint `w` of the root pushed to
+// the leaves. Parameter gradients go to gl[theta slot]; the adjoint reaching lag table `id` goes to hacc[id].
+__device__ __forceinline__ void rev_entry(const uint8_t *op, const int16_t *arg, const int8_t *aux, const int8_t *left,
+                                          int i0, int i1, const double *th, double ti, double tj, double delta,
+                                          int lag, int pi, int pj, const double *tab, int G, const double *sig, int Q,
+                                          double w, double *gl, double *hacc)
+{
+    double val[MAX_PROG], adj[MAX_PROG];
+    for (int i = i0; i < i1; ++i) {
+        const int o = op[i];
+        const double *p = th + arg[i];
+        double v;
+        switch (o) {
+        case OP_CONSTANT: v = p[0]; break;
+        case OP_LINEAR: v = fma(p[2], (ti - p[0]) * (tj - p[0]), p[1]); break;
+        case OP_SQEXP: { double r = delta / p[0]; v = p[1] * exp(-0.5 * (r * r)); break; }
+        case OP_GAMMAEXP: { double r = delta / p[0]; v = p[2] * exp(-pow(r, p[1])); break; }
+        case OP_PERIODIC: {
+            double sn = sin(3.14159265358979323846 * (delta / p[1]));
+            v = p[2] * exp(-2.0 * (sn * sn) / (p[0] * p[0]));
+            break;
+        }
+        case OP_TABLE: v = tab[arg[i] * G + lag]; break;
+        case OP_PLUS: v = val[left[i]] + val[i - 1]; break;
+        case OP_TIMES: v = val[left[i]] * val[i - 1]; break;
+        case OP_CHANGEPOINT_TAB: {
+            const double si = sig[aux[i] * Q + pi], sj = sig[aux[i] * Q + pj];
+            v = ((1.0 - si) * (1.0 - sj)) * val[left[i]] + (si * sj) * val[i - 1];
+            break;
+        }
+        default: {   // OP_CHANGEPOINT
+            const double si = 0.5 * (1.0 + tanh((ti - p[0]) / p[1]));
+            const double sj = 0.5 * (1.0 + tanh((tj - p[0]) / p[1]));
+            v = ((1.0 - si) * (1.0 - sj)) * val[left[i]] + (si * sj) * val[i - 1];
+            break;
+        }
+        }
+        val[i] = v;
+        adj[i] = 0.0;
+    }
+    adj[i1 - 1] = w;
+    for (int i = i1 - 1; i >= i0; --i) {
+        const int o = op[i];
+        const double ad = adj[i];
+        const double *p = th + arg[i];
+        double *gp = gl + arg[i];
+        switch (o) {
+        case OP_CONSTANT: gp[0] += ad; break;
+        case OP_LINEAR: {
+            const double u = ti - p[0], v2 = tj - p[0];
+            gp[0] += ad * (-p[2] * (u + v2));
+            gp[1] += ad;
+            gp[2] += ad * (u * v2);
+            break;
+        }
+        case OP_SQEXP: {
+            const double r = delta / p[0];
+            gp[0] += ad * (val[i] * (r * r) / p[0]);
+            gp[1] += ad * (val[i] / p[1]);
+            break;
+        }
+        case OP_GAMMAEXP: {
+            const double r = delta / p[0];
+            const double rg = pow(r, p[1]);
+            gp[0] += ad * (val[i] * p[1] * rg / p[0]);
+            gp[1] += r > 0.0 ? ad * (-val[i] * rg * log(r)) : 0.0;
+            gp[2] += ad * (val[i] / p[2]);
+            break;
+        }
+        case OP_PERIODIC: {
+            const double ang = 3.14159265358979323846 * (delta / p[1]);
+            const double sn = sin(ang), cs = cos(ang);
+            const double l2 = p[0] * p[0];
+            gp[0] += ad * (val[i] * 4.0 * (sn * sn) / (l2 * p[0]));
+            gp[1] += ad * (val[i] * 4.0 * sn * cs * ang / (l2 * p[1]));
+            gp[2] += ad * (val[i] / p[2]);
+            break;
+        }
+        case OP_TABLE: hacc[arg[i]] += ad; break;
+        case OP_PLUS: adj[left[i]] += ad; adj[i - 1] += ad; break;
+        case OP_TIMES: adj[left[i]] += ad * val[i - 1]; adj[i - 1] += ad * val[left[i]]; break;
+        default: {   // ChangePoint (direct or tabulated): (1-si)(1-sj) kL + si sj kR, si = sigma((ti - loc) / scale)
+            const double xi = (ti - p[0]) / p[1], xj = (tj - p[0]) / p[1];
+            double si, sj;
+            if (o == OP_CHANGEPOINT_TAB) { si = sig[aux[i] * Q + pi]; sj = sig[aux[i] * Q + pj]; }
+            else { si = 0.5 * (1.0 + tanh(xi)); sj = 0.5 * (1.0 + tanh(xj)); }
+            const double kl = val[left[i]], kr = val[i - 1];
+            adj[left[i]] += ad * ((1.0 - si) * (1.0 - sj));
+            adj[i - 1] += ad * (si * sj);
+            // d sigma / d x = 2 sigma (1 - sigma); dx / d loc = -1 / scale; dx / d scale = -x / scale
+            const double dsi = 2.0 * si * (1.0 - si), dsj = 2.0 * sj * (1.0 - sj);
+            const double dk_dsi = -(1.0 - sj) * kl + sj * kr;
+            const double dk_dsj = -(1.0 - si) * kl + si * kr;
+            gp[0] += ad * (dk_dsi * dsi + dk_dsj * dsj) * (-1.0 / p[1]);
+            gp[1] += ad * (dk_dsi * dsi * (-xi / p[1]) + dk_dsj * dsj * (-xj / p[1]));
+            break;
+        }
+        }
+    }
+}
+
+struct GradTileLayout {
+    int nt;
+    int region_bytes;         // union region: {lcolT, part} during the sweep, {tt, theta, hx, gg, ginv} afterwards
+    int nsec;                 // threads that take the second half of a low lag (0 .. kGT2 - Gd)
+    int Gd;                   // lags handled (lag-grid extent, or n when times are pairwise)
+    int scratch_stride;       // bytes of global scratch per CTA (lag tables + sigma tables)
+    char *scratch;
+    unsigned long long *work_counter;
+};
+
+__global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, const GradTileLayout lay)
+{
+    extern __shared__ __align__(16) double smem[];
+    __shared__ TreeProgram tp;
+    __shared__ RevProgram rp;
+    __shared__ long long s_next;
+    __shared__ double s_red[kGW];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = a.n, nt = lay.nt, Q = nt * 8, ntiles = tri(nt);
+    const int G = a.G, Gd = lay.Gd, nsec = lay.nsec;
+
+    double *tiles = smem;
+    double *alpha = tiles + ntiles * 64;        // [Q]
+    double *invs = alpha + Q;                   // [64] inverse of the current diagonal tile of L
+    double *region = invs + 64;
+    // sweep view of the region
+    double *lcolT = region;                     // [nt][64] operand layout of L_KI^T
+    double *part = lcolT + nt * 64;             // [kGW][64] partial sums of the diagonal tile, accumulator layout
+    // differentiation view of the region
+    double *tt = region;                        // [Q]
+    double *th = tt + Q;                        // [MAX_THETA]
+    double *hx = th + MAX_THETA;                // [ntab_cap][nsec]
+    int *gg = reinterpret_cast<int *>(hx + a.ntab_cap * nsec);   // [Q]
+    short *ginv = reinterpret_cast<short *>(gg + Q);             // [Gd]
+    double *tab = reinterpret_cast<double *>(lay.scratch + (size_t)blockIdx.x * lay.scratch_stride);   // [ntab_cap][G]
+    double *sig = tab + a.ntab_cap * (G > 0 ? G : 0);                                                    // [ncp_cap][Q]
+
+    const int lr = lane >> 2, lj = lane & 3;
+    const int oi0 = op_idx(lr, 2 * lj), oi1 = op_idx(lr, 2 * lj + 1);
+    const int tr0 = op_idx(lj, lr);                       // transposed fragment: element (lj, lr); chunk 1 is +32
+    const int cv0 = (lane & ~3) + (lj >> 1), cv1 = cv0 + 2;
+    const bool odd = lane & 1;
+    const uint32_t tiles_a = smem_addr(tiles), lcol_a = smem_addr(lcolT), invs_a = smem_addr(invs);
+    const int nreg = warp < nt ? (nt - 1 - warp) / kGW + 1 : 0;
+    const int Ilast = warp + (nreg - 1) * kGW;
+    const bool has_alpha = (warp == nt % kGW);
+
+    // C (accumulator layout) times invL, result in accumulator layout: X * invL = X * (invL^T)^T
+    auto times_inv = [&](double c0, double c1, double &x0, double &x1) {
+        const double ibx = lds64(invs_a + tr0 * 8), iby = lds64(invs_a + tr0 * 8 + 256);
+        const double v00 = shfl(c0, cv0), v01 = shfl(c1, cv0);
+        const double v10 = shfl(c0, cv1), v11 = shfl(c1, cv1);
+        x0 = 0.0; x1 = 0.0;
+        dmma(x0, x1, odd ? v01 : v00, ibx);
+        dmma(x0, x1, odd ? v11 : v10, iby);
+    };
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_next = (long long)atomicAdd(lay.work_counter, 1ull);
+        __syncthreads();
+        const int64_t b = s_next;
+        if (b >= a.B) break;
+        const int64_t s = b / a.P;
+        const int p = (int)(b % a.P);
+        const int64_t po = a.prog_off[p], plen = a.prog_off[p + 1] - po;
+        const int64_t to = a.theta_off[p], ntheta = a.theta_off[p + 1] - to;
+        const int64_t ntot = a.theta_off[a.P];
+        double *gout = a.grad_theta + s * ntot + to;
+        const double *theta_g = a.theta + s * a.theta_stride_k + to;
+        if (a.info[b] != 0) {
+            for (int j = tid; j < ntheta; j += kGT2) gout[j] = nan("");
+            if (tid == 0) a.grad_noise[b] = nan("");
+            continue;
+        }
+        // ---- 0. program, factor -----------------------------------------------------------------------------
+        if (a.compiled) {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(a.compiled + p);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(&tp);
+            for (int i = tid; i < (int)(sizeof(TreeProgram) / 4); i += kGT2) dst[i] = src[i];
+        } else if (tid == 0) {
+            if (ntheta > MAX_THETA) tp.error = -3;
+            else tree_compile(tp, a.prog + po, (int)plen, (int)ntheta, G > 0 ? a.ntab_cap : 0, a.ncp_cap);
+        }
+        {
+            const double2 *Lg = reinterpret_cast<const double2 *>(a.L + (size_t)b * ((size_t)ntiles * 64));
+            double2 *Ls = reinterpret_cast<double2 *>(tiles);
+            for (int i = tid; i < ntiles * 32; i += kGT2) Ls[i] = Lg[i];
+        }
+        __syncthreads();
+        if (tp.error) {
+            for (int j = tid; j < ntheta; j += kGT2) gout[j] = nan("");
+            if (tid == 0) a.grad_noise[b] = nan("");
+            continue;
+        }
+        if (tid == 0) left_roots(tp.cop, tp.clen, rp.cleft);
+        if (tid == 32) left_roots(tp.sop, tp.slen, rp.sleft);
+        const double *zb = a.z + (size_t)b * Q;
+        const double *Wb = a.Winv + (size_t)b * ((size_t)nt * 64);
+
+        // ---- 1. S = K^-1 in place, alpha = K^-1 y ------------------------------------------------------------
+        for (int I = nt - 1; I >= 0; --I) {
+            __syncthreads();                                   // column I+1 of S complete (incl. its diagonal tile)
+            for (int e = tid; e < (nt - 1 - I) * 64; e += kGT2) {
+                const int K = I + 1 + (e >> 6), el = e & 63, r = el >> 3, c = el & 7;
+                lcolT[K * 64 + op_idx(c, r)] = tiles[(tri(K) + I) * 64 + op_idx(r, c)];
+            }
+            if (tid < 64) invs[tid] = Wb[I * 64 + tid];
+            __syncthreads();
+            const int NA = Ilast > I ? (Ilast - I - 1) / kGW + 1 : 0;      // owned rows J > I (slots from the bottom)
+            double pd[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+            for (int u = 0; u < kMaxRows; ++u) {
+                if (u < NA) {
+                    const int J = Ilast - u * kGW;
+                    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+                    const uint32_t rowa = tiles_a + (uint32_t)(tri(J) * 512 + lane * 16);
+                    for (int K = I + 1; K <= J; ++K) {
+                        const double2 af = lds128(rowa + (uint32_t)K * 512u);
+                        const double2 bf = lds128(lcol_a + (uint32_t)(K * 512 + lane * 16));
+                        dmma(acc[0][0], acc[0][1], af.x, bf.x);
+                        dmma(acc[1][0], acc[1][1], af.y, bf.y);
+                    }
+                    for (int K = J + 1; K < nt; ++K) {
+                        const uint32_t ta = tiles_a + (uint32_t)((tri(K) + J) * 512 + tr0 * 8);
+                        const double ax = lds64(ta), ay = lds64(ta + 256);
+                        const double2 bf = lds128(lcol_a + (uint32_t)(K * 512 + lane * 16));
+                        dmma(acc[0][0], acc[0][1], ax, bf.x);
+                        dmma(acc[1][0], acc[1][1], ay, bf.y);
+                    }
+                    double x0, x1;
+                    times_inv(-(acc[0][0] + acc[1][0]), -(acc[0][1] + acc[1][1]), x0, x1);
+                    const uint32_t dt = tiles_a + (uint32_t)((tri(J) + I) * 512);
+                    sts64(dt + oi0 * 8, x0);
+                    sts64(dt + oi1 * 8, x1);
+                }
+            }
+            if (has_alpha) {
+                double ya[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+                for (int K = I + 1; K < nt; ++K) {
+                    const double2 bf = lds128(lcol_a + (uint32_t)(K * 512 + lane * 16));
+                    const double a0 = lr == 0 ? alpha[K * 8 + lj] : 0.0;
+                    const double a1 = lr == 0 ? alpha[K * 8 + 4 + lj] : 0.0;
+                    dmma(ya[0][0], ya[0][1], a0, bf.x);
+                    dmma(ya[1][0], ya[1][1], a1, bf.y);
+                }
+                const double z0 = lr == 0 ? zb[I * 8 + 2 * lj] : 0.0;
+                const double z1 = lr == 0 ? zb[I * 8 + 2 * lj + 1] : 0.0;
+                double x0, x1;
+                times_inv(z0 - (ya[0][0] + ya[1][0]), z1 - (ya[0][1] + ya[1][1]), x0, x1);
+                if (lr == 0) { alpha[I * 8 + 2 * lj] = x0; alpha[I * 8 + 2 * lj + 1] = x1; }
+            }
+            __syncwarp();
+            // partial sum of the diagonal tile over the owned rows: sum_J S_JI^T L_JI (new S_JI, staged L_JI)
+#pragma unroll
+            for (int u = 0; u < kMaxRows; ++u) {
+                if (u < NA) {
+                    const int J = Ilast - u * kGW;
+                    const uint32_t ta = tiles_a + (uint32_t)((tri(J) + I) * 512 + tr0 * 8);
+                    const double ax = lds64(ta), ay = lds64(ta + 256);
+                    const double2 bf = lds128(lcol_a + (uint32_t)(J * 512 + lane * 16));
+                    dmma(pd[0][0], pd[0][1], ax, bf.x);
+                    dmma(pd[1][0], pd[1][1], ay, bf.y);
+                }
+            }
+            *reinterpret_cast<double2 *>(part + warp * 64 + lane * 2) = make_double2(pd[0][0] + pd[1][0], pd[0][1] + pd[1][1]);
+            __syncthreads();
+            if (warp == I % kGW) {
+                double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+                for (int w = 0; w < kGW; ++w) {
+                    const double2 v = *reinterpret_cast<const double2 *>(part + w * 64 + lane * 2);
+                    t0 += v.x; t1 += v.y;
+                }
+                // invL^T in accumulator layout: element (lr, c) = invL[c][lr]
+                const double r0 = invs[op_idx(2 * lj, lr)] - t0, r1 = invs[op_idx(2 * lj + 1, lr)] - t1;
+                double x0, x1;
+                times_inv(r0, r1, x0, x1);
+                const uint32_t dt = tiles_a + (uint32_t)((tri(I) + I) * 512);
+                sts64(dt + oi0 * 8, x0);
+                sts64(dt + oi1 * 8, x1);
+            }
+        }
+        __syncthreads();
+
+        // ---- 2. tables for the forward values of the compiled program ------------------------------------------
+        for (int i = tid; i < Q; i += kGT2) {
+            tt[i] = i < n ? a.t[i] : 0.0;
+            gg[i] = (a.g && i < n) ? a.g[i] : i;
+        }
+        for (int i = tid; i < Gd; i += kGT2) ginv[i] = -1;
+        for (int i = tid; i < ntheta && i < MAX_THETA; i += kGT2) th[i] = theta_g[i];
+        __syncthreads();
+        const int g0 = gg[0];
+        for (int i = tid; i < n; i += kGT2) ginv[gg[i] - g0] = (short)i;
+        const int ntab = tp.ntab, ncp = tp.ncp;
+        for (int e = tid; e < ntab * G; e += kGT2) {
+            const int id = e / G, lg = e - id * G;
+            const int s0 = tp.tab_src0[id], s1 = tp.tab_src1[id];
+            tab[e] = tree_eval(tp.sop + s0, tp.sarg + s0, nullptr, s1 - s0, th, 0.0, 0.0, (double)lg * a.step, 0,
+                               nullptr, 0, nullptr, 0, 0, 0);
+        }
+        for (int e = tid; e < ncp * Q; e += kGT2) {
+            const int id = e / Q, i = e - id * Q;
+            const double *cp = th + tp.cp_theta[id];
+            sig[e] = 0.5 * (1.0 + tanh((tt[i] - cp[0]) / cp[1]));
+        }
+        __syncthreads();
+
+        // ---- 3. reverse mode per entry: thread <-> lag ---------------------------------------------------------
+        double gl[MAX_THETA];
+        for (int j = 0; j < (int)ntheta; ++j) gl[j] = 0.0;
+        double hacc[MAX_TABLES];
+#pragma unroll
+        for (int j = 0; j < MAX_TABLES; ++j) hacc[j] = 0.0;
+        double gnoise = 0.0;
+        const bool grid = a.g != nullptr;
+        for (int item = tid; item < Gd + nsec; item += kGT2) {
+            const bool second = item >= Gd;
+            const int d = second ? item - Gd : item;
+            const int mid = (min(d, n) + n) >> 1;
+            const int a_lo = second ? mid : 0;
+            const int a_hi = (second || d >= nsec) ? n : mid;
+            for (int ia = a_lo; ia < a_hi; ++ia) {
+                const int gb = gg[ia] - g0 - d;
+                if (gb < 0) continue;
+                const int ib = ginv[gb];
+                if (ib < 0) continue;
+                const double Sab = tiles[(tri(ia >> 3) + (ib >> 3)) * 64 + op_idx(ia & 7, ib & 7)];
+                const double Wab = 0.5 * (alpha[ia] * alpha[ib] - Sab);
+                const double w = d == 0 ? Wab : 2.0 * Wab;
+                if (d == 0) gnoise += Wab;
+                const double ti = tt[ia], tj = tt[ib];
+                const double delta = grid ? (double)d * a.step : fabs(ti - tj);
+                rev_entry(tp.cop, tp.carg, tp.caux, rp.cleft, 0, tp.clen, th, ti, tj, delta, d, ia, ib, tab, G, sig, Q,
+                          w, gl, hacc);
+            }
+        }
+        // second halves hand their table adjoints to the lag's first thread (fixed order: reproducible)
+        if (tid >= Gd && tid < Gd + nsec) {
+#pragma unroll
+            for (int j = 0; j < MAX_TABLES; ++j)
+                if (j < ntab) hx[j * nsec + (tid - Gd)] = hacc[j];
+        }
+        __syncthreads();
+        // ---- 4. table adjoints through the stationary sub-trees, once per (table, lag) -------------------------
+        for (int d = tid; d < G; d += kGT2) {
+            // with Gd > kGT2 a thread owns several lags and hacc mixes them: only reached when Gd <= kGT2 (plan)
+#pragma unroll
+            for (int j = 0; j < MAX_TABLES; ++j) {
+                if (j < ntab) {
+                    double A = hacc[j];
+                    if (d < nsec) A += hx[j * nsec + d];
+                    if (A != 0.0) {
+                        double dummy[1];
+                        rev_entry(tp.sop, tp.sarg, nullptr, rp.sleft, tp.tab_src0[j], tp.tab_src1[j], th, 0.0, 0.0,
+                                  (double)d * a.step, 0, 0, 0, nullptr, 0, nullptr, 0, A, gl, dummy);
+                    }
+                }
+            }
+        }
+        // ---- 5. block reduction --------------------------------------------------------------------------------
+        for (int j = 0; j <= (int)ntheta; ++j) {
+            const double v = warp_sum(j < (int)ntheta ? gl[j] : gnoise);
+            __syncthreads();
+            if (lane == 0) s_red[warp] = v;
+            __syncthreads();
+            if (tid == 0) {
+                double r = 0.0;
+                for (int w = 0; w < kGW; ++w) r += s_red[w];
+                if (j < (int)ntheta) gout[j] = r; else a.grad_noise[b] = r;
+            }
+        }
+    }
+}
+
+size_t region_bytes_for(int nt, int Gd, int ntab_cap, int nsec)
+{
+    const int Q = nt * 8;
+    const size_t sweep = ((size_t)nt * 64 + (size_t)kGW * 64) * 8;
+    size_t diff = ((size_t)Q + MAX_THETA + (size_t)ntab_cap * nsec) * 8 + (size_t)Q * 4 + (size_t)Gd * 2;
+    diff = (diff + 15) & ~size_t(15);
+    return std::max(sweep, diff);
+}
+
+}  // namespace
+
+GradTilePlan plan_grad_tile(int n, int G, int ntab_cap, int ncp_cap, int smem_optin, int smem_per_sm)
+{
+    GradTilePlan pl{};
+    const int nt = (n + 7) / 8, Q = nt * 8;
+    pl.nt = nt;
+    pl.Gd = G > 0 ? G : n;
+    if (pl.Gd > kGT2) { pl.ok = 0; return pl; }                 // one lag per thread (register accumulators)
+    cudaFuncAttributes fa{};
+    size_t static_smem = 4096;
+    if (cudaFuncGetAttributes(&fa, grad_tile_kernel) == cudaSuccess) static_smem = fa.sharedSizeBytes + 1024;
+    else cudaGetLastError();
+    const size_t base = ((size_t)(nt * (nt + 1) / 2) * 64 + Q + 64) * 8;
+    // second-half threads: as many as there are idle threads, fewer if that is what keeps two CTAs per SM
+    int nsec = std::min(kGT2 - pl.Gd, pl.Gd);
+    const size_t two = (size_t)smem_per_sm / 2;
+    while (nsec > 0 && base + region_bytes_for(nt, pl.Gd, ntab_cap, nsec) + static_smem > two &&
+           base + region_bytes_for(nt, pl.Gd, ntab_cap, 0) + static_smem <= two)
+        nsec -= std::min(nsec, 8);
+    pl.nsec = nsec;
+    pl.region_bytes = (int)region_bytes_for(nt, pl.Gd, ntab_cap, nsec);
+    pl.smem_bytes = base + pl.region_bytes;
+    pl.scratch_stride = (int)((((size_t)ntab_cap * (G > 0 ? G : 0) + (size_t)ncp_cap * Q) * 8 + 255) & ~size_t(255));
+    if (pl.scratch_stride == 0) pl.scratch_stride = 256;
+    pl.ok = pl.smem_bytes + static_smem - 1024 <= (size_t)smem_optin;
+    return pl;
+}
+
+int grad_tile_grid(const GradTilePlan &pl, int64_t B, int num_sms)
+{
+    int per_sm = 0;
+    cudaFuncSetAttribute(grad_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grad_tile_kernel, kGT2, pl.smem_bytes) != cudaSuccess ||
+        per_sm < 1) {
+        cudaGetLastError();
+        per_sm = 1;
+    }
+    return (int)std::min<int64_t>((int64_t)per_sm * num_sms, B);
+}
+
+cudaError_t launch_grad_tile(const GradArgs &a, const GradTilePlan &pl, char *scratch, unsigned long long *work_counter,
+                             int grid, cudaStream_t stream)
+{
+    GradTileLayout lay{};
+    lay.nt = pl.nt; lay.region_bytes = pl.region_bytes; lay.nsec = pl.nsec; lay.Gd = pl.Gd;
+    lay.scratch_stride = pl.scratch_stride; lay.scratch = scratch; lay.work_counter = work_counter;
+    cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(grad_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
+    if (e != cudaSuccess) return e;
+    grad_tile_kernel<<<grid, kGT2, pl.smem_bytes, stream>>>(a, lay);
+    return cudaGetLastError();
+}
+
+}  // namespace nagp

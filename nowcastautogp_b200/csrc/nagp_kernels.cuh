@@ -44,6 +44,7 @@ struct FusedArgs {
     const TreeProgram *compiled; // [P] programs compiled on the host with these capacities (nullable: compile on device)
     double *Lkeep;               // nullable: the factor of every instance, tile-packed operand layout [B, tri(nt)*64]
     double *zkeep;               // nullable (with Lkeep): z = L^-1 y per instance [B, 8*nt]
+    double *Wkeep;               // nullable (with Lkeep): inverses of the diagonal tiles, operand layout [B, nt*64]
 };
 
 size_t fused_smem_bytes_v1(int q, int G, int ntab_cap, int ncp_cap);
@@ -100,9 +101,26 @@ struct GradArgs {
     double *grad_noise;          // [B]
     double *S;                   // nullable global scratch [grid][n*n] when n*n doubles do not fit shared memory
     const int32_t *info;         // [B] from the factorisation: instances with info != 0 get NaN gradients
+    // tile version only
+    const double *Winv;          // [B, nt*64] inverses of the diagonal tiles of L (FusedArgs::Wkeep)
+    int G;                       // lag-grid extent (0: pairwise times)
+    int ntab_cap, ncp_cap;       // table capacities the programs were compiled with
+    const TreeProgram *compiled; // [P] nullable
 };
 size_t grad_smem_bytes(int n, int smem_optin, bool *s_in_smem);
 cudaError_t launch_grad(const GradArgs &a, int grid, size_t smem_bytes, cudaStream_t stream);
+
+// Tile (DMMA) version: K^-1 in place over the factor in shared memory, lag-binned reverse mode.
+struct GradTilePlan {
+    int ok;
+    int nt, Gd, nsec;
+    int region_bytes, scratch_stride;
+    size_t smem_bytes;
+};
+GradTilePlan plan_grad_tile(int n, int G, int ntab_cap, int ncp_cap, int smem_optin, int smem_per_sm);
+int grad_tile_grid(const GradTilePlan &pl, int64_t B, int num_sms);
+cudaError_t launch_grad_tile(const GradArgs &a, const GradTilePlan &pl, char *scratch, unsigned long long *work_counter,
+                             int grid, cudaStream_t stream);
 
 // Scenario-shared fast path: per (scenario, particle) O(k^2 + hk) tail of the forward solve.
 struct AppendArgs {

@@ -10,6 +10,15 @@ from nowcastautogp_b200 import synthetic as syn
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=[0, 1], ids=["tile", "column"], autouse=True)
+def grad_variant(engine, request):
+    """0: tile kernel (in-place K^-1 on the tensor pipe, lag-binned reverse mode); 1: the first column kernel,
+    kept as the fallback for unsorted grids and n beyond the shared-memory-resident size."""
+    engine.set_variant(request.param)
+    yield request.param
+    engine.set_variant(0)
+
+
 def fd_grad(oracle_q, prog, theta, noise, t, y, g, step):
     """4th-order central differences in every theta slot and the noise (steps exactly representable)."""
     theta = np.asarray(theta, float)
