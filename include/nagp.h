@@ -193,6 +193,20 @@ int32_t nagp_forecast_with_nowcasts(nagp_ctx *ctx, int64_t K, int64_t P, int64_t
                                     double ess_thr, const double *zeta,
                                     double *x, double *logw_out, double *ess_out, int32_t *info);
 
+/* ---- (f4) inverse transformation + per-date quantiles of a forecast matrix --------------------------------
+ * /root/reference/src/forecasting.jl:50,73,166 apply `inv_transformation.(x)` to the (h, K*D) draws on the host,
+ * and every vignette then takes row quantiles (/root/reference/docs/vignettes/getting-started.jl:432-435).
+ * For the three built-in transformations of get_transformations (/root/reference/src/transformations.jl:134-170)
+ * both happen here on the device. kind: 0 identity, 1 "positive" max(exp(y) - offset, 0), 2 "percentage"
+ * max(logistic(y) * 100 - offset, 0), 3 "boxcox" (the inverse with the clamping rules of
+ * /root/reference/src/transformations.jl:6-44; lambda, offset, max_value = maximum of the fitted values).
+ * x[h, N] column-major (the layout nagp_draw / nagp_forecast_with_nowcasts write; host or device);
+ * x_out (nullable; may alias x) receives the transformed matrix; q[h, nq] row-major (nullable iff nq == 0)
+ * receives, per forecast date, Julia's default `quantile` (type 7) of the TRANSFORMED draws at probs[nq]. */
+int32_t nagp_forecast_summary(nagp_ctx *ctx, int32_t kind, double lambda, double offset, double max_value,
+                              int64_t h, int64_t N, const double *x, double *x_out,
+                              int64_t nq, const double *probs, double *q);
+
 #ifdef __cplusplus
 }
 #endif

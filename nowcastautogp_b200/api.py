@@ -67,9 +67,13 @@ def make_and_fit_model(data: TData, *, n_particles: int = 1, smc_data_proportion
     return model
 
 
-def _apply(inv_transformation: Callable, x: np.ndarray) -> np.ndarray:
+def _apply(inv_transformation: Callable, x: np.ndarray, engine=None) -> np.ndarray:
     if inv_transformation is _identity:
         return x
+    spec = getattr(inv_transformation, "spec", None)
+    if spec is not None and engine is not None and x.ndim == 2 and x.size:
+        # built-in inverse of get_transformations: one device pass over the whole draw matrix
+        return engine.forecast_summary(x, spec)[0]
     try:
         out = inv_transformation(x)                 # vectorised closures (np.exp, scaled logistic …)
         if isinstance(out, np.ndarray) and out.shape == x.shape:
@@ -90,7 +94,7 @@ def forecast(model: GPModel, forecast_dates, forecast_draws: int, *, inv_transfo
         for i in range(forecast_draws):
             model.mcmc_parameters(forecast_n_hmc)
             x[:, i] = model.predict_mvn(dates).rand(rng=model.rng)
-    return _apply(inv_transformation, np.ascontiguousarray(x))
+    return _apply(inv_transformation, np.ascontiguousarray(x), model._engine())
 
 
 class _ScenarioParams:
@@ -146,7 +150,7 @@ def forecast_with_nowcasts(base_model: GPModel, nowcasts: Sequence[TData], forec
     x, _ = _forecast_with_nowcasts(base_model, nowcasts, forecast_dates, forecast_draws_per_nowcast,
                                    n_mcmc=n_mcmc, n_hmc=n_hmc, ess_threshold=ess_threshold,
                                    forecast_n_hmc=forecast_n_hmc, rng=rng)
-    return _apply(inv_transformation, x)
+    return _apply(inv_transformation, x, base_model._engine())
 
 
 def forecast_with_nowcasts_sharded(base_models: Sequence[GPModel], nowcasts: Sequence[Sequence[TData]],
@@ -172,7 +176,8 @@ def forecast_with_nowcasts_sharded(base_models: Sequence[GPModel], nowcasts: Seq
 
     draws, logw = sharded_forecast(compute, len(base_models), [len(nc) for nc in nowcasts], h, D, P,
                                    group=group, device=device)
-    return {s: _apply(inv_transformation, np.ascontiguousarray(x)) for s, x in draws.items()}, logw
+    return {s: _apply(inv_transformation, np.ascontiguousarray(x), base_models[s]._engine())
+            for s, x in draws.items()}, logw
 
 
 def _forecast_with_nowcasts(base_model: GPModel, nowcasts: Sequence[TData], forecast_dates,

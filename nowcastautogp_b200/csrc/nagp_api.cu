@@ -634,6 +634,41 @@ int32_t nagp_logml_grad(nagp_ctx *ctx, int64_t K, int64_t P, const uint8_t *prog
     return on_device(info) ? NAGP_OK : worst_info(info, B);
 }
 
+// ---- (f4) inverse transformation + row quantiles of the forecast matrix -------------------------------------
+int32_t nagp_forecast_summary(nagp_ctx *ctx, int32_t kind, double lambda, double offset, double max_value,
+                              int64_t h, int64_t N, const double *x, double *x_out,
+                              int64_t nq, const double *probs, double *q)
+{
+    if (!ctx) return NAGP_E_ARG;
+    if (kind < 0 || kind > 3 || h <= 0 || N <= 0 || !x || nq < 0 || (nq > 0 && (!probs || !q)) || (!x_out && nq == 0))
+        return fail(ctx, NAGP_E_ARG, "nagp_forecast_summary: bad argument");
+    if (nq > 0 && !on_device(probs))
+        for (int64_t j = 0; j < nq; ++j)
+            if (!(probs[j] >= 0.0 && probs[j] <= 1.0)) return fail(ctx, NAGP_E_ARG, "nagp_forecast_summary: probability outside [0, 1]");
+    NAGP_CUDA(ctx, cudaSetDevice(ctx->device));
+    NAGP_TRY(arena_reset(ctx));
+    const double *d_x = nullptr, *d_probs = nullptr;
+    double *d_out = nullptr, *d_rows = nullptr, *d_q = nullptr;
+    NAGP_TRY(stage_in(ctx, x, (size_t)(h * N), &d_x));
+    if (x_out) {
+        if (x_out == x && on_device(x)) d_out = const_cast<double *>(d_x);       // in place on the device
+        else NAGP_TRY(stage_out(ctx, x_out, (size_t)(h * N), &d_out));
+    }
+    if (nq > 0) {
+        NAGP_TRY(scratch(ctx, (size_t)(h * N), &d_rows));
+        NAGP_TRY(stage_in(ctx, probs, (size_t)nq, &d_probs));
+        NAGP_TRY(stage_out(ctx, q, (size_t)(h * nq), &d_q));
+    }
+    NAGP_CUDA(ctx, launch_inverse_transform(kind, lambda, offset, max_value, h, N, d_x, d_out, d_rows, ctx->num_sms,
+                                            ctx->stream));
+    ctx->launches += 1;
+    if (nq > 0) {
+        NAGP_CUDA(ctx, launch_row_quantiles(h, N, d_rows, nq, d_probs, d_q, ctx->stream));
+        ctx->launches += 1;
+    }
+    return finish(ctx);
+}
+
 // ---- appendable factor store for long series (SMC data annealing, BASELINE config 5) -----------------
 int32_t nagp_factor_store_large(nagp_ctx *ctx, int64_t P, const uint8_t *prog, const int64_t *prog_off,
                                 const double *theta, const int64_t *theta_off, const double *noise,

@@ -156,4 +156,11 @@ struct DrawArgs {
 };
 cudaError_t launch_draw(const DrawArgs &a, cudaStream_t stream);
 
+// Forecast summary: elementwise inverse transformation (x [h,N] column-major -> out same layout and/or
+// rows [h][N]) and per-row type-7 quantiles by radix select.
+cudaError_t launch_inverse_transform(int kind, double lam, double offset, double max_value, int64_t h, int64_t N,
+                                     const double *x, double *out, double *rows, int num_sms, cudaStream_t stream);
+cudaError_t launch_row_quantiles(int64_t h, int64_t N, const double *rows, int64_t nq, const double *probs, double *q,
+                                 cudaStream_t stream);
+
 }  // namespace nagp

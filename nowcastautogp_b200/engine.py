@@ -280,6 +280,25 @@ class Engine:
         return xbuf.T if x is None else xbuf
 
 
+    # ---- (f4) inverse transformation + per-date quantiles ---------------------------------------------
+    def forecast_summary(self, x, spec=(0, 0.0, 0.0, 0.0), probs=None, want_x: bool = True):
+        """x [h, N] transformed-space draws (numpy) → (inverse-transformed x [h, N] or None, quantiles [h, nq] or
+        None). `spec = (kind, lambda, offset, max_value)` as carried by `transformations.InverseTransform`."""
+        x = np.asarray(x, np.float64)
+        h, N = x.shape
+        xin = np.ascontiguousarray(x.T)                       # (N, h) C-order = column-major (h, N)
+        xout = np.empty_like(xin) if want_x else None
+        nq = 0 if probs is None else len(probs)
+        pr = None if probs is None else np.ascontiguousarray(probs, np.float64)
+        q = np.empty((h, nq)) if nq else None
+        kind, lam, offset, max_value = spec
+        self._check(self._lib.nagp_forecast_summary(
+            self._ctx, int(kind), float(lam), float(offset), float(max_value), h, N, xin.ctypes.data,
+            None if xout is None else xout.ctypes.data, nq, None if pr is None else pr.ctypes.data,
+            None if q is None else q.ctypes.data))
+        return (None if xout is None else xout.T), q
+
+
 class Factor:
     """Device-resident factors of one base model (nagp_factor handle)."""
 
