@@ -355,7 +355,42 @@ def main():
                 "append_roofline": {"bound": "hbm", "achieved": bytes_ / (ms_app * 1e-3) / 1e9, "unit": "GB/s",
                                     "bytes_per_launch": bytes_}}
 
-    micro = None if args.no_micro else {"logml": micro_logml(), "append": micro_append()}
+    # ---- the HMC primitive — logML + gradient for every (scenario, particle) chain of the workload ----
+    def micro_grad():
+        m = n + k
+        total = int(w.ens.theta_off[-1])
+        outs = (torch.empty((K, P), dtype=torch.float64, device=dev), torch.empty((K, total), dtype=torch.float64, device=dev),
+                torch.empty((K, P), dtype=torch.float64, device=dev), torch.zeros((K, P), dtype=torch.int32, device=dev))
+
+        def run():
+            eng.logml_grad(ens_dev, w.t[:m], d_y1, y2=d_y2, g=w.g[:m], step=w.step, theta=d_theta, noise=d_noise, out=outs)
+        ms = timed(run, max(3, args.steps // 2), 3)
+        ok_ = int(outs[3].abs().max().item()) == 0 and bool(torch.isfinite(outs[1]).all().item())
+        fl_ = K * P * (m ** 3 / 3.0 + 2.0 * m ** 3 / 3.0)          # factorisation + inverse from the factor
+        return {"what": "logML + d logML/d(theta, noise) for K*P = 32000 per-scenario HMC chains at n+k=151 "
+                        "(one leapfrog stage of mcmc_parameters! on every chain): tile kernel keeps L, gradient kernel "
+                        "forms K^-1 in place on the FP64 tensor pipe and differentiates the tree per lag",
+                "value": K * P * world / (ms * 1e-3), "unit": "gradient evals/s", "ms_per_step": ms, "ok": ok_,
+                "roofline": {"bound": "tensor", "achieved": fl_ / (ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+                             "flops_per_launch": fl_, "note": "m^3/3 (Cholesky) + 2m^3/3 (inverse) per instance; "
+                             "the per-entry reverse-mode work is not counted"}}
+
+    # ---- inverse transformation + 25/50/75 % bands of the (h, K*D) draw matrix ---------------------
+    def micro_summary():
+        d_q = torch.empty((h, 3), dtype=torch.float64, device=dev)
+        d_p = to_dev(np.array([0.25, 0.5, 0.75]))
+        lib, ctx = eng._lib, eng._ctx
+
+        def run():
+            eng._check(lib.nagp_forecast_summary(ctx, 1, 0.0, 0.0, 0.0, h, K * D, d_x.data_ptr(), d_x.data_ptr(), 3,
+                                                 d_p.data_ptr(), d_q.data_ptr()))
+        step_device()
+        ms = timed(run, max(3, args.steps // 2), 3)
+        return {"what": "inverse 'positive' transformation in place + 25/50/75 % row quantiles of the (9, 20000) draws",
+                "ms_per_step": ms, "bytes_per_launch": int(h * K * D * (8 + 16 + 2 * 3 * 8 * 8))}
+
+    micro = None if args.no_micro else {"logml": micro_logml(), "append": micro_append(), "grad": micro_grad(),
+                                        "summary": micro_summary()}
 
     # sanity: the step produced finite draws and no factorisation failed
     step_device()
@@ -408,6 +443,9 @@ def main():
             micro["append"]["factor_roofline"].update(peak=peak_tf, frac=micro["append"]["factor_roofline"]["achieved"] / peak_tf)
             micro["append"]["append_roofline"].update(peak=hbm_peak, peak_source="MEASURED_PEAKS.json hbm_gbs",
                                                       frac=micro["append"]["append_roofline"]["achieved"] / hbm_peak)
+            micro["grad"]["roofline"].update(peak=peak_tf, frac=micro["grad"]["roofline"]["achieved"] / peak_tf)
+            line["hmc_gradient_microbench"] = micro["grad"]
+            line["summary_microbench"] = micro["summary"]
             line["logml_microbench"] = micro["logml"]
             line["append_microbench"] = micro["append"]
         if world == 1 and not args.no_cpu_baseline:

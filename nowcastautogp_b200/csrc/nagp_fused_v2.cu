@@ -83,6 +83,9 @@ struct V2Layout {
     unsigned long long *work_counter;   // dynamic instance scheduler (zeroed before the launch)
 };
 
+// KEEP: also write the factor, z and the inverse diagonal tiles to HBM for the gradient kernel (a separate
+// instantiation, so the forecast path does not carry that code: it measured 4 % slower with it inline).
+template <bool KEEP>
 __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, const V2Layout lay)
 {
     extern __shared__ __align__(16) double smem[];
@@ -339,7 +342,7 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                 sts64(dt + oi1 * 8, d1);
                 sts64(invL_a + oi0 * 8, w0);
                 sts64(invL_a + oi1 * 8, w1);
-                if (a.Wkeep) {
+                if (KEEP && a.Wkeep) {
                     double *wk = a.Wkeep + ((size_t)b * nt + J) * 64;
                     wk[oi0] = w0; wk[oi1] = w1;
                 }
@@ -402,7 +405,7 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
         }
         DBG_G(4);
 
-        if (a.Lkeep && !s_info) {
+        if (KEEP && a.Lkeep && !s_info) {
             // keep the factor for the gradient kernel: tiles as they are (operand layout), z padded to Q
             double *Lo = a.Lkeep + (size_t)b * ((size_t)ntiles * 64);
             for (int i = tid; i < ntiles * 32; i += kT2)
@@ -514,7 +517,7 @@ V2Plan plan_fused_v2(int q, int G, int ntheta_cap, int ntab_cap, int ncp_cap, in
     size_t total_aux = sz[0] + sz[1] + sz[2] + sz[3] + sz[4];
     cudaFuncAttributes fa{};
     size_t static_smem = 2560 + 1024;
-    if (cudaFuncGetAttributes(&fa, fused_v2_kernel) == cudaSuccess) static_smem = fa.sharedSizeBytes + 1024;   // + per-CTA reservation
+    if (cudaFuncGetAttributes(&fa, fused_v2_kernel<true>) == cudaSuccess) static_smem = fa.sharedSizeBytes + 1024;   // + per-CTA reservation
     else cudaGetLastError();
     // budget: 2 CTAs/SM if the mandatory part allows it, else everything the opt-in limit gives
     size_t two = (size_t)smem_per_sm / 2;
@@ -537,8 +540,8 @@ V2Plan plan_fused_v2(int q, int G, int ntheta_cap, int ntab_cap, int ncp_cap, in
 int fused_v2_grid(const V2Plan &pl, int64_t B, int num_sms)
 {
     int per_sm = 0;
-    cudaFuncSetAttribute(fused_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_v2_kernel, kT2, pl.smem_bytes) != cudaSuccess ||
+    cudaFuncSetAttribute(fused_v2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_v2_kernel<true>, kT2, pl.smem_bytes) != cudaSuccess ||
         per_sm < 1) {
         cudaGetLastError();
         per_sm = 1;
@@ -558,9 +561,12 @@ cudaError_t launch_fused_v2(const FusedArgs &a, const V2Plan &pl, char *scratch,
     for (int i = 0; i < 5; ++i) { lay.aux_off[i] = pl.aux_off[i]; lay.aux_smem[i] = pl.aux_smem[i]; }
     lay.scratch_stride = pl.scratch_stride;
     lay.scratch = scratch;
-    cudaError_t e = cudaFuncSetAttribute(fused_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
+    const bool keep = a.Lkeep != nullptr;
+    cudaError_t e = keep ? cudaFuncSetAttribute(fused_v2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes)
+                         : cudaFuncSetAttribute(fused_v2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (e != cudaSuccess) return e;
-    fused_v2_kernel<<<grid, kT2, pl.smem_bytes, stream>>>(a, lay);
+    if (keep) fused_v2_kernel<true><<<grid, kT2, pl.smem_bytes, stream>>>(a, lay);
+    else fused_v2_kernel<false><<<grid, kT2, pl.smem_bytes, stream>>>(a, lay);
     return cudaGetLastError();
 }
 

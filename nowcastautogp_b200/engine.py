@@ -136,19 +136,23 @@ class Engine:
 
     # ---- (f1) gradient of the log marginal likelihood -----------------------------------------------
     def logml_grad(self, ens: FlatEnsemble, t, y1, y2=None, g=None, step: float = 0.0, theta=None, noise=None,
-                   K: int = 1, check: bool = False):
+                   K: int = 1, check: bool = False, out=None):
         """logML over the n + k points [y1 | y2[s]] and its gradient w.r.t. every theta slot and the noise.
-        Returns (logml [K,P], grad_theta [K,total], grad_noise [K,P], info [K,P])."""
+        Returns (logml [K,P], grad_theta [K,total], grad_noise [K,P], info [K,P]); `out` may supply those four
+        buffers (host or device) to keep the call free of host copies."""
         P = ens.size
         n = len(y1)
-        k = 0 if y2 is None else int(np.asarray(y2).shape[-1])
+        k = 0 if y2 is None else int(np.shape(y2)[-1])
         if y2 is not None:
-            K = int(np.asarray(y2).shape[0])
+            K = int(np.shape(y2)[0])
         elif theta is not None:
-            K = int(np.asarray(theta).shape[0])
+            K = int(np.shape(theta)[0])
         total = int(ens.theta_off[-1])
-        logml, gth = np.empty((K, P)), np.empty((K, total))
-        gnz, info = np.empty((K, P)), np.zeros((K, P), np.int32)
+        if out is not None:
+            logml, gth, gnz, info = out
+        else:
+            logml, gth = np.empty((K, P)), np.empty((K, total))
+            gnz, info = np.empty((K, P)), np.zeros((K, P), np.int32)
         th = ens.theta if theta is None else theta
         nz = ens.noise if noise is None else noise
         keep = [_ptr(ens.prog), _ptr(ens.prog_off), _ptr(th, np.float64), _ptr(ens.theta_off), _ptr(nz, np.float64),
