@@ -118,6 +118,8 @@ void nagp_factor_free(nagp_factor *f);
  *   logml[K*P]           log marginal likelihood over all n + k points
  *   grad_theta[K*total]  d logML / d theta for every theta slot, same CSR layout as theta (per scenario)
  *   grad_noise[K*P]      d logML / d noise
+ * y1_stride: 0 = every instance shares y1[n]; n = instance b = s*P + p reads y1 + b*n (independent series fitted
+ * in lockstep: one "particle" per (series, particle) pair, K = 1).
  * Constrained-space derivatives; the caller applies its own chain rule to the unconstrained parameters.
  * n + k <= 232 in this version (NAGP_E_SIZE beyond). */
 int32_t nagp_logml_grad(nagp_ctx *ctx, int64_t K, int64_t P,
@@ -125,7 +127,7 @@ int32_t nagp_logml_grad(nagp_ctx *ctx, int64_t K, int64_t P,
                         const double *theta, const int64_t *theta_off, int64_t theta_stride_k,
                         const double *noise, int64_t noise_stride_k,
                         int64_t n, int64_t k, const double *t, const int32_t *g, double step,
-                        const double *y1, const double *y2,
+                        const double *y1, int64_t y1_stride, const double *y2,
                         double *logml, double *grad_theta, double *grad_noise, int32_t *info);
 
 /* ---- (a2/a4) appendable factor for long series: SMC data annealing, rank-append Cholesky ---------

@@ -67,6 +67,60 @@ def make_and_fit_model(data: TData, *, n_particles: int = 1, smc_data_proportion
     return model
 
 
+def make_and_fit_models(datas: Sequence[TData], *, n_particles: int = 1, smc_data_proportion: float = 0.1,
+                        flat_threshold: float = 1e-3, config: Optional[GPConfig] = None, rng=None, engine=None,
+                        share_order: bool = True, **kwargs) -> List[GPModel]:
+    """`make_and_fit_model` for S independent series at once (the per-jurisdiction loop of
+    `docs/vignettes/getting-started.jl:540-552`): one host thread per series runs the unchanged SMC logic, and a
+    `CoalescingEngine` merges the S concurrent likelihood / gradient requests of every step into one device
+    launch of S·P instances (`coalesce.py`). Series with identical dates share one shuffled observation order
+    (`share_order`) so that their requests stay on the same time grid. The result of each series is what
+    `make_and_fit_model(data, rng=<its spawned generator>, obs_order=<the shared order>)` gives on its own."""
+    import threading
+    from .coalesce import CoalescingEngine
+    from .gpmodel import default_engine
+    if "n_mcmc" not in kwargs or "n_hmc" not in kwargs:
+        raise TypeError("make_and_fit_models: keyword arguments n_mcmc and n_hmc are required")
+    S = len(datas)
+    if S == 0:
+        return []
+    eng = default_engine() if engine is None else engine
+    seq = np.random.SeedSequence(rng.integers(2 ** 63) if rng is not None else None)
+    rngs = [np.random.default_rng(ss) for ss in seq.spawn(S + 1)]
+    same_dates = all(len(d.ds) == len(datas[0].ds) and np.array_equal(np.asarray(d.ds), np.asarray(datas[0].ds))
+                     for d in datas)
+    order = rngs[S].permutation(len(datas[0].y)) if (share_order and same_dates and kwargs.get("shuffle", True)) else None
+    hub = CoalescingEngine(eng, S)
+    models: List[Optional[GPModel]] = [None] * S
+    errors: List[Optional[BaseException]] = [None] * S
+
+    def work(s: int) -> None:
+        try:
+            kw = dict(kwargs)
+            if order is not None:
+                kw["obs_order"] = order
+            models[s] = make_and_fit_model(datas[s], n_particles=n_particles, smc_data_proportion=smc_data_proportion,
+                                           flat_threshold=flat_threshold, config=config, rng=rngs[s],
+                                           engine=hub.client(s), **kw)
+        except BaseException as e:      # noqa: BLE001 - re-raised on the calling thread
+            errors[s] = e
+        finally:
+            hub.retire(s)
+
+    threads = [threading.Thread(target=work, args=(s,), name=f"nagp-fit-{s}") for s in range(S)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    for e in errors:
+        if e is not None:
+            raise e
+    for m in models:
+        m.engine = eng
+    make_and_fit_models.last_stats = {"requests": hub.requests, "device_calls": hub.device_calls}
+    return models
+
+
 def _apply(inv_transformation: Callable, x: np.ndarray, engine=None) -> np.ndarray:
     if inv_transformation is _identity:
         return x

@@ -1,0 +1,147 @@
+"""Request coalescing for independent series fitted at the same time (BASELINE configs[3]).
+
+The reference fits one `make_and_fit_model` per jurisdiction in a host loop (`docs/vignettes/getting-started.jl:
+540-552`); inside, every SMC / MCMC / HMC step scores the P particles of THAT series (`src/make_and_fit_model.jl:
+91`). P = 8…64 instances per launch leaves a 148-SM device almost idle, and the steps of one chain are sequential
+by nature. The parallelism is across series: S series × P particles per step.
+
+`CoalescingEngine` wraps one `Engine` for S concurrent clients (one host thread per series, each running the
+unchanged `GPModel.fit_smc` logic). A client's `logml_batch` / `logml_grad` call blocks until every still-active
+client has submitted its next request; the last one to arrive merges all pending requests with the same time grid
+into ONE device call (concatenated ensembles, per-instance observation vectors) and scatters the results back.
+Requests on different grids simply become separate calls. The device context is only ever entered by one thread.
+Everything else (`ess`, `factor_store`, `predict`, `draw`, …) is forwarded under the same lock.
+"""
+from __future__ import annotations
+
+import threading
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from .kernels import FlatEnsemble
+
+
+def concat_ensembles(parts: List[FlatEnsemble]) -> FlatEnsemble:
+    prog = np.concatenate([np.asarray(e.prog, np.uint8) for e in parts])
+    theta = np.concatenate([np.asarray(e.theta, np.float64) for e in parts])
+    noise = np.concatenate([np.asarray(e.noise, np.float64) for e in parts])
+    prog_off, theta_off = [np.zeros(1, np.int64)], [np.zeros(1, np.int64)]
+    po = to = 0
+    for e in parts:
+        prog_off.append(np.asarray(e.prog_off[1:], np.int64) + po)
+        theta_off.append(np.asarray(e.theta_off[1:], np.int64) + to)
+        po += int(e.prog_off[-1]); to += int(e.theta_off[-1])
+    return FlatEnsemble(prog, np.concatenate(prog_off), theta, np.concatenate(theta_off), noise)
+
+
+class _Request:
+    __slots__ = ("kind", "key", "ens", "t", "g", "step", "y", "result", "error")
+
+    def __init__(self, kind, ens, t, g, step, y):
+        self.kind, self.ens, self.t, self.g, self.step = kind, ens, np.asarray(t, np.float64), g, float(step)
+        self.y = np.asarray(y, np.float64)
+        self.key = (kind, len(self.t), self.t.tobytes(), None if g is None else np.asarray(g, np.int32).tobytes(), self.step)
+        self.result = None
+        self.error = None
+
+
+class CoalescingEngine:
+    def __init__(self, engine, n_clients: int):
+        self.engine = engine
+        self._cv = threading.Condition()
+        self._active = int(n_clients)
+        self._pending: Dict[int, _Request] = {}
+        self._generation = 0
+        self.device_calls = 0          # merged launches issued
+        self.requests = 0              # client requests served
+
+    # ---- client life cycle ----------------------------------------------------------------------------
+    def client(self, cid: int) -> "_Client":
+        return _Client(self, cid)
+
+    def retire(self, cid: int) -> None:
+        """A client is done (or failed): stop waiting for it."""
+        with self._cv:
+            self._active -= 1
+            if self._pending and len(self._pending) >= self._active:
+                self._flush()
+
+    # ---- coalescing -------------------------------------------------------------------------------------
+    def _submit(self, cid: int, req: _Request):
+        with self._cv:
+            self._pending[cid] = req
+            self.requests += 1
+            if len(self._pending) >= self._active:
+                self._flush()
+            else:
+                gen = self._generation
+                while self._generation == gen:
+                    self._cv.wait()
+        if req.error is not None:
+            raise req.error
+        return req.result
+
+    def _flush(self) -> None:
+        """Caller holds the lock and is the only thread that touches the device."""
+        groups: Dict[Tuple, List[_Request]] = {}
+        for cid in sorted(self._pending):
+            r = self._pending[cid]
+            groups.setdefault(r.key, []).append(r)
+        for reqs in groups.values():
+            try:
+                self._run_group(reqs)
+            except Exception as e:          # every member of the group sees the failure
+                for r in reqs:
+                    r.error = e
+        self._pending = {}
+        self._generation += 1
+        self._cv.notify_all()
+
+    def _run_group(self, reqs: List[_Request]) -> None:
+        r0 = reqs[0]
+        n = len(r0.t)
+        ens = concat_ensembles([r.ens for r in reqs])
+        sizes = [r.ens.size for r in reqs]
+        y = np.concatenate([np.broadcast_to(r.y, (sz, n)) for r, sz in zip(reqs, sizes)]).reshape(-1)
+        self.device_calls += 1
+        if r0.kind == "logml":
+            lm, info = self.engine.logml_batch(ens, r0.t, y, g=r0.g, step=r0.step, y_stride=n)
+            o = 0
+            for r, sz in zip(reqs, sizes):
+                r.result = (lm[o:o + sz].copy(), info[o:o + sz].copy()); o += sz
+        else:
+            lm, gth, gnz, info = self.engine.logml_grad(ens, r0.t, y, g=r0.g, step=r0.step, y_stride=n)
+            o = to = 0
+            for r, sz in zip(reqs, sizes):
+                nth = int(r.ens.theta_off[-1])
+                r.result = (lm[:, o:o + sz].copy(), gth[:, to:to + nth].copy(), gnz[:, o:o + sz].copy(),
+                            info[:, o:o + sz].copy())
+                o += sz; to += nth
+
+    def _forward(self, name, *args, **kwargs):
+        with self._cv:
+            return getattr(self.engine, name)(*args, **kwargs)
+
+
+class _Client:
+    """What a `GPModel` sees as its engine."""
+
+    def __init__(self, hub: CoalescingEngine, cid: int):
+        self._hub, self._cid = hub, cid
+
+    def logml_batch(self, ens, t, y, g=None, step: float = 0.0, **kw):
+        assert not kw.get("y_stride"), "per-instance y goes through the coalescer itself"
+        return self._hub._submit(self._cid, _Request("logml", ens, t, g, step, y))
+
+    def logml_grad(self, ens, t, y1, y2=None, g=None, step: float = 0.0, theta=None, noise=None, **kw):
+        if y2 is not None or theta is not None or noise is not None:      # per-scenario chains: not a fit-time call
+            return self._hub._forward("logml_grad", ens, t, y1, y2=y2, g=g, step=step, theta=theta, noise=noise, **kw)
+        return self._hub._submit(self._cid, _Request("grad", ens, t, g, step, y1))
+
+    def __getattr__(self, name):
+        hub = self._hub
+        attr = getattr(hub.engine, name)
+        if not callable(attr):
+            return attr
+        return lambda *a, **k: hub._forward(name, *a, **k)

@@ -542,12 +542,12 @@ void nagp_factor_free(nagp_factor *f)
 int32_t nagp_logml_grad(nagp_ctx *ctx, int64_t K, int64_t P, const uint8_t *prog, const int64_t *prog_off,
                         const double *theta, const int64_t *theta_off, int64_t theta_stride_k,
                         const double *noise, int64_t noise_stride_k, int64_t n, int64_t k, const double *t,
-                        const int32_t *g, double step, const double *y1, const double *y2,
+                        const int32_t *g, double step, const double *y1, int64_t y1_stride, const double *y2,
                         double *logml, double *grad_theta, double *grad_noise, int32_t *info)
 {
     if (!ctx) return NAGP_E_ARG;
     if (K <= 0 || P <= 0 || !prog || !prog_off || !theta || !theta_off || !noise || !t || !y1 || !logml ||
-        !grad_theta || !grad_noise || !info || (k > 0 && !y2) || n <= 0 || k < 0)
+        !grad_theta || !grad_noise || !info || (k > 0 && !y2) || n <= 0 || k < 0 || (y1_stride != 0 && y1_stride < n))
         return fail(ctx, NAGP_E_ARG, "nagp_logml_grad: null or empty argument");
     if (n + k > fused_v2_max_q()) return fail(ctx, NAGP_E_SIZE, "nagp_logml_grad: n + k > 232 not supported yet");
     if (on_device(prog_off) || on_device(theta_off))
@@ -572,7 +572,8 @@ int32_t nagp_logml_grad(nagp_ctx *ctx, int64_t K, int64_t P, const uint8_t *prog
     NAGP_TRY(stage_in(ctx, t, (size_t)m, &a.t));
     NAGP_TRY(stage_in(ctx, g, (size_t)m, &a.g));
     a.step = step;
-    NAGP_TRY(stage_in(ctx, y1, (size_t)n, &a.y1));
+    NAGP_TRY(stage_in(ctx, y1, (size_t)(y1_stride ? (B - 1) * y1_stride + n : n), &a.y1));
+    a.y1_stride = y1_stride;
     NAGP_TRY(stage_in(ctx, y2, (size_t)(K * k), &a.y2));
     a.ya = 1.0; a.yb = 0.0;
     NAGP_TRY(stage_out(ctx, logml, (size_t)B, &a.logml_m));

@@ -136,12 +136,12 @@ class Engine:
 
     # ---- (f1) gradient of the log marginal likelihood -----------------------------------------------
     def logml_grad(self, ens: FlatEnsemble, t, y1, y2=None, g=None, step: float = 0.0, theta=None, noise=None,
-                   K: int = 1, check: bool = False, out=None):
+                   K: int = 1, check: bool = False, out=None, y_stride: int = 0):
         """logML over the n + k points [y1 | y2[s]] and its gradient w.r.t. every theta slot and the noise.
         Returns (logml [K,P], grad_theta [K,total], grad_noise [K,P], info [K,P]); `out` may supply those four
         buffers (host or device) to keep the call free of host copies."""
         P = ens.size
-        n = len(y1)
+        n = int(y_stride) if y_stride else len(y1)
         k = 0 if y2 is None else int(np.shape(y2)[-1])
         if y2 is not None:
             K = int(np.shape(y2)[0])
@@ -160,8 +160,8 @@ class Engine:
                 _ptr(logml), _ptr(gth), _ptr(gnz), _ptr(info)]
         p = [x[0] for x in keep]
         rc = self._lib.nagp_logml_grad(self._ctx, K, P, p[0], p[1], p[2], p[3], 0 if theta is None else total,
-                                       p[4], 0 if noise is None else P, n, k, p[5], p[6], step, p[7], p[8],
-                                       p[9], p[10], p[11], p[12])
+                                       p[4], 0 if noise is None else P, n, k, p[5], p[6], step, p[7], int(y_stride),
+                                       p[8], p[9], p[10], p[11], p[12])
         self._check(rc, raise_posdef=check)
         return logml, gth, gnz, info
 

@@ -335,7 +335,7 @@ class GPModel:
     # ---- AutoGP.fit_smc!: src/make_and_fit_model.jl:91 --------------------------------------------------
     def fit_smc(self, *, schedule: Sequence[int], n_mcmc: int, n_hmc: int, shuffle: bool = True,
                 biased: bool = False, adaptive_rejuvenation: bool = False, hmc_config=None,
-                verbose: bool = False, ess_fraction: float = 0.5) -> None:
+                verbose: bool = False, ess_fraction: float = 0.5, obs_order=None) -> None:
         """Data-annealed SMC [R]: for each cumulative count in `schedule` absorb the next batch of
         observations (one batched device logML call for all particles), resample when the ESS
         drops below `ess_fraction`·P (AutoGP's adaptive default, `docs/vignettes/setting-priors.jl:
@@ -343,7 +343,11 @@ class GPModel:
         `n_mcmc` and `n_hmc` are required keywords, as in AutoGP (`test/test_gpconfig.jl:37-43`)."""
         n = len(self.y)
         self._hmc_config = hmc_config
-        self.obs_order = self.rng.permutation(n) if shuffle else np.arange(n)
+        if obs_order is not None:           # series fitted in lockstep share one order, so their requests coalesce
+            self.obs_order = np.asarray(obs_order, np.int64)
+            assert sorted(self.obs_order.tolist()) == list(range(n)), "obs_order must be a permutation of the observations"
+        else:
+            self.obs_order = self.rng.permutation(n) if shuffle else np.arange(n)
         for step in schedule:
             step = int(min(step, n))
             idx = np.sort(self.obs_order[:step])
