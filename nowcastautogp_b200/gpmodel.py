@@ -14,6 +14,7 @@ and predictive moment is a batched call into libnagp.
 from __future__ import annotations
 
 import copy
+import functools
 from dataclasses import dataclass, field
 from functools import reduce
 from math import gcd
@@ -147,6 +148,59 @@ def slot_dtheta_dz(name: str, z: float, theta: float, config: GPConfig) -> float
     return pr["wildcard"]["sigma"] * theta
 
 
+# ---- the same two maps over whole slot vectors (every particle of a call at once) ---------------------------
+_SLOT_CODE = {"period": 1, "gamma": 2, "intercept": 3, "location": 4, "scale": 5}      # 0: wildcard (log-normal)
+
+
+@functools.lru_cache(maxsize=65536)
+def slot_codes(prog: bytes) -> np.ndarray:
+    """Slot kind of every theta slot of a program (cached per structure)."""
+    out = np.array([_SLOT_CODE.get(nm, 0) for nm in kn.theta_slot_names(prog)], np.int8)
+    out.setflags(write=False)
+    return out
+
+
+def transform_slots(codes: np.ndarray, z: np.ndarray, config: GPConfig) -> np.ndarray:
+    """`slot_transform` over a vector of slots."""
+    pr = config.prior
+    z = np.clip(np.asarray(z, np.float64), -60.0, 60.0)
+    th = np.exp(pr["wildcard"]["mu"] + pr["wildcard"]["sigma"] * z)
+    m = codes == 1
+    if m.any():
+        th[m] = np.exp(pr["period"]["mu"] + pr["period"]["sigma"] * z[m])
+    m = codes == 2
+    if m.any():
+        th[m] = 2.0 * _logistic(pr["gamma"]["mu"] + pr["gamma"]["sigma"] * z[m])
+    m = codes == 3
+    if m.any():
+        th[m] = z[m]
+    m = codes == 4
+    if m.any():
+        th[m] = [_norm_cdf(v) for v in z[m]]
+    m = codes == 5
+    if m.any():
+        th[m] = config.cp_scale
+    return th
+
+
+def dtheta_dz_slots(codes: np.ndarray, z: np.ndarray, theta: np.ndarray, config: GPConfig) -> np.ndarray:
+    """`slot_dtheta_dz` over a vector of slots."""
+    pr = config.prior
+    out = pr["wildcard"]["sigma"] * theta
+    m = codes == 1
+    if m.any():
+        out[m] = pr["period"]["sigma"] * theta[m]
+    m = codes == 2
+    if m.any():
+        out[m] = pr["gamma"]["sigma"] * theta[m] * (1.0 - 0.5 * theta[m])
+    out[codes == 3] = 1.0
+    m = codes == 4
+    if m.any():
+        out[m] = np.exp(-0.5 * z[m] * z[m]) / np.sqrt(2.0 * np.pi)
+    out[codes == 5] = 0.0
+    return out
+
+
 HMC_DEFAULT = {"n_leapfrog": 10, "eps": 0.02}     # Gen.hmc's L = 10 [R]; step sized for N(0,1)-scaled z
 
 
@@ -158,8 +212,7 @@ class Particle:
     noise_z: float
 
     def theta(self, config: GPConfig) -> List[float]:
-        names = kn.theta_slot_names(self.prog)
-        return [slot_transform(nm, zz, config) for nm, zz in zip(names, self.z)]
+        return transform_slots(slot_codes(self.prog), self.z, config).tolist()
 
     def noise(self, config: GPConfig) -> float:
         if config.noise is not None:
@@ -211,15 +264,43 @@ def subtree_slices(prog: bytes) -> List[Tuple[int, int]]:
 
 
 def pack_particles(particles: Sequence[Particle], config: GPConfig) -> kn.FlatEnsemble:
+    """All particles of a call as one flat ensemble; the z -> theta map runs once over the concatenated slots."""
     progs = [p.prog for p in particles]
-    thetas = [p.theta(config) for p in particles]
     prog_off = np.zeros(len(progs) + 1, np.int64)
     theta_off = np.zeros(len(progs) + 1, np.int64)
     np.cumsum([len(p) for p in progs], out=prog_off[1:])
-    np.cumsum([len(t) for t in thetas], out=theta_off[1:])
+    np.cumsum([len(p.z) for p in particles], out=theta_off[1:])
+    codes = np.concatenate([slot_codes(p.prog) for p in particles]) if particles else np.zeros(0, np.int8)
+    z = np.concatenate([p.z for p in particles]) if particles else np.zeros(0)
+    assert len(codes) == len(z), "particle with a z vector that does not match its structure"
+    if config.noise is not None:
+        noise = np.full(len(progs), float(config.noise))
+    else:
+        noise = transform_slots(np.zeros(len(progs), np.int8), np.array([p.noise_z for p in particles]), config)
     return kn.FlatEnsemble(np.frombuffer(b"".join(progs), np.uint8).copy(), prog_off,
-                           np.asarray([x for t in thetas for x in t], np.float64), theta_off,
-                           np.asarray([p.noise(config) for p in particles], np.float64))
+                           transform_slots(codes, z, config), theta_off, noise)
+
+
+class _FlatChains:
+    """The particles of one call laid out for vector arithmetic: concatenated slot vectors and their offsets."""
+
+    def __init__(self, particles: Sequence[Particle], config: GPConfig):
+        self.P = len(particles)
+        progs = [p.prog for p in particles]
+        self.prog = np.frombuffer(b"".join(progs), np.uint8).copy()
+        self.prog_off = np.zeros(self.P + 1, np.int64)
+        self.off = np.zeros(self.P + 1, np.int64)
+        np.cumsum([len(p) for p in progs], out=self.prog_off[1:])
+        np.cumsum([len(p.z) for p in particles], out=self.off[1:])
+        self.codes = np.concatenate([slot_codes(p.prog) for p in particles]) if self.P else np.zeros(0, np.int8)
+        self.Z = np.concatenate([p.z for p in particles]) if self.P else np.zeros(0)
+        self.NZ = np.array([p.noise_z for p in particles], np.float64)
+        self.noise_codes = np.zeros(self.P, np.int8)
+        self._seg = np.repeat(np.arange(self.P), np.diff(self.off))
+
+    def segsum(self, v: np.ndarray) -> np.ndarray:
+        """Per-particle sums of a slot vector (particles without slots give 0)."""
+        return np.bincount(self._seg, weights=v, minlength=self.P)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -402,31 +483,42 @@ class GPModel:
     def _logpost_grad(self, particles: Sequence[Particle], idx: np.ndarray):
         """log p(y[idx] | particle) + log N(z; 0, I) and its gradient in unconstrained space, all particles in
         one `nagp_logml_grad` call. Returns (lp [P], list of dz arrays, dnoise_z [P])."""
-        cfg = self.config
+        flat = _FlatChains(particles, self.config)
+        lp, dZ, dNZ = self._logpost_grad_flat(flat, flat.Z, flat.NZ, self._grid_of(idx))
+        return lp, [dZ[flat.off[i]:flat.off[i + 1]] for i in range(len(particles))], dNZ
+
+    def _grid_of(self, idx: np.ndarray):
         t, g, step = self._times(self.ds[idx])
-        ens = pack_particles(particles, cfg)
-        lm, gth, gnz, info = self._engine().logml_grad(ens, t, self.y_transform.apply(self.y[idx]), g=g, step=step)
+        return t, g, step, self.y_transform.apply(self.y[idx])
+
+    def _logpost_grad_flat(self, flat: "_FlatChains", Z: np.ndarray, NZ: np.ndarray, grid):
+        """The same over concatenated slot vectors: Z [sum slots], NZ [P] -> (lp [P], dZ, dNZ)."""
+        cfg = self.config
+        t, g, step, y = grid
+        theta = transform_slots(flat.codes, Z, cfg)
+        noise = (np.full(flat.P, float(cfg.noise)) if cfg.noise is not None
+                 else transform_slots(flat.noise_codes, NZ, cfg))
+        ens = kn.FlatEnsemble(flat.prog, flat.prog_off, theta, flat.off, noise)
+        lm, gth, gnz, info = self._engine().logml_grad(ens, t, y, g=g, step=step)
         lm, gth, gnz, info = lm[0], gth[0], gnz[0], info[0]
         lp = np.where(info == 0, lm, -np.inf)
-        dzs, dnz = [], np.zeros(len(particles))
-        for i, p in enumerate(particles):
-            names = kn.theta_slot_names(p.prog)
-            th = ens.theta[ens.theta_off[i]:ens.theta_off[i + 1]]
-            jac = np.array([slot_dtheta_dz(nm, zz, tv, cfg) for nm, zz, tv in zip(names, p.z, th)])
-            dz = np.nan_to_num(gth[ens.theta_off[i]:ens.theta_off[i + 1]], nan=0.0, posinf=0.0, neginf=0.0) * jac - p.z
-            lp[i] += -0.5 * float(p.z @ p.z)
-            if cfg.noise is None:
-                dnz[i] = (gnz[i] if np.isfinite(gnz[i]) else 0.0) * slot_dtheta_dz("noise", p.noise_z, ens.noise[i], cfg) - p.noise_z
-                lp[i] += -0.5 * p.noise_z ** 2
-            dzs.append(np.where(np.isfinite(dz), dz, 0.0))
-        return lp, dzs, np.where(np.isfinite(dnz), dnz, 0.0)
+        dZ = np.where(np.isfinite(gth), gth, 0.0) * dtheta_dz_slots(flat.codes, Z, theta, cfg) - Z
+        dZ = np.where(np.isfinite(dZ), dZ, 0.0)
+        lp = lp - 0.5 * flat.segsum(Z * Z)
+        dNZ = np.zeros(flat.P)
+        if cfg.noise is None:
+            dNZ = np.where(np.isfinite(gnz), gnz, 0.0) * dtheta_dz_slots(flat.noise_codes, NZ, noise, cfg) - NZ
+            dNZ = np.where(np.isfinite(dNZ), dNZ, 0.0)
+            lp = lp - 0.5 * NZ ** 2
+        return lp, dZ, dNZ
 
     def mcmc_parameters(self, n_hmc: int, hmc_config: Optional[dict] = None) -> float:
         """`AutoGP.mcmc_parameters!(model, n_hmc)` (`src/forecasting.jl:148,65`): `n_hmc` Hamiltonian Monte
         Carlo steps on the unconstrained hyperparameters of every particle (N(0,1) prior on z [R]), all
         particles advanced together: each leapfrog stage is ONE device call giving every particle's log
-        marginal likelihood and its gradient (`nagp_logml_grad`). Beyond the gradient kernel's size limit the
-        move degrades to random-walk Metropolis on the same target. Returns the acceptance rate."""
+        marginal likelihood and its gradient (`nagp_logml_grad`); the integrator runs over the concatenated
+        slot vectors of all particles. Beyond the gradient kernel's size limit the move degrades to
+        random-walk Metropolis on the same target. Returns the acceptance rate."""
         from .engine import NagpError
         hc = dict(HMC_DEFAULT, **(hmc_config or getattr(self, "_hmc_config", None) or {}))
         L, eps = int(hc["n_leapfrog"]), float(hc["eps"])
@@ -435,45 +527,43 @@ class GPModel:
         if len(idx) == 0 or n_hmc <= 0:
             return 0.0
         learn_noise = self.config.noise is None
+        flat = _FlatChains(self.particles, self.config)
+        grid = self._grid_of(idx)
+        Z, NZ = flat.Z, flat.NZ
         try:
-            lp, dzs, dnz = self._logpost_grad(self.particles, idx)
+            lp, dZ, dNZ = self._logpost_grad_flat(flat, Z, NZ, grid)
         except NagpError as e:
             if e.code != -4:
                 raise
             return self._metropolis_parameters(n_hmc)
         acc = 0
         for _ in range(n_hmc):
-            cur = [p.copy() for p in self.particles]
-            mom = [self.rng.standard_normal(len(p.z)) for p in cur]
+            mom = self.rng.standard_normal(len(Z))
             mnz = self.rng.standard_normal(P) if learn_noise else np.zeros(P)
-            h0 = -lp + np.array([0.5 * float(m @ m) for m in mom]) + 0.5 * mnz ** 2
-            prop = [p.copy() for p in cur]
-            g_z, g_n, lp_new = dzs, dnz, lp
+            h0 = -lp + 0.5 * flat.segsum(mom * mom) + 0.5 * mnz ** 2
+            Zq, NZq, g_z, g_n, lp_new = Z, NZ, dZ, dNZ, lp
             for _l in range(L):
-                for i, q in enumerate(prop):
-                    mom[i] = mom[i] + 0.5 * eps * g_z[i]
-                    q.z = q.z + eps * mom[i]
-                    if learn_noise:
-                        mnz[i] += 0.5 * eps * g_n[i]
-                        q.noise_z = float(q.noise_z + eps * mnz[i])
-                lp_new, g_z, g_n = self._logpost_grad(prop, idx)
-                for i in range(P):
-                    mom[i] = mom[i] + 0.5 * eps * g_z[i]
-                    if learn_noise:
-                        mnz[i] += 0.5 * eps * g_n[i]
-            h1 = -lp_new + np.array([0.5 * float(m @ m) for m in mom]) + 0.5 * mnz ** 2
+                mom = mom + 0.5 * eps * g_z
+                Zq = Zq + eps * mom
+                if learn_noise:
+                    mnz = mnz + 0.5 * eps * g_n
+                    NZq = NZq + eps * mnz
+                lp_new, g_z, g_n = self._logpost_grad_flat(flat, Zq, NZq, grid)
+                mom = mom + 0.5 * eps * g_z
+                if learn_noise:
+                    mnz = mnz + 0.5 * eps * g_n
+            h1 = -lp_new + 0.5 * flat.segsum(mom * mom) + 0.5 * mnz ** 2
             accept = np.log(self.rng.uniform(size=P)) < np.where(np.isfinite(h1), h0 - h1, -np.inf)
-            new_dzs, new_dnz, new_lp = [], dnz.copy(), lp.copy()
-            for i in range(P):
-                if accept[i]:
-                    self.particles[i] = prop[i]
-                    new_dzs.append(g_z[i]); new_dnz[i] = g_n[i]; new_lp[i] = lp_new[i]
-                    prior = -0.5 * float(prop[i].z @ prop[i].z) - (0.5 * prop[i].noise_z ** 2 if learn_noise else 0.0)
-                    self._logml[i] = lp_new[i] - prior
-                    acc += 1
-                else:
-                    new_dzs.append(dzs[i])
-            dzs, dnz, lp = new_dzs, new_dnz, new_lp
+            acc += int(accept.sum())
+            slot_acc = np.repeat(accept, np.diff(flat.off))
+            Z, dZ = np.where(slot_acc, Zq, Z), np.where(slot_acc, g_z, dZ)
+            NZ, dNZ, lp = np.where(accept, NZq, NZ), np.where(accept, g_n, dNZ), np.where(accept, lp_new, lp)
+        prior = -0.5 * flat.segsum(Z * Z) - (0.5 * NZ ** 2 if learn_noise else 0.0)
+        moved = np.array([not np.array_equal(Z[flat.off[i]:flat.off[i + 1]], p.z) or NZ[i] != p.noise_z
+                          for i, p in enumerate(self.particles)])
+        for i in np.nonzero(moved)[0]:
+            self.particles[i] = Particle(self.particles[i].prog, Z[flat.off[i]:flat.off[i + 1]].copy(), float(NZ[i]))
+            self._logml[i] = lp[i] - prior[i]
         return acc / max(1, n_hmc * P)
 
     def _metropolis_parameters(self, n_steps: int, step_size: float = 0.15) -> float:
