@@ -21,10 +21,11 @@
 //
 // The tree is then differentiated in reverse mode per matrix entry over the COMPILED program (stationary
 // sub-trees folded into lag tables, ChangePoint sigmoids tabulated per point, as in the Gram pass of the tile
-// kernel). A thread owns one lag d and walks the rows a with b = ginv[g_a - d]: the adjoint that reaches a lag
-// table is summed per (table, lag) in a register — no atomics, fixed order, bit-reproducible — and only
-// afterwards pushed through the stationary sub-tree once per (table, lag): G transcendental evaluations per
-// table instead of n^2/2. Low lags (long diagonals) are split between two threads.
+// kernel). A lane owns one lag d of a group of 32 and walks rows a with b = ginv[g_a - d]; the rows are dealt
+// round-robin to the 8 warps. The adjoint that reaches a lag table is summed per (table, lag, warp) in a register
+// — no atomics, fixed order, bit-reproducible — and only afterwards pushed through the stationary sub-tree once
+// per (table, lag): G transcendental evaluations per table instead of n^2/2. A fully stationary tree needs no
+// per-entry interpretation at all (the entry's weight is the table's adjoint).
 // Formulas: docs/KERNEL_SPEC.md §3, §8.
 #include <algorithm>
 
@@ -161,10 +162,9 @@ __device__ __forceinline__ void rev_entry(const uint8_t *op, const int16_t *arg,
 
 struct GradTileLayout {
     int nt;
-    int region_bytes;         // union region: {lcolT, part} during the sweep, {tt, theta, hx, gg, ginv} afterwards
-    int nsec;                 // threads that take the second half of a low lag (0 .. kGT2 - Gd)
+    int region_bytes;         // union region: {lcolT, part} during the sweep, {tt, theta, gg, ginv} afterwards
     int Gd;                   // lags handled (lag-grid extent, or n when times are pairwise)
-    int scratch_stride;       // bytes of global scratch per CTA (lag tables + sigma tables)
+    int scratch_stride;       // bytes of global scratch per CTA (lag tables, sigma tables, per-warp table adjoints)
     char *scratch;
     unsigned long long *work_counter;
 };
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = a.n, nt = lay.nt, Q = nt * 8, ntiles = tri(nt);
-    const int G = a.G, Gd = lay.Gd, nsec = lay.nsec;
+    const int G = a.G, Gd = lay.Gd;
 
     double *tiles = smem;
     double *alpha = tiles + ntiles * 64;        // [Q]
@@ -191,11 +191,11 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
     // differentiation view of the region
     double *tt = region;                        // [Q]
     double *th = tt + Q;                        // [MAX_THETA]
-    double *hx = th + MAX_THETA;                // [ntab_cap][nsec]
-    int *gg = reinterpret_cast<int *>(hx + a.ntab_cap * nsec);   // [Q]
+    int *gg = reinterpret_cast<int *>(th + MAX_THETA);           // [Q]
     short *ginv = reinterpret_cast<short *>(gg + Q);             // [Gd]
     double *tab = reinterpret_cast<double *>(lay.scratch + (size_t)blockIdx.x * lay.scratch_stride);   // [ntab_cap][G]
     double *sig = tab + a.ntab_cap * (G > 0 ? G : 0);                                                    // [ncp_cap][Q]
+    double *hpart = sig + a.ncp_cap * Q;         // [kGW][ntab_cap][32 ceil(Gd/32)] per-warp partial table adjoints
 
     const int lr = lane >> 2, lj = lane & 3;
     const int oi0 = op_idx(lr, 2 * lj), oi1 = op_idx(lr, 2 * lj + 1);
@@ -369,55 +369,52 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
         }
         __syncthreads();
 
-        // ---- 3. reverse mode per entry: thread <-> lag ---------------------------------------------------------
+        // ---- 3. reverse mode per entry: lane <-> lag within a group of 32 lags, rows dealt round-robin to the warps --
+        // Every warp walks every lag group over its own rows (a = warp, warp + 8, ...), so the triangle's uneven
+        // diagonals cost all warps the same; a lag's adjoint sum is then split over the 8 warps and recombined in a
+        // fixed order below (bit-reproducible, no atomics).
         double gl[MAX_THETA];
         for (int j = 0; j < (int)ntheta; ++j) gl[j] = 0.0;
-        double hacc[MAX_TABLES];
-#pragma unroll
-        for (int j = 0; j < MAX_TABLES; ++j) hacc[j] = 0.0;
         double gnoise = 0.0;
         const bool grid = a.g != nullptr;
-        for (int item = tid; item < Gd + nsec; item += kGT2) {
-            const bool second = item >= Gd;
-            const int d = second ? item - Gd : item;
-            const int mid = (min(d, n) + n) >> 1;
-            const int a_lo = second ? mid : 0;
-            const int a_hi = (second || d >= nsec) ? n : mid;
-            for (int ia = a_lo; ia < a_hi; ++ia) {
-                const int gb = gg[ia] - g0 - d;
-                if (gb < 0) continue;
-                const int ib = ginv[gb];
+        const bool single_table = (tp.clen == 1 && tp.cop[0] == OP_TABLE);
+        const int ngroups = (Gd + 31) >> 5, Gp = ngroups * 32;
+        for (int lg = 0; lg < ngroups; ++lg) {
+            const int d = lg * 32 + lane;
+            double hacc[MAX_TABLES];
+#pragma unroll
+            for (int j = 0; j < MAX_TABLES; ++j) hacc[j] = 0.0;
+            for (int ia = warp; ia < n; ia += kGW) {
+                const int ga = gg[ia] - g0;
+                if (ga < lg * 32) continue;                    // no lag of this group reaches back from row ia
+                const int gb = ga - d;
+                const int ib = (gb >= 0 && d < Gd) ? ginv[gb] : -1;
                 if (ib < 0) continue;
                 const double Sab = tiles[(tri(ia >> 3) + (ib >> 3)) * 64 + op_idx(ia & 7, ib & 7)];
                 const double Wab = 0.5 * (alpha[ia] * alpha[ib] - Sab);
                 const double w = d == 0 ? Wab : 2.0 * Wab;
                 if (d == 0) gnoise += Wab;
+                if (single_table) { hacc[0] += w; continue; }   // fully stationary tree: the entry's weight IS the adjoint
                 const double ti = tt[ia], tj = tt[ib];
                 const double delta = grid ? (double)d * a.step : fabs(ti - tj);
                 rev_entry(tp.cop, tp.carg, tp.caux, rp.cleft, 0, tp.clen, th, ti, tj, delta, d, ia, ib, tab, G, sig, Q,
                           w, gl, hacc);
             }
-        }
-        // second halves hand their table adjoints to the lag's first thread (fixed order: reproducible)
-        if (tid >= Gd && tid < Gd + nsec) {
 #pragma unroll
             for (int j = 0; j < MAX_TABLES; ++j)
-                if (j < ntab) hx[j * nsec + (tid - Gd)] = hacc[j];
+                if (j < ntab) hpart[(warp * a.ntab_cap + j) * Gp + d] = hacc[j];
         }
         __syncthreads();
         // ---- 4. table adjoints through the stationary sub-trees, once per (table, lag) -------------------------
         for (int d = tid; d < G; d += kGT2) {
-            // with Gd > kGT2 a thread owns several lags and hacc mixes them: only reached when Gd <= kGT2 (plan)
+            for (int j = 0; j < ntab; ++j) {
+                double A = 0.0;
 #pragma unroll
-            for (int j = 0; j < MAX_TABLES; ++j) {
-                if (j < ntab) {
-                    double A = hacc[j];
-                    if (d < nsec) A += hx[j * nsec + d];
-                    if (A != 0.0) {
-                        double dummy[1];
-                        rev_entry(tp.sop, tp.sarg, nullptr, rp.sleft, tp.tab_src0[j], tp.tab_src1[j], th, 0.0, 0.0,
-                                  (double)d * a.step, 0, 0, 0, nullptr, 0, nullptr, 0, A, gl, dummy);
-                    }
+                for (int w = 0; w < kGW; ++w) A += hpart[(w * a.ntab_cap + j) * Gp + d];
+                if (A != 0.0) {
+                    double dummy[1];
+                    rev_entry(tp.sop, tp.sarg, nullptr, rp.sleft, tp.tab_src0[j], tp.tab_src1[j], th, 0.0, 0.0,
+                              (double)d * a.step, 0, 0, 0, nullptr, 0, nullptr, 0, A, gl, dummy);
                 }
             }
         }
@@ -436,11 +433,11 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
     }
 }
 
-size_t region_bytes_for(int nt, int Gd, int ntab_cap, int nsec)
+size_t region_bytes_for(int nt, int Gd)
 {
     const int Q = nt * 8;
     const size_t sweep = ((size_t)nt * 64 + (size_t)kGW * 64) * 8;
-    size_t diff = ((size_t)Q + MAX_THETA + (size_t)ntab_cap * nsec) * 8 + (size_t)Q * 4 + (size_t)Gd * 2;
+    size_t diff = ((size_t)Q + MAX_THETA) * 8 + (size_t)Q * 4 + (size_t)Gd * 2;
     diff = (diff + 15) & ~size_t(15);
     return std::max(sweep, diff);
 }
@@ -453,24 +450,20 @@ GradTilePlan plan_grad_tile(int n, int G, int ntab_cap, int ncp_cap, int smem_op
     const int nt = (n + 7) / 8, Q = nt * 8;
     pl.nt = nt;
     pl.Gd = G > 0 ? G : n;
-    if (pl.Gd > kGT2) { pl.ok = 0; return pl; }                 // one lag per thread (register accumulators)
+    if (pl.Gd > 16384) { pl.ok = 0; return pl; }                 // ginv holds 16-bit row indices
     cudaFuncAttributes fa{};
     size_t static_smem = 4096;
     if (cudaFuncGetAttributes(&fa, grad_tile_kernel) == cudaSuccess) static_smem = fa.sharedSizeBytes + 1024;
     else cudaGetLastError();
     const size_t base = ((size_t)(nt * (nt + 1) / 2) * 64 + Q + 64) * 8;
-    // second-half threads: as many as there are idle threads, fewer if that is what keeps two CTAs per SM
-    int nsec = std::min(kGT2 - pl.Gd, pl.Gd);
-    const size_t two = (size_t)smem_per_sm / 2;
-    while (nsec > 0 && base + region_bytes_for(nt, pl.Gd, ntab_cap, nsec) + static_smem > two &&
-           base + region_bytes_for(nt, pl.Gd, ntab_cap, 0) + static_smem <= two)
-        nsec -= std::min(nsec, 8);
-    pl.nsec = nsec;
-    pl.region_bytes = (int)region_bytes_for(nt, pl.Gd, ntab_cap, nsec);
+    pl.nsec = 0;
+    pl.region_bytes = (int)region_bytes_for(nt, pl.Gd);
     pl.smem_bytes = base + pl.region_bytes;
-    pl.scratch_stride = (int)((((size_t)ntab_cap * (G > 0 ? G : 0) + (size_t)ncp_cap * Q) * 8 + 255) & ~size_t(255));
+    const size_t Gp = (size_t)((pl.Gd + 31) / 32) * 32;
+    pl.scratch_stride = (int)((((size_t)ntab_cap * (G > 0 ? G : 0) + (size_t)ncp_cap * Q + (size_t)kGW * ntab_cap * Gp) * 8 + 255) & ~size_t(255));
     if (pl.scratch_stride == 0) pl.scratch_stride = 256;
     pl.ok = pl.smem_bytes + static_smem - 1024 <= (size_t)smem_optin;
+    (void)smem_per_sm;
     return pl;
 }
 
@@ -490,7 +483,7 @@ cudaError_t launch_grad_tile(const GradArgs &a, const GradTilePlan &pl, char *sc
                              int grid, cudaStream_t stream)
 {
     GradTileLayout lay{};
-    lay.nt = pl.nt; lay.region_bytes = pl.region_bytes; lay.nsec = pl.nsec; lay.Gd = pl.Gd;
+    lay.nt = pl.nt; lay.region_bytes = pl.region_bytes; lay.Gd = pl.Gd;
     lay.scratch_stride = pl.scratch_stride; lay.scratch = scratch; lay.work_counter = work_counter;
     cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
