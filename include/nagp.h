@@ -130,6 +130,32 @@ int32_t nagp_logml_grad(nagp_ctx *ctx, int64_t K, int64_t P,
                         const double *y1, int64_t y1_stride, const double *y2,
                         double *logml, double *grad_theta, double *grad_noise, int32_t *info);
 
+/* ---- (f1) mcmc_parameters!: HMC on the unconstrained hyperparameters, leapfrog on the device -------------------
+ * /root/reference/src/forecasting.jl:148 and :65; the n_hmc steps of fit_smc! (/root/reference/src/make_and_fit_model.jl:91).
+ * K scenarios x P particles = K*P chains advance together; nothing returns to the host inside a chain: each
+ * leapfrog stage is [half kick, drift, z -> theta] -> logML + gradient kernels -> [chain rule, half kick], each
+ * iteration ends with one accept/reject kernel, and the iteration is replayed as one CUDA graph.
+ * Target: log p(y | theta(z)) + log N(z; 0, I). z -> theta per slot (slot_kind[total], parameters slot_a/slot_b):
+ *   0 exp(a + b z)   2 2*logistic(a + b z)   3 z   4 Phi(z)   5 the constant a (not sampled);
+ * the noise uses (noise_kind, noise_a, noise_b) the same way (kind 5: fixed noise = noise_a, noise_z untouched).
+ *   z[K*total], noise_z[K*P]    host, in/out: the chains' unconstrained states (total = theta_off[P])
+ *   momenta[n_steps*K*total], noise_momenta[n_steps*K*P] (NULL iff noise_kind == 5), log_u[n_steps*K*P]:
+ *       the standard-normal momenta and log-uniform accept thresholds of every iteration, supplied by the caller
+ *       (as the normals of the forecast draws are), so a host integrator fed the same numbers walks the same chain
+ *   logml[K*P] log marginal likelihood of the final state, n_accept[K*P] accepted iterations, info[K*P] factorisation
+ *       status of the final state (> 0: the INITIAL state was not positive definite and no proposal was accepted).
+ * y1/y1_stride/y2, t/g/step as in nagp_logml_grad. n + k <= 232 (NAGP_E_SIZE beyond). */
+int32_t nagp_hmc(nagp_ctx *ctx, int64_t K, int64_t P,
+                 const uint8_t *prog, const int64_t *prog_off, const int64_t *theta_off,
+                 const int32_t *slot_kind, const double *slot_a, const double *slot_b,
+                 int32_t noise_kind, double noise_a, double noise_b,
+                 double *z, double *noise_z,
+                 int64_t n, int64_t k, const double *t, const int32_t *g, double step,
+                 const double *y1, int64_t y1_stride, const double *y2,
+                 int64_t n_steps, int64_t n_leapfrog, double eps,
+                 const double *momenta, const double *noise_momenta, const double *log_u,
+                 double *logml, int32_t *n_accept, int32_t *info);
+
 /* ---- (a2/a4) appendable factor for long series: SMC data annealing, rank-append Cholesky ---------
  * AutoGP.fit_smc! walks a schedule of growing observation counts (/root/reference/src/make_and_fit_model.jl:
  * 89-91, linear_schedule) and re-scores every particle from scratch at each step; add_data! does the same

@@ -31,6 +31,8 @@ SIGNATURES = {
     "nagp_factor_free": (None, [_vp]),
     "nagp_logml_grad": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _vp, _f64,
                                _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "nagp_hmc": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f64, _f64, _vp, _vp, _i64, _i64, _vp, _vp,
+                        _f64, _vp, _i64, _vp, _i64, _i64, _f64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nagp_factor_store_large": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _f64, _vp,
                                        C.POINTER(_vp), _vp, _vp]),
     "nagp_factor_append": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),

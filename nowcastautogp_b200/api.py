@@ -16,7 +16,8 @@ from typing import Callable, List, Optional, Sequence
 
 import numpy as np
 
-from .gpmodel import GPConfig, GPModel, HMC_DEFAULT, pack_particles, slot_dtheta_dz, slot_transform
+from .gpmodel import (GPConfig, GPModel, HMC_DEFAULT, device_noise_spec, device_slot_spec, dtheta_dz_slots,
+                      pack_particles, slot_codes, transform_slots)
 from .tdata import TData
 from . import kernels as kn
 
@@ -159,7 +160,8 @@ class _ScenarioParams:
         self.m = model
         self.K, self.P = K, model.num_particles()
         self.prog_all = b"".join(p.prog for p in model.particles)
-        self.names = kn.theta_slot_names(self.prog_all)
+        self.codes = np.concatenate([slot_codes(p.prog) for p in model.particles])
+        self.codes_k = np.tile(self.codes, K)
         self.z = np.tile(np.concatenate([p.z for p in model.particles]), (K, 1))
         self.noise_z = np.tile(np.array([p.noise_z for p in model.particles]), (K, 1))
         self.ens = pack_particles(model.particles, model.config)
@@ -168,25 +170,21 @@ class _ScenarioParams:
 
     def theta(self, z, noise_z):
         cfg = self.m.config
-        th = np.empty_like(z)
-        for j, nm in enumerate(self.names):
-            th[:, j] = [slot_transform(nm, v, cfg) for v in z[:, j]]
+        th = transform_slots(self.codes_k, z.reshape(-1), cfg).reshape(z.shape)
         if cfg.noise is not None:
             nz = np.full(noise_z.shape, float(cfg.noise))
         else:
-            nz = np.vectorize(lambda v: slot_transform("noise", v, cfg))(noise_z)
+            nz = transform_slots(np.zeros(noise_z.size, np.int8), noise_z.reshape(-1), cfg).reshape(noise_z.shape)
         return np.ascontiguousarray(th), np.ascontiguousarray(nz)
 
     def jacobian(self, z, th, noise_z, nz):
         """d theta / d z per slot [K, total] and d noise / d noise_z [K, P]."""
         cfg = self.m.config
-        jz = np.empty_like(z)
-        for j, nm in enumerate(self.names):
-            jz[:, j] = [slot_dtheta_dz(nm, a, b, cfg) for a, b in zip(z[:, j], th[:, j])]
+        jz = dtheta_dz_slots(self.codes_k, z.reshape(-1), th.reshape(-1), cfg).reshape(z.shape)
         if cfg.noise is not None:
             jn = np.zeros_like(noise_z)
         else:
-            jn = np.vectorize(lambda a, b: slot_dtheta_dz("noise", a, b, cfg))(noise_z, nz)
+            jn = dtheta_dz_slots(np.zeros(noise_z.size, np.int8), noise_z.reshape(-1), nz.reshape(-1), cfg).reshape(noise_z.shape)
         return jz, jn
 
     def log_prior(self, z, noise_z):
@@ -355,7 +353,34 @@ def _forecast_with_nowcasts(base_model: GPModel, nowcasts: Sequence[TData], fore
 
     def hmc(n_steps):
         """`n_steps` HMC steps on all K x P chains at once (mcmc_parameters! on every scenario's model copy,
-        forecasting.jl:148 and :65): each leapfrog stage is one `nagp_logml_grad` call."""
+        forecasting.jl:148 and :65), integrator on the device: one `nagp_hmc` call."""
+        nonlocal lm
+        from .engine import NagpError
+        L, eps = int(HMC_DEFAULT["n_leapfrog"]), float(HMC_DEFAULT["eps"])
+        if not HMC_DEFAULT.get("device", True):
+            return hmc_host(n_steps)
+        total = sp.z.shape[1]
+        mom, mnz, logu = np.empty((n_steps, K, total)), np.empty((n_steps, K, P)), np.empty((n_steps, K, P))
+        for it in range(n_steps):
+            mom[it] = rng.standard_normal((K, total))
+            if learn_noise:
+                mnz[it] = rng.standard_normal((K, P))
+            logu[it] = np.log(rng.uniform(size=(K, P)))
+        kind, sa, sb = device_slot_spec(sp.codes, m.config)
+        try:
+            sp.z, sp.noise_z, lml, _, _ = eng.hmc(
+                ens.prog, ens.prog_off, ens.theta_off, kind, sa, sb, device_noise_spec(m.config), sp.z, sp.noise_z,
+                t[:n + k], y1, y2=y2 if k else None, g=None if g is None else g[:n + k], step=step, n_leapfrog=L, eps=eps,
+                momenta=mom, noise_momenta=mnz if learn_noise else None, log_u=logu)
+        except NagpError as e:
+            if e.code != -4:
+                raise
+            return metropolis(n_steps)
+        lm = lml
+
+    def hmc_host(n_steps):
+        """The same chains with the integrator on the host: each leapfrog stage is one `nagp_logml_grad` call
+        (cross-check of `nagp_hmc`; `HMC_DEFAULT["device"] = False`)."""
         nonlocal lm
         from .engine import NagpError
         L, eps = int(HMC_DEFAULT["n_leapfrog"]), float(HMC_DEFAULT["eps"])

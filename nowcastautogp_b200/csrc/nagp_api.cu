@@ -539,24 +539,37 @@ void nagp_factor_free(nagp_factor *f)
 
 
 // ---- (f1) gradient of the log marginal likelihood: the HMC primitive --------------------------------------
-int32_t nagp_logml_grad(nagp_ctx *ctx, int64_t K, int64_t P, const uint8_t *prog, const int64_t *prog_off,
-                        const double *theta, const int64_t *theta_off, int64_t theta_stride_k,
-                        const double *noise, int64_t noise_stride_k, int64_t n, int64_t k, const double *t,
-                        const int32_t *g, double step, const double *y1, int64_t y1_stride, const double *y2,
-                        double *logml, double *grad_theta, double *grad_noise, int32_t *info)
+}  // extern "C"
+
+namespace {
+
+// Everything one "logML + gradient" evaluation launches, on device buffers that stay valid for the call:
+// the tile kernel (keeping the factor) followed by the gradient kernel. Built once, enqueued as often as needed
+// (once by nagp_logml_grad, once per leapfrog stage by nagp_hmc — also inside a CUDA-graph capture).
+struct GradJob {
+    FusedArgs a{};
+    V2Plan vpl{};
+    int vgrid = 0;
+    char *vscr = nullptr;
+    unsigned long long *vcounter = nullptr;
+    GradArgs ga{};
+    GradTilePlan gpl{};
+    int ggrid = 0;
+    char *gscr = nullptr;
+    unsigned long long *gcounter = nullptr;
+    size_t col_smem = 0;       // column-kernel fallback
+};
+
+// theta/noise/logml/grad_theta/grad_noise/info may be host or device; theta_dev etc. come back as device pointers.
+int32_t build_grad_job(nagp_ctx *ctx, int64_t K, int64_t P, const uint8_t *prog, const int64_t *prog_off,
+                       const double *theta, const int64_t *theta_off, int64_t theta_stride_k, const double *noise,
+                       int64_t noise_stride_k, int64_t n, int64_t k, const double *t, const int32_t *g, double step,
+                       const double *y1, int64_t y1_stride, const double *y2, double *logml, double *grad_theta,
+                       double *grad_noise, int32_t *info, GradJob *job)
 {
-    if (!ctx) return NAGP_E_ARG;
-    if (K <= 0 || P <= 0 || !prog || !prog_off || !theta || !theta_off || !noise || !t || !y1 || !logml ||
-        !grad_theta || !grad_noise || !info || (k > 0 && !y2) || n <= 0 || k < 0 || (y1_stride != 0 && y1_stride < n))
-        return fail(ctx, NAGP_E_ARG, "nagp_logml_grad: null or empty argument");
-    if (n + k > fused_v2_max_q()) return fail(ctx, NAGP_E_SIZE, "nagp_logml_grad: n + k > 232 not supported yet");
-    if (on_device(prog_off) || on_device(theta_off))
-        return fail(ctx, NAGP_E_ARG, "prog_off/theta_off must be host arrays");
-    NAGP_CUDA(ctx, cudaSetDevice(ctx->device));
-    NAGP_TRY(arena_reset(ctx));
     const int64_t m = n + k, B = K * P, ntheta = theta_off[P];
     const int nt = (int)((m + 7) / 8);
-    FusedArgs a{};
+    FusedArgs &a = job->a;
     NAGP_TRY(grid_extent(ctx, g, m, &a.G));
     NAGP_TRY(plan_tables(ctx, P, prog, prog_off, theta_off, (int)m, a.G, &a.ntab_cap, &a.ncp_cap));
     a.B = B; a.P = P;
@@ -583,7 +596,7 @@ int32_t nagp_logml_grad(nagp_ctx *ctx, int64_t K, int64_t P, const uint8_t *prog
     NAGP_TRY(scratch(ctx, (size_t)B * (size_t)(nt * (nt + 1) / 2) * 64, &a.Lkeep));
     NAGP_TRY(scratch(ctx, (size_t)B * nt * 8, &a.zkeep));
     // tile version of the gradient kernel: needs a strictly increasing lag grid (one point per grid index) or
-    // pairwise times, one lag per thread, and the factor resident in shared memory
+    // pairwise times, and the factor resident in shared memory
     bool increasing = true;
     if (g) {
         std::vector<int32_t> gh((size_t)m);
@@ -595,42 +608,194 @@ int32_t nagp_logml_grad(nagp_ctx *ctx, int64_t K, int64_t P, const uint8_t *prog
         }
         for (int64_t i = 1; i < m; ++i) increasing = increasing && gh[i] > gh[i - 1];
     }
-    GradTilePlan gpl{};
     if (increasing && ctx->variant != 1)
-        gpl = plan_grad_tile((int)m, a.G, a.ntab_cap, a.ncp_cap, ctx->smem_optin, ctx->smem_per_sm);
-    if (gpl.ok) NAGP_TRY(scratch(ctx, (size_t)B * nt * 64, &a.Wkeep));
-    const int saved_variant = ctx->variant;
-    ctx->variant = 2;                                   // the tile kernel is the one that keeps the factor
-    const int32_t rc = run_fused(ctx, a, theta_off);
-    ctx->variant = saved_variant;
-    NAGP_TRY(rc);
+        job->gpl = plan_grad_tile((int)m, a.G, a.ntab_cap, a.ncp_cap, ctx->smem_optin, ctx->smem_per_sm);
+    if (job->gpl.ok) NAGP_TRY(scratch(ctx, (size_t)B * nt * 64, &a.Wkeep));
+    // the tile kernel is the one that keeps the factor
+    int64_t nth = 1;
+    for (int64_t p = 0; p < P; ++p) nth = std::max(nth, theta_off[p + 1] - theta_off[p]);
+    job->vpl = plan_fused_v2((int)m, a.G, (int)std::min<int64_t>(nth, MAX_THETA), a.ntab_cap, a.ncp_cap, ctx->smem_optin,
+                             ctx->smem_per_sm);
+    if (!job->vpl.ok) return fail(ctx, NAGP_E_SIZE, "nagp_logml_grad: problem too large for the tile kernel");
+    if ((int64_t)ctx->compiled.size() == P)
+        NAGP_TRY(stage_in(ctx, ctx->compiled.data(), ctx->compiled.size(), &a.compiled));
+    job->vgrid = fused_v2_grid(job->vpl, B, ctx->num_sms);
+    if (job->vpl.scratch_stride) NAGP_TRY(scratch(ctx, (size_t)job->vgrid * job->vpl.scratch_stride, &job->vscr));
+    NAGP_TRY(scratch(ctx, 1, &job->vcounter));
 
-    GradArgs ga{};
+    GradArgs &ga = job->ga;
     ga.B = B; ga.P = P; ga.prog = a.prog; ga.prog_off = a.prog_off; ga.theta = a.theta; ga.theta_off = a.theta_off;
     ga.theta_stride_k = theta_stride_k; ga.n = (int)m; ga.t = a.t; ga.g = a.g; ga.step = step;
     ga.L = a.Lkeep; ga.z = a.zkeep; ga.info = d_info;
     NAGP_TRY(stage_out(ctx, grad_theta, (size_t)(K * ntheta), &ga.grad_theta));
     NAGP_TRY(stage_out(ctx, grad_noise, (size_t)B, &ga.grad_noise));
-    if (gpl.ok) {
+    if (job->gpl.ok) {
         ga.Winv = a.Wkeep; ga.G = a.G; ga.ntab_cap = a.ntab_cap; ga.ncp_cap = a.ncp_cap;
-        if ((int64_t)ctx->compiled.size() == P) NAGP_TRY(stage_in(ctx, ctx->compiled.data(), ctx->compiled.size(), &ga.compiled));
-        const int grid = grad_tile_grid(gpl, B, ctx->num_sms);
+        ga.compiled = a.compiled;
+        job->ggrid = grad_tile_grid(job->gpl, B, ctx->num_sms);
         if (getenv("NAGP_DEBUG"))
-            fprintf(stderr, "[nagp] grad tile kernel: n=%d G=%d Gd=%d nsec=%d smem=%zu B region=%d scratch/CTA=%d grid=%d\n",
-                    (int)m, a.G, gpl.Gd, gpl.nsec, gpl.smem_bytes, gpl.region_bytes, gpl.scratch_stride, grid);
-        char *scr = nullptr;
-        NAGP_TRY(scratch(ctx, (size_t)grid * gpl.scratch_stride, &scr));
-        unsigned long long *counter = nullptr;
-        NAGP_TRY(scratch(ctx, 1, &counter));
-        NAGP_CUDA(ctx, launch_grad_tile(ga, gpl, scr, counter, grid, ctx->stream));
+            fprintf(stderr, "[nagp] grad tile kernel: n=%d G=%d Gd=%d smem=%zu B region=%d scratch/CTA=%d grid=%d\n",
+                    (int)m, a.G, job->gpl.Gd, job->gpl.smem_bytes, job->gpl.region_bytes, job->gpl.scratch_stride, job->ggrid);
+        NAGP_TRY(scratch(ctx, (size_t)job->ggrid * job->gpl.scratch_stride, &job->gscr));
+        NAGP_TRY(scratch(ctx, 1, &job->gcounter));
     } else {
         bool s_in_smem = true;
-        const size_t smem = grad_smem_bytes((int)m, ctx->smem_optin, &s_in_smem);
-        const int grid = (int)std::min<int64_t>(B, ctx->num_sms);
-        if (!s_in_smem) NAGP_TRY(scratch(ctx, (size_t)grid * m * m, &ga.S));
-        NAGP_CUDA(ctx, launch_grad(ga, grid, smem, ctx->stream));
+        job->col_smem = grad_smem_bytes((int)m, ctx->smem_optin, &s_in_smem);
+        job->ggrid = (int)std::min<int64_t>(B, ctx->num_sms);
+        if (!s_in_smem) NAGP_TRY(scratch(ctx, (size_t)job->ggrid * m * m, &ga.S));
     }
-    ctx->launches += 1;
+    return NAGP_OK;
+}
+
+int32_t enqueue_grad_job(nagp_ctx *ctx, const GradJob &job)
+{
+    NAGP_CUDA(ctx, launch_fused_v2(job.a, job.vpl, job.vscr, job.vcounter, job.vgrid, ctx->stream));
+    if (job.gpl.ok) NAGP_CUDA(ctx, launch_grad_tile(job.ga, job.gpl, job.gscr, job.gcounter, job.ggrid, ctx->stream));
+    else NAGP_CUDA(ctx, launch_grad(job.ga, job.ggrid, job.col_smem, ctx->stream));
+    ctx->launches += 2;
+    return NAGP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t nagp_logml_grad(nagp_ctx *ctx, int64_t K, int64_t P, const uint8_t *prog, const int64_t *prog_off,
+                        const double *theta, const int64_t *theta_off, int64_t theta_stride_k,
+                        const double *noise, int64_t noise_stride_k, int64_t n, int64_t k, const double *t,
+                        const int32_t *g, double step, const double *y1, int64_t y1_stride, const double *y2,
+                        double *logml, double *grad_theta, double *grad_noise, int32_t *info)
+{
+    if (!ctx) return NAGP_E_ARG;
+    if (K <= 0 || P <= 0 || !prog || !prog_off || !theta || !theta_off || !noise || !t || !y1 || !logml ||
+        !grad_theta || !grad_noise || !info || (k > 0 && !y2) || n <= 0 || k < 0 || (y1_stride != 0 && y1_stride < n))
+        return fail(ctx, NAGP_E_ARG, "nagp_logml_grad: null or empty argument");
+    if (n + k > fused_v2_max_q()) return fail(ctx, NAGP_E_SIZE, "nagp_logml_grad: n + k > 232 not supported yet");
+    if (on_device(prog_off) || on_device(theta_off))
+        return fail(ctx, NAGP_E_ARG, "prog_off/theta_off must be host arrays");
+    NAGP_CUDA(ctx, cudaSetDevice(ctx->device));
+    NAGP_TRY(arena_reset(ctx));
+    GradJob job;
+    NAGP_TRY(build_grad_job(ctx, K, P, prog, prog_off, theta, theta_off, theta_stride_k, noise, noise_stride_k, n, k, t, g,
+                            step, y1, y1_stride, y2, logml, grad_theta, grad_noise, info, &job));
+    NAGP_TRY(enqueue_grad_job(ctx, job));
+    NAGP_TRY(finish(ctx));
+    return on_device(info) ? NAGP_OK : worst_info(info, K * P);
+}
+
+// ---- (f1) HMC on the hyperparameters, leapfrog on the device ---------------------------------------------------
+int32_t nagp_hmc(nagp_ctx *ctx, int64_t K, int64_t P, const uint8_t *prog, const int64_t *prog_off,
+                 const int64_t *theta_off, const int32_t *slot_kind, const double *slot_a, const double *slot_b,
+                 int32_t noise_kind, double noise_a, double noise_b, double *z, double *noise_z,
+                 int64_t n, int64_t k, const double *t, const int32_t *g, double step,
+                 const double *y1, int64_t y1_stride, const double *y2,
+                 int64_t n_steps, int64_t n_leapfrog, double eps,
+                 const double *momenta, const double *noise_momenta, const double *log_u,
+                 double *logml, int32_t *n_accept, int32_t *info)
+{
+    if (!ctx) return NAGP_E_ARG;
+    const bool learn_noise = noise_kind != 5;
+    if (K <= 0 || P <= 0 || !prog || !prog_off || !theta_off || !slot_kind || !slot_a || !slot_b || !z || !noise_z ||
+        !t || !y1 || (k > 0 && !y2) || n <= 0 || k < 0 || n_steps < 0 || n_leapfrog <= 0 || !(eps > 0.0) ||
+        (n_steps > 0 && (!momenta || !log_u || (learn_noise && !noise_momenta))) || !logml || !n_accept || !info ||
+        (y1_stride != 0 && y1_stride < n))
+        return fail(ctx, NAGP_E_ARG, "nagp_hmc: null or empty argument");
+    if (n + k > fused_v2_max_q()) return fail(ctx, NAGP_E_SIZE, "nagp_hmc: n + k > 232 not supported yet");
+    if (on_device(prog_off) || on_device(theta_off) || on_device(z) || on_device(noise_z))
+        return fail(ctx, NAGP_E_ARG, "nagp_hmc: prog_off/theta_off/z/noise_z must be host arrays");
+    NAGP_CUDA(ctx, cudaSetDevice(ctx->device));
+    NAGP_TRY(arena_reset(ctx));
+    const int64_t total = theta_off[P], B = K * P;
+    HmcArgs h{};
+    h.K = K; h.P = P; h.total = total; h.L = (int)n_leapfrog; h.eps = eps;
+    h.noise_kind = noise_kind; h.noise_a = noise_a; h.noise_b = noise_b;
+    NAGP_TRY(stage_in(ctx, slot_kind, (size_t)total, &h.slot_kind));
+    NAGP_TRY(stage_in(ctx, slot_a, (size_t)total, &h.slot_a));
+    NAGP_TRY(stage_in(ctx, slot_b, (size_t)total, &h.slot_b));
+    NAGP_TRY(stage_in(ctx, momenta, (size_t)(n_steps * K * total), &h.momenta));
+    NAGP_TRY(stage_in(ctx, noise_momenta, (size_t)(learn_noise ? n_steps * B : 0), &h.noise_momenta));
+    NAGP_TRY(stage_in(ctx, log_u, (size_t)(n_steps * B), &h.log_u));
+    // chain state on the device; z / noise_z are copied in here and copied back at the end
+    const double *z_in = nullptr, *nz_in = nullptr;
+    NAGP_TRY(stage_in(ctx, (const double *)z, (size_t)(K * total), &z_in));
+    NAGP_TRY(stage_in(ctx, (const double *)noise_z, (size_t)B, &nz_in));
+    h.Z = const_cast<double *>(z_in); h.NZ = const_cast<double *>(nz_in);
+    ctx->outs.push_back({z, h.Z, (size_t)(K * total) * sizeof(double)});
+    ctx->outs.push_back({noise_z, h.NZ, (size_t)B * sizeof(double)});
+    NAGP_TRY(scratch(ctx, (size_t)(K * total), &h.Zq));
+    NAGP_TRY(scratch(ctx, (size_t)B, &h.NZq));
+    NAGP_TRY(scratch(ctx, (size_t)(K * total), &h.mom));
+    NAGP_TRY(scratch(ctx, (size_t)B, &h.mnz));
+    NAGP_TRY(scratch(ctx, (size_t)(K * total), &h.gZ));
+    NAGP_TRY(scratch(ctx, (size_t)B, &h.gNZ));
+    NAGP_TRY(scratch(ctx, (size_t)(K * total), &h.gq));
+    NAGP_TRY(scratch(ctx, (size_t)B, &h.gnq));
+    NAGP_TRY(scratch(ctx, (size_t)B, &h.lp));
+    NAGP_TRY(scratch(ctx, (size_t)(K * total), &h.theta));
+    NAGP_TRY(scratch(ctx, (size_t)B, &h.noise));
+    NAGP_TRY(scratch(ctx, (size_t)B, &h.logml_q));
+    NAGP_TRY(scratch(ctx, (size_t)(K * total), &h.grad_theta));
+    NAGP_TRY(scratch(ctx, (size_t)B, &h.grad_noise));
+    NAGP_TRY(scratch(ctx, (size_t)B, &h.info_q));
+    NAGP_TRY(scratch(ctx, 1, &h.iter));
+    NAGP_TRY(stage_out(ctx, logml, (size_t)B, &h.logml_cur));
+    NAGP_TRY(stage_out(ctx, n_accept, (size_t)B, &h.n_accept));
+    NAGP_TRY(stage_out(ctx, info, (size_t)B, &h.info_cur));
+
+    GradJob job;
+    NAGP_TRY(build_grad_job(ctx, K, P, prog, prog_off, h.theta, theta_off, total, h.noise, P, n, k, t, g, step, y1,
+                            y1_stride, y2, h.logml_q, h.grad_theta, h.grad_noise, h.info_q, &job));
+    h.theta_off = job.a.theta_off;
+
+    // initial state: log posterior and gradient at (Z, NZ)
+    NAGP_CUDA(ctx, launch_hmc_stage(h, HMC_INIT, ctx->num_sms, ctx->stream));
+    NAGP_TRY(enqueue_grad_job(ctx, job));
+    NAGP_CUDA(ctx, launch_hmc_stage(h, HMC_INIT_DONE, ctx->num_sms, ctx->stream));
+    ctx->launches += 2;
+
+    // one HMC iteration = begin, L x (half kick + drift + transform, logML + gradient, half kick), accept.
+    // Every kernel reads the iteration counter from device memory, so the sequence is identical each time:
+    // captured once into a CUDA graph and replayed n_steps times (no host round trip inside the chain).
+    auto enqueue_iteration = [&]() -> int32_t {
+        NAGP_CUDA(ctx, launch_hmc_stage(h, HMC_BEGIN, ctx->num_sms, ctx->stream));
+        for (int l = 0; l < h.L; ++l) {
+            NAGP_CUDA(ctx, launch_hmc_stage(h, HMC_LEAP_PRE, ctx->num_sms, ctx->stream));
+            NAGP_TRY(enqueue_grad_job(ctx, job));
+            NAGP_CUDA(ctx, launch_hmc_stage(h, HMC_LEAP_POST, ctx->num_sms, ctx->stream));
+        }
+        NAGP_CUDA(ctx, launch_hmc_stage(h, HMC_ACCEPT, ctx->num_sms, ctx->stream));
+        ctx->launches += 2 + 2 * h.L;
+        return NAGP_OK;
+    };
+    bool graphed = false;
+    if (n_steps > 1 && !getenv("NAGP_NO_GRAPH")) {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        const int64_t launches_before = ctx->launches;
+        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+            const int32_t rc = enqueue_iteration();
+            const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+            if (rc == NAGP_OK && e == cudaSuccess && graph &&
+                cudaGraphInstantiate(&exec, graph, nullptr, nullptr, 0) == cudaSuccess) {
+                graphed = true;
+                for (int64_t it = 0; it < n_steps && graphed; ++it)
+                    if (cudaGraphLaunch(exec, ctx->stream) != cudaSuccess) graphed = false;
+                ctx->launches = launches_before + (int64_t)(2 + 4 * h.L) * n_steps;
+            }
+            if (exec) {
+                cudaStreamSynchronize(ctx->stream);
+                cudaGraphExecDestroy(exec);
+            }
+            if (graph) cudaGraphDestroy(graph);
+        }
+        if (!graphed) {
+            cudaGetLastError();
+            ctx->launches = launches_before;
+            return fail(ctx, NAGP_E_CUDA, "nagp_hmc: CUDA graph capture of the HMC iteration failed (set NAGP_NO_GRAPH=1 to run it as plain stream launches)");
+        }
+    }
+    if (!graphed)
+        for (int64_t it = 0; it < n_steps; ++it) NAGP_TRY(enqueue_iteration());
     NAGP_TRY(finish(ctx));
     return on_device(info) ? NAGP_OK : worst_info(info, B);
 }

@@ -156,6 +156,29 @@ struct DrawArgs {
 };
 cudaError_t launch_draw(const DrawArgs &a, cudaStream_t stream);
 
+// HMC on the unconstrained hyperparameters with the leapfrog integrator on the device.
+// Chains: K scenarios x P particles; slot vectors are [K, total] (total = theta_off[P]), per-chain scalars [K, P].
+enum HmcStage : int { HMC_INIT = 0, HMC_INIT_DONE = 1, HMC_BEGIN = 2, HMC_LEAP_PRE = 3, HMC_LEAP_POST = 4, HMC_ACCEPT = 5 };
+struct HmcArgs {
+    int64_t K, P, total;
+    int L;
+    double eps;
+    const int64_t *theta_off;                 // [P+1] device
+    const int32_t *slot_kind;                 // [total]: 0 exp(a + b z), 2 2*logistic(a + b z), 3 z, 4 Phi(z), 5 constant a
+    const double *slot_a, *slot_b;            // [total]
+    int32_t noise_kind; double noise_a, noise_b;
+    const double *momenta, *noise_momenta, *log_u;      // [n_steps, K, total], [n_steps, K, P], [n_steps, K, P]
+    double *Z, *NZ;                           // current state
+    double *Zq, *NZq, *mom, *mnz;             // trajectory
+    double *gZ, *gNZ, *gq, *gnq;              // z-space gradients of the log posterior (current, trajectory)
+    double *lp;                               // current log posterior
+    double *theta, *noise;                    // constrained parameters the likelihood kernels read
+    double *logml_q, *grad_theta, *grad_noise; int32_t *info_q;     // what they write
+    double *logml_cur; int32_t *n_accept, *info_cur;                // outputs
+    int32_t *iter;                            // iteration counter (device), read by every stage
+};
+cudaError_t launch_hmc_stage(const HmcArgs &h, int stage, int num_sms, cudaStream_t stream);
+
 // Forecast summary: elementwise inverse transformation (x [h,N] column-major -> out same layout and/or
 // rows [h][N]) and per-row type-7 quantiles by radix select.
 cudaError_t launch_inverse_transform(int kind, double lam, double offset, double max_value, int64_t h, int64_t N,

@@ -165,6 +165,32 @@ class Engine:
         self._check(rc, raise_posdef=check)
         return logml, gth, gnz, info
 
+    def hmc(self, prog, prog_off, theta_off, slot_kind, slot_a, slot_b, noise_spec, z, noise_z, t, y1, y2=None,
+            g=None, step: float = 0.0, y_stride: int = 0, n_leapfrog: int = 10, eps: float = 0.02, momenta=None,
+            noise_momenta=None, log_u=None):
+        """`nagp_hmc`: K x P chains, `len(log_u)` iterations, integrator on the device. z [K,total] and noise_z
+        [K,P] are updated in place. Returns (logml [K,P], n_accept [K,P], info [K,P])."""
+        z = np.ascontiguousarray(z, np.float64)
+        noise_z = np.ascontiguousarray(noise_z, np.float64)
+        K, P = noise_z.shape
+        n = int(y_stride) if y_stride else len(y1)
+        k = 0 if y2 is None else int(np.shape(y2)[-1])
+        n_steps = 0 if log_u is None else len(log_u)
+        logml, nacc, info = np.empty((K, P)), np.zeros((K, P), np.int32), np.zeros((K, P), np.int32)
+        nk, na, nb = noise_spec
+        keep = [_ptr(np.ascontiguousarray(prog, np.uint8)), _ptr(np.ascontiguousarray(prog_off, np.int64)),
+                _ptr(np.ascontiguousarray(theta_off, np.int64)), _ptr(np.ascontiguousarray(slot_kind, np.int32)),
+                _ptr(np.ascontiguousarray(slot_a, np.float64)), _ptr(np.ascontiguousarray(slot_b, np.float64)),
+                _ptr(z), _ptr(noise_z), _ptr(t, np.float64), _ptr(g, np.int32), _ptr(y1, np.float64),
+                _ptr(y2, np.float64), _ptr(momenta, np.float64), _ptr(noise_momenta, np.float64),
+                _ptr(log_u, np.float64), _ptr(logml), _ptr(nacc), _ptr(info)]
+        p = [x[0] for x in keep]
+        rc = self._lib.nagp_hmc(self._ctx, K, P, p[0], p[1], p[2], p[3], p[4], p[5], int(nk), float(na), float(nb),
+                                p[6], p[7], n, k, p[8], p[9], step, p[10], int(y_stride), p[11], n_steps,
+                                int(n_leapfrog), float(eps), p[12], p[13], p[14], p[15], p[16], p[17])
+        self._check(rc, raise_posdef=False)
+        return z, noise_z, logml, nacc, info
+
     # ---- (a3)/(a4)/(a7) ----------------------------------------------------------------------------
     def factor_store(self, ens: FlatEnsemble, n, k, h, t, y1, logw0=None, ya=1.0, yb=0.0, g=None, step=0.0,
                      noise_pred=-1.0, check: bool = True) -> "Factor":

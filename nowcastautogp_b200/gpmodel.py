@@ -201,6 +201,29 @@ def dtheta_dz_slots(codes: np.ndarray, z: np.ndarray, theta: np.ndarray, config:
     return out
 
 
+def device_slot_spec(codes: np.ndarray, config: GPConfig):
+    """The z -> theta map of every slot in the form `nagp_hmc` takes: (kind int32, a, b) per slot."""
+    pr = config.prior
+    kind = np.zeros(len(codes), np.int32)
+    a = np.full(len(codes), float(pr["wildcard"]["mu"]))
+    b = np.full(len(codes), float(pr["wildcard"]["sigma"]))
+    m = codes == 1
+    a[m], b[m] = pr["period"]["mu"], pr["period"]["sigma"]
+    m = codes == 2
+    kind[m], a[m], b[m] = 2, pr["gamma"]["mu"], pr["gamma"]["sigma"]
+    kind[codes == 3] = 3
+    kind[codes == 4] = 4
+    m = codes == 5
+    kind[m], a[m] = 5, float(config.cp_scale)
+    return kind, a, b
+
+
+def device_noise_spec(config: GPConfig):
+    if config.noise is not None:
+        return 5, float(config.noise), 0.0
+    return 0, float(config.prior["wildcard"]["mu"]), float(config.prior["wildcard"]["sigma"])
+
+
 HMC_DEFAULT = {"n_leapfrog": 10, "eps": 0.02}     # Gen.hmc's L = 10 [R]; step sized for N(0,1)-scaled z
 
 
@@ -515,10 +538,49 @@ class GPModel:
     def mcmc_parameters(self, n_hmc: int, hmc_config: Optional[dict] = None) -> float:
         """`AutoGP.mcmc_parameters!(model, n_hmc)` (`src/forecasting.jl:148,65`): `n_hmc` Hamiltonian Monte
         Carlo steps on the unconstrained hyperparameters of every particle (N(0,1) prior on z [R]), all
-        particles advanced together: each leapfrog stage is ONE device call giving every particle's log
-        marginal likelihood and its gradient (`nagp_logml_grad`); the integrator runs over the concatenated
-        slot vectors of all particles. Beyond the gradient kernel's size limit the move degrades to
-        random-walk Metropolis on the same target. Returns the acceptance rate."""
+        particles advanced together in ONE device call (`nagp_hmc`): the leapfrog integrator, the z -> theta
+        maps and the accept/reject step run on the device, the host only supplies the momenta and the uniforms
+        (drawn in the order the host integrator `_mcmc_parameters_host` draws them, so both walk the same
+        chain). Beyond the gradient kernel's size limit the move degrades to random-walk Metropolis on the same
+        target. Returns the acceptance rate."""
+        from .engine import NagpError
+        hc = dict(HMC_DEFAULT, **(hmc_config or getattr(self, "_hmc_config", None) or {}))
+        if not hc.get("device", True):
+            return self._mcmc_parameters_host(n_hmc, hmc_config)
+        idx = self._obs_idx()
+        P = len(self.particles)
+        if len(idx) == 0 or n_hmc <= 0:
+            return 0.0
+        cfg = self.config
+        learn_noise = cfg.noise is None
+        flat = _FlatChains(self.particles, cfg)
+        t, g, step, y = self._grid_of(idx)
+        total = len(flat.Z)
+        mom, mnz, logu = np.empty((n_hmc, total)), np.empty((n_hmc, P)), np.empty((n_hmc, P))
+        for it in range(n_hmc):
+            mom[it] = self.rng.standard_normal(total)
+            if learn_noise:
+                mnz[it] = self.rng.standard_normal(P)
+            logu[it] = np.log(self.rng.uniform(size=P))
+        kind, sa, sb = device_slot_spec(flat.codes, cfg)
+        try:
+            Z, NZ, lm, nacc, info = self._engine().hmc(
+                flat.prog, flat.prog_off, flat.off, kind, sa, sb, device_noise_spec(cfg), flat.Z[None, :].copy(),
+                flat.NZ[None, :].copy(), t, y, g=g, step=step, n_leapfrog=int(hc["n_leapfrog"]), eps=float(hc["eps"]),
+                momenta=mom, noise_momenta=mnz if learn_noise else None, log_u=logu)
+        except NagpError as e:
+            if e.code != -4:
+                raise
+            return self._metropolis_parameters(n_hmc)
+        Z, NZ, lm, nacc = Z[0], NZ[0], lm[0], nacc[0]
+        for i in np.nonzero(nacc > 0)[0]:
+            self.particles[i] = Particle(self.particles[i].prog, Z[flat.off[i]:flat.off[i + 1]].copy(), float(NZ[i]))
+            self._logml[i] = lm[i]
+        return float(nacc.sum()) / max(1, n_hmc * P)
+
+    def _mcmc_parameters_host(self, n_hmc: int, hmc_config: Optional[dict] = None) -> float:
+        """The same move with the integrator on the host: each leapfrog stage is one `nagp_logml_grad` call.
+        Kept as the cross-check of `nagp_hmc` (`hmc_config={"device": False}`)."""
         from .engine import NagpError
         hc = dict(HMC_DEFAULT, **(hmc_config or getattr(self, "_hmc_config", None) or {}))
         L, eps = int(hc["n_leapfrog"]), float(hc["eps"])

@@ -135,3 +135,57 @@ def test_hmc_parameter_move(engine):
     assert np.isfinite(after).all() and np.allclose(after, m._logml, rtol=1e-9, atol=1e-9)
     prior = lambda ps: np.array([-0.5 * (p.z @ p.z + p.noise_z ** 2) for p in ps])
     assert np.median(after) > np.median(before)          # prior draws are far from the posterior mode
+
+
+def test_device_hmc_walks_the_host_chain(engine):
+    """`nagp_hmc` (leapfrog, z -> theta maps and accept/reject on the device, the iteration replayed as a CUDA
+    graph) against the host integrator calling `nagp_logml_grad` per stage, fed the same momenta and uniforms:
+    same accept decisions, same final states to 1e-8 (the two differ only in libm ulps of the z -> theta maps)."""
+    import nowcastautogp_b200 as ng
+    rng = np.random.default_rng(11)
+    dates = np.arange(np.datetime64("2024-01-01"), np.datetime64("2024-03-15"))
+    vals = 10 + 2 * np.sin(np.arange(len(dates)) / 5.0) + 0.1 * rng.standard_normal(len(dates))
+    for cfg in (ng.GPConfig(), ng.GPConfig(noise=0.05)):
+        base = ng.GPModel(dates, vals, n_particles=7, config=cfg, rng=np.random.default_rng(5), engine=engine)
+        base.n_obs = len(vals)
+        base._logml = base.logml(base.particles, base._obs_idx())
+        d = base.to_dict()
+        out = []
+        for device in (True, False):
+            m = ng.GPModel.from_dict(d, engine=engine, rng=np.random.default_rng(99))
+            rate = m.mcmc_parameters(6, {"device": device, "eps": 0.03})
+            out.append((rate, m))
+        (r_dev, m_dev), (r_host, m_host) = out
+        assert r_dev == r_host and r_dev > 0.2
+        for a, b in zip(m_dev.particles, m_host.particles):
+            assert a.prog == b.prog
+            np.testing.assert_allclose(a.z, b.z, rtol=1e-8, atol=1e-8)
+            assert abs(a.noise_z - b.noise_z) < 1e-8
+        np.testing.assert_allclose(m_dev._logml, m_host._logml, rtol=1e-8)
+        again = m_dev.logml(m_dev.particles, m_dev._obs_idx())
+        np.testing.assert_allclose(again, m_dev._logml, rtol=1e-9)
+
+
+def test_per_scenario_device_hmc_in_forecast_with_nowcasts(engine):
+    """forecast_with_nowcasts(n_hmc > 0): K x P chains in one nagp_hmc call; same draws as the host integrator."""
+    import nowcastautogp_b200 as ng
+    from nowcastautogp_b200 import api
+    rng = np.random.default_rng(3)
+    dates = np.arange(np.datetime64("2024-01-01"), np.datetime64("2024-02-20"))
+    vals = 30 + 4 * np.sin(np.arange(len(dates)) / 6.0) + 0.3 * rng.standard_normal(len(dates))
+    data = ng.TData(dates, vals, transformation=lambda v: v)
+    model = ng.make_and_fit_model(data, n_particles=4, smc_data_proportion=0.5, n_mcmc=2, n_hmc=1,
+                                  rng=np.random.default_rng(1), engine=engine)
+    nds = dates[-1] + np.arange(1, 3)
+    nowcasts = ng.create_nowcast_data([[vals[-1] * 1.01, vals[-1] * 1.02], [vals[-1] * 0.97, vals[-1] * 0.99],
+                                       [vals[-1], vals[-1] * 1.05]], list(nds))
+    fdates = nds[-1] + np.arange(1, 5)
+    xs = []
+    for device in (True, False):
+        api.HMC_DEFAULT["device"] = device
+        try:
+            xs.append(ng.forecast_with_nowcasts(model, nowcasts, fdates, 6, n_hmc=3, rng=np.random.default_rng(8)))
+        finally:
+            api.HMC_DEFAULT.pop("device", None)
+    assert xs[0].shape == (4, 18) and np.isfinite(xs[0]).all()
+    np.testing.assert_allclose(xs[0], xs[1], rtol=1e-6, atol=1e-6)
