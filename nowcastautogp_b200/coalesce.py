@@ -36,12 +36,14 @@ def concat_ensembles(parts: List[FlatEnsemble]) -> FlatEnsemble:
 
 
 class _Request:
-    __slots__ = ("kind", "key", "ens", "t", "g", "step", "y", "result", "error")
+    __slots__ = ("kind", "key", "ens", "t", "g", "step", "y", "extra", "result", "error")
 
-    def __init__(self, kind, ens, t, g, step, y):
+    def __init__(self, kind, ens, t, g, step, y, extra=None, extra_key=()):
         self.kind, self.ens, self.t, self.g, self.step = kind, ens, np.asarray(t, np.float64), g, float(step)
         self.y = np.asarray(y, np.float64)
-        self.key = (kind, len(self.t), self.t.tobytes(), None if g is None else np.asarray(g, np.int32).tobytes(), self.step)
+        self.extra = extra
+        self.key = (kind, len(self.t), self.t.tobytes(), None if g is None else np.asarray(g, np.int32).tobytes(),
+                    self.step) + tuple(extra_key)
         self.result = None
         self.error = None
 
@@ -110,13 +112,28 @@ class CoalescingEngine:
             o = 0
             for r, sz in zip(reqs, sizes):
                 r.result = (lm[o:o + sz].copy(), info[o:o + sz].copy()); o += sz
-        else:
+        elif r0.kind == "grad":
             lm, gth, gnz, info = self.engine.logml_grad(ens, r0.t, y, g=r0.g, step=r0.step, y_stride=n)
             o = to = 0
             for r, sz in zip(reqs, sizes):
                 nth = int(r.ens.theta_off[-1])
                 r.result = (lm[:, o:o + sz].copy(), gth[:, to:to + nth].copy(), gnz[:, o:o + sz].copy(),
                             info[:, o:o + sz].copy())
+                o += sz; to += nth
+        else:   # "hmc": the chains of every series side by side (K = 1), momenta / uniforms concatenated per iteration
+            x0 = r0.extra
+            cat = lambda name, axis: np.concatenate([r.extra[name] for r in reqs], axis=axis)
+            learn = x0["noise_momenta"] is not None
+            Z, NZ, lm, nacc, info = self.engine.hmc(
+                ens.prog, ens.prog_off, ens.theta_off, cat("kind", 0), cat("a", 0), cat("b", 0), x0["noise_spec"],
+                cat("z", 1), cat("noise_z", 1), r0.t, y, g=r0.g, step=r0.step, y_stride=n, n_leapfrog=x0["n_leapfrog"],
+                eps=x0["eps"], momenta=cat("momenta", 1), noise_momenta=cat("noise_momenta", 1) if learn else None,
+                log_u=cat("log_u", 1))
+            o = to = 0
+            for r, sz in zip(reqs, sizes):
+                nth = int(r.ens.theta_off[-1])
+                r.result = (Z[:, to:to + nth].copy(), NZ[:, o:o + sz].copy(), lm[:, o:o + sz].copy(),
+                            nacc[:, o:o + sz].copy(), info[:, o:o + sz].copy())
                 o += sz; to += nth
 
     def _forward(self, name, *args, **kwargs):
@@ -138,6 +155,25 @@ class _Client:
         if y2 is not None or theta is not None or noise is not None:      # per-scenario chains: not a fit-time call
             return self._hub._forward("logml_grad", ens, t, y1, y2=y2, g=g, step=step, theta=theta, noise=noise, **kw)
         return self._hub._submit(self._cid, _Request("grad", ens, t, g, step, y1))
+
+    def hmc(self, prog, prog_off, theta_off, slot_kind, slot_a, slot_b, noise_spec, z, noise_z, t, y1, y2=None, g=None,
+            step: float = 0.0, y_stride: int = 0, n_leapfrog: int = 10, eps: float = 0.02, momenta=None,
+            noise_momenta=None, log_u=None):
+        z, noise_z = np.asarray(z, np.float64), np.asarray(noise_z, np.float64)
+        if y2 is not None or y_stride or z.shape[0] != 1 or log_u is None:       # per-scenario chains: not a fit-time call
+            return self._hub._forward("hmc", prog, prog_off, theta_off, slot_kind, slot_a, slot_b, noise_spec, z, noise_z, t,
+                                      y1, y2=y2, g=g, step=step, y_stride=y_stride, n_leapfrog=n_leapfrog, eps=eps,
+                                      momenta=momenta, noise_momenta=noise_momenta, log_u=log_u)
+        P = noise_z.shape[1]
+        ens = FlatEnsemble(np.asarray(prog, np.uint8), np.asarray(prog_off, np.int64), np.zeros(int(theta_off[-1])),
+                           np.asarray(theta_off, np.int64), np.zeros(P))
+        extra = dict(kind=np.asarray(slot_kind, np.int32), a=np.asarray(slot_a, np.float64), b=np.asarray(slot_b, np.float64),
+                     noise_spec=tuple(noise_spec), z=z, noise_z=noise_z, n_leapfrog=int(n_leapfrog), eps=float(eps),
+                     momenta=np.asarray(momenta, np.float64),
+                     noise_momenta=None if noise_momenta is None else np.asarray(noise_momenta, np.float64),
+                     log_u=np.asarray(log_u, np.float64))
+        key = (len(log_u), int(n_leapfrog), float(eps), tuple(noise_spec), noise_momenta is None)
+        return self._hub._submit(self._cid, _Request("hmc", ens, t, g, step, y1, extra, key))
 
     def __getattr__(self, name):
         hub = self._hub

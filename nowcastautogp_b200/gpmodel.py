@@ -250,14 +250,18 @@ class Particle:
         return len(self.prog)
 
 
+def _draw_code(rng, probs) -> int:
+    """1 + a categorical draw from unnormalised weights (inverse CDF on one uniform)."""
+    cum = np.cumsum(np.asarray(probs, float))
+    return 1 + int(min(np.searchsorted(cum, rng.random() * cum[-1], side="right"), len(cum) - 1))
+
+
 def sample_structure(rng, config: GPConfig, depth: int = 1) -> List[int]:
     """Post-order opcode list drawn from the PCFG prior (`node_dist_*`)."""
     max_depth = config.max_depth if config.max_depth > 0 else config.hard_max_depth
     if depth >= max_depth:
-        probs = np.asarray(config.node_dist_leaf, float)
-        return [1 + int(rng.choice(len(probs), p=probs / probs.sum()))]
-    probs = np.asarray(config.node_dist_cp if config.changepoints else config.node_dist_nocp, float)
-    code = 1 + int(rng.choice(len(probs), p=probs / probs.sum()))
+        return [_draw_code(rng, config.node_dist_leaf)]
+    code = _draw_code(rng, config.node_dist_cp if config.changepoints else config.node_dist_nocp)
     if code <= kn.OP_PERIODIC:
         return [code]
     return sample_structure(rng, config, depth + 1) + sample_structure(rng, config, depth + 1) + [code]

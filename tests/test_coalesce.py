@@ -29,6 +29,16 @@ class FakeEngine:
         self.calls.pop()
         return lm[None], np.asarray(ens.theta)[None] * 2.0, np.asarray(ens.noise)[None] * 3.0, info[None]
 
+    def hmc(self, prog, prog_off, theta_off, kind, a, b, noise_spec, z, noise_z, t, y1, y2=None, g=None, step=0.0,
+            y_stride=0, n_leapfrog=10, eps=0.02, momenta=None, noise_momenta=None, log_u=None):
+        P = noise_z.shape[1]
+        self.calls.append(("hmc", P, len(t)))
+        y = np.asarray(y1).reshape(P, len(t))
+        # "final state" = z + sum of its momenta; logml = y[0] of the chain's series + number of slots
+        ns = np.diff(theta_off)
+        return (z + momenta.sum(0)[None], noise_z + (0 if noise_momenta is None else noise_momenta.sum(0)[None]),
+                (y[:, 0] + ns)[None], np.full((1, P), len(log_u), np.int32), np.zeros((1, P), np.int32))
+
     def ess(self, logw):
         return np.ones(len(logw)), None
 
@@ -133,3 +143,31 @@ def test_lockstep_fit_equals_one_at_a_time(engine):
         assert np.array_equal(solo.log_weights, models[s].log_weights)
     x = ng.forecast(models[0], dates[-1] + np.arange(1, 5), 10)
     assert x.shape == (4, 10) and np.isfinite(x).all()
+
+
+def test_hmc_requests_merge():
+    fake = FakeEngine()
+    S = 4
+    hub = CoalescingEngine(fake, S)
+    t = np.linspace(0, 1, 9)
+    out = [None] * S
+
+    def work(s):
+        try:
+            ens = _ens(7 * s, 2 + s)
+            total, P = int(ens.theta_off[-1]), ens.size
+            rng = np.random.default_rng(s)
+            z, nz = rng.standard_normal((1, total)), rng.standard_normal((1, P))
+            mom, mnz, lu = rng.standard_normal((3, total)), rng.standard_normal((3, P)), rng.standard_normal((3, P))
+            Z, NZ, lm, nacc, info = hub.client(s).hmc(ens.prog, ens.prog_off, ens.theta_off, np.zeros(total, np.int32),
+                                                      np.zeros(total), np.ones(total), (0, -1.5, 1.0), z, nz, t,
+                                                      np.full(len(t), float(s)), momenta=mom, noise_momenta=mnz, log_u=lu)
+            out[s] = (np.allclose(Z, z + mom.sum(0)), np.allclose(NZ, nz + mnz.sum(0)),
+                      np.allclose(lm[0], s + np.diff(ens.theta_off)), (nacc == 3).all(), Z.shape == z.shape)
+        finally:
+            hub.retire(s)
+    ths = [threading.Thread(target=work, args=(s,)) for s in range(S)]
+    [th.start() for th in ths]
+    [th.join(timeout=30) for th in ths]
+    assert all(o is not None and all(o) for o in out), out
+    assert fake.calls == [("hmc", 2 + 3 + 4 + 5, 9)]
