@@ -375,6 +375,41 @@ def main():
                              "flops_per_launch": fl_, "note": "m^3/3 (Cholesky) + 2m^3/3 (inverse) per instance; "
                              "the per-entry reverse-mode work is not counted"}}
 
+    # ---- device-resident HMC — one iteration (10 leapfrog stages) of all K*P chains, one C-ABI call -------
+    def micro_hmc():
+        from nowcastautogp_b200 import kernels as kn_
+        m = n + k
+        names = kn_.theta_slot_names(w.ens.prog.tobytes())
+        base = w.ens.theta
+        ident = np.array([nm in ("intercept", "location") for nm in names]) | (base <= 0)
+        fixed = np.array([nm == "scale" for nm in names])
+        kind = np.where(fixed, 5, np.where(ident, 3, 0)).astype(np.int32)
+        sa = np.where(fixed, base, np.where(ident, 0.0, np.log(np.where(base > 0, base, 1.0))))
+        sb = np.ones(len(base))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            z0 = np.where(kind[None, :] == 0, np.log(theta_k / np.where(base > 0, base, 1.0)[None, :]), theta_k)
+        z0 = np.ascontiguousarray(np.where(np.isfinite(z0), z0, 0.0))
+        nz0 = np.ascontiguousarray(np.log(noise_k / w.ens.noise[None, :]))
+        rng_ = np.random.default_rng(99 + rank)
+        Lf, n_it = 10, 1
+        mom = rng_.standard_normal((n_it, K, len(base)))
+        mnz = rng_.standard_normal((n_it, K, P))
+        logu = np.log(rng_.uniform(size=(n_it, K, P)))
+        res = {}
+
+        def run():
+            res["out"] = eng.hmc(w.ens.prog, w.ens.prog_off, w.ens.theta_off, kind, sa, sb, (0, 0.0, 1.0), z0.copy(),
+                                 nz0.copy() + np.log(w.ens.noise)[None, :], w.t[:m], w.y1, y2=w.y2, g=w.g[:m], step=w.step,
+                                 n_leapfrog=Lf, eps=0.002, momenta=mom, noise_momenta=mnz, log_u=logu)
+        ms = timed(run, 2, 1)
+        _, _, lm_, nacc_, info_ = res["out"]
+        evals = K * P * (n_it * Lf + 1)
+        return {"what": "nagp_hmc: 1 HMC iteration (10 leapfrog stages + the initial evaluation = 11 logML+gradient "
+                        "evaluations) of all K*P = 32000 per-scenario chains in ONE C-ABI call with host buffers; integrator, "
+                        "z->theta maps and accept/reject on the device",
+                "value": evals * world / (ms * 1e-3), "unit": "gradient evals/s", "ms_per_step": ms,
+                "accept_rate": float(nacc_.mean()) / n_it, "ok": bool(np.isfinite(lm_[info_ == 0]).all())}
+
     # ---- inverse transformation + 25/50/75 % bands of the (h, K*D) draw matrix ---------------------
     def micro_summary():
         d_q = torch.empty((h, 3), dtype=torch.float64, device=dev)
@@ -390,7 +425,7 @@ def main():
                 "ms_per_step": ms, "bytes_per_launch": int(h * K * D * (8 + 16 + 2 * 3 * 8 * 8))}
 
     micro = None if args.no_micro else {"logml": micro_logml(), "append": micro_append(), "grad": micro_grad(),
-                                        "summary": micro_summary()}
+                                        "hmc": micro_hmc(), "summary": micro_summary()}
 
     # sanity: the step produced finite draws and no factorisation failed
     step_device()
@@ -445,6 +480,7 @@ def main():
                                                       frac=micro["append"]["append_roofline"]["achieved"] / hbm_peak)
             micro["grad"]["roofline"].update(peak=peak_tf, frac=micro["grad"]["roofline"]["achieved"] / peak_tf)
             line["hmc_gradient_microbench"] = micro["grad"]
+            line["hmc_microbench"] = micro["hmc"]
             line["summary_microbench"] = micro["summary"]
             line["logml_microbench"] = micro["logml"]
             line["append_microbench"] = micro["append"]

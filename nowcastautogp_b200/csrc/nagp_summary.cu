@@ -78,20 +78,51 @@ __device__ double select_rank(const double *row, int64_t N, int64_t rank, unsign
         const int shift = 56 - 8 * pass;
         for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
         __syncthreads();
-        for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
-            const unsigned long long k = sort_key(row[i]);
-            if ((k & mask) == prefix) atomicAdd(&hist[(unsigned)(k >> shift) & 255u], 1u);
+        // latency-bound on the L2 reads of the row: four independent loads in flight per thread
+        {
+            const int64_t stride = blockDim.x;
+            int64_t i = threadIdx.x;
+            for (; i + 3 * stride < N; i += 4 * stride) {
+                const unsigned long long k0 = sort_key(row[i]), k1 = sort_key(row[i + stride]);
+                const unsigned long long k2 = sort_key(row[i + 2 * stride]), k3 = sort_key(row[i + 3 * stride]);
+                if ((k0 & mask) == prefix) atomicAdd(&hist[(unsigned)(k0 >> shift) & 255u], 1u);
+                if ((k1 & mask) == prefix) atomicAdd(&hist[(unsigned)(k1 >> shift) & 255u], 1u);
+                if ((k2 & mask) == prefix) atomicAdd(&hist[(unsigned)(k2 >> shift) & 255u], 1u);
+                if ((k3 & mask) == prefix) atomicAdd(&hist[(unsigned)(k3 >> shift) & 255u], 1u);
+            }
+            for (; i < N; i += stride) {
+                const unsigned long long k0 = sort_key(row[i]);
+                if ((k0 & mask) == prefix) atomicAdd(&hist[(unsigned)(k0 >> shift) & 255u], 1u);
+            }
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            int64_t cum = 0;
-            int bin = 0;
-            for (; bin < 255; ++bin) {
-                if (cum + (int64_t)hist[bin] > rank) break;
-                cum += hist[bin];
+        if (threadIdx.x < 32) {
+            // warp 0: each lane sums 8 consecutive bins, exclusive scan over lanes, then the owning lane walks its 8
+            const int lane = threadIdx.x;
+            unsigned loc[8];
+            unsigned long long tot = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { loc[j] = hist[lane * 8 + j]; tot += loc[j]; }
+            unsigned long long incl = tot;
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
             }
-            s_state[0] = prefix | ((unsigned long long)bin << shift);
-            s_state[1] = (unsigned long long)(rank - cum);
+            const unsigned long long excl = incl - tot;
+            const bool mine = (unsigned long long)rank >= excl && (unsigned long long)rank < incl;
+            const unsigned who = __ballot_sync(0xffffffffu, mine);
+            // rank beyond the count can only come from an inconsistent histogram: clamp to the last non-empty lane
+            const int owner = who ? __ffs(who) - 1 : 31;
+            if (lane == owner) {
+                unsigned long long cum = excl;
+                int j = 0;
+                for (; j < 7; ++j) {
+                    if (cum + loc[j] > (unsigned long long)rank) break;
+                    cum += loc[j];
+                }
+                s_state[0] = prefix | ((unsigned long long)(lane * 8 + j) << shift);
+                s_state[1] = (unsigned long long)rank - cum;
+            }
         }
         __syncthreads();
         prefix = s_state[0];
@@ -105,7 +136,7 @@ __device__ double select_rank(const double *row, int64_t N, int64_t rank, unsign
 // One CTA per (row, probability). Julia `quantile(v, p)` (Statistics, alpha = beta = 1):
 //   aleph = n p + (1 - p); j = clamp(trunc(aleph), 1, n - 1); gamma = clamp(aleph - j, 0, 1);
 //   q = v[j] + gamma (v[j+1] - v[j]) for finite neighbours, (1 - gamma) v[j] + gamma v[j+1] otherwise.
-__global__ void __launch_bounds__(256) row_quantile_kernel(int64_t h, int64_t N, const double *rows, int64_t nq,
+__global__ void __launch_bounds__(1024) row_quantile_kernel(int64_t h, int64_t N, const double *rows, int64_t nq,
                                                            const double *probs, double *q)
 {
     __shared__ unsigned hist[256];
@@ -147,7 +178,7 @@ cudaError_t launch_row_quantiles(int64_t h, int64_t N, const double *rows, int64
                                  cudaStream_t stream)
 {
     if (h * nq == 0) return cudaSuccess;
-    row_quantile_kernel<<<(unsigned)(h * nq), 256, 0, stream>>>(h, N, rows, nq, probs, q);
+    row_quantile_kernel<<<(unsigned)(h * nq), 1024, 0, stream>>>(h, N, rows, nq, probs, q);
     return cudaGetLastError();
 }
 
