@@ -378,12 +378,24 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
         double gnoise = 0.0;
         const bool grid = a.g != nullptr;
         const bool single_table = (tp.clen == 1 && tp.cop[0] == OP_TABLE);
+        // Short compiled programs — one leaf, or two leaves under one Plus / Times / tabulated ChangePoint, leaves being
+        // lag tables, Linear or Constant (most prior-sampled trees once the stationary sub-trees are folded) — are
+        // differentiated in registers without the interpreter: adjoints and parameter sums live in named registers.
+        auto short_leaf = [](int o) { return o == OP_TABLE || o == OP_LINEAR || o == OP_CONSTANT; };
+        const int k0 = tp.cop[0], k1 = tp.clen == 3 ? tp.cop[1] : 0, kb = tp.clen == 3 ? tp.cop[2] : 0;
+        const bool short_prog = !single_table && short_leaf(k0) &&
+                                (tp.clen == 1 || (tp.clen == 3 && short_leaf(k1) &&
+                                                  (kb == OP_PLUS || kb == OP_TIMES || kb == OP_CHANGEPOINT_TAB)));
+        const int a0 = tp.carg[0], a1 = tp.clen == 3 ? tp.carg[1] : 0, ab = tp.clen == 3 ? tp.carg[2] : 0;
+        const double *sgb = sig + (tp.clen == 3 ? tp.caux[2] : 0) * Q;
+        double la0[3] = {0.0, 0.0, 0.0}, la1[3] = {0.0, 0.0, 0.0}, cpa[2] = {0.0, 0.0};
         const int ngroups = (Gd + 31) >> 5, Gp = ngroups * 32;
         for (int lg = 0; lg < ngroups; ++lg) {
             const int d = lg * 32 + lane;
             double hacc[MAX_TABLES];
 #pragma unroll
             for (int j = 0; j < MAX_TABLES; ++j) hacc[j] = 0.0;
+            double ha0 = 0.0, ha1 = 0.0;
             for (int ia = warp; ia < n; ia += kGW) {
                 const int ga = gg[ia] - g0;
                 if (ga < lg * 32) continue;                    // no lag of this group reaches back from row ia
@@ -394,15 +406,65 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
                 const double Wab = 0.5 * (alpha[ia] * alpha[ib] - Sab);
                 const double w = d == 0 ? Wab : 2.0 * Wab;
                 if (d == 0) gnoise += Wab;
-                if (single_table) { hacc[0] += w; continue; }   // fully stationary tree: the entry's weight IS the adjoint
+                if (single_table) { ha0 += w; continue; }       // fully stationary tree: the entry's weight IS the adjoint
                 const double ti = tt[ia], tj = tt[ib];
+                if (short_prog) {
+                    auto leaf_val = [&](int o, int arg) {
+                        if (o == OP_TABLE) return tab[arg * G + d];
+                        if (o == OP_LINEAR) return fma(th[arg + 2], (ti - th[arg]) * (tj - th[arg]), th[arg + 1]);
+                        return th[arg];
+                    };
+                    auto leaf_back = [&](int o, int arg, double ad, double &ha, double (&la)[3]) {
+                        if (o == OP_TABLE) ha += ad;
+                        else if (o == OP_LINEAR) {
+                            const double u = ti - th[arg], v2 = tj - th[arg];
+                            la[0] += ad * (-th[arg + 2] * (u + v2));
+                            la[1] += ad;
+                            la[2] += ad * (u * v2);
+                        } else la[0] += ad;
+                    };
+                    if (kb == 0) {
+                        leaf_back(k0, a0, w, ha0, la0);
+                    } else {
+                        const double v0 = leaf_val(k0, a0), v1 = leaf_val(k1, a1);
+                        double w0, w1;
+                        if (kb == OP_PLUS) { w0 = w; w1 = w; }
+                        else if (kb == OP_TIMES) { w0 = w * v1; w1 = w * v0; }
+                        else {
+                            const double si = sgb[ia], sj = sgb[ib];
+                            const double xi = (ti - th[ab]) / th[ab + 1], xj = (tj - th[ab]) / th[ab + 1];
+                            w0 = w * ((1.0 - si) * (1.0 - sj));
+                            w1 = w * (si * sj);
+                            const double dsi = 2.0 * si * (1.0 - si), dsj = 2.0 * sj * (1.0 - sj);
+                            const double dk_dsi = -(1.0 - sj) * v0 + sj * v1;
+                            const double dk_dsj = -(1.0 - si) * v0 + si * v1;
+                            cpa[0] += w * (dk_dsi * dsi + dk_dsj * dsj) * (-1.0 / th[ab + 1]);
+                            cpa[1] += w * (dk_dsi * dsi * (-xi / th[ab + 1]) + dk_dsj * dsj * (-xj / th[ab + 1]));
+                        }
+                        leaf_back(k0, a0, w0, ha0, la0);
+                        leaf_back(k1, a1, w1, ha1, la1);
+                    }
+                    continue;
+                }
                 const double delta = grid ? (double)d * a.step : fabs(ti - tj);
                 rev_entry(tp.cop, tp.carg, tp.caux, rp.cleft, 0, tp.clen, th, ti, tj, delta, d, ia, ib, tab, G, sig, Q,
                           w, gl, hacc);
             }
+            if (single_table || short_prog) {
+                // named accumulators back to their tables (two leaves may share nothing: table ids are distinct)
+                if (k0 == OP_TABLE) hacc[a0] += ha0;
+                if (k1 == OP_TABLE) hacc[a1] += ha1;
+            }
 #pragma unroll
             for (int j = 0; j < MAX_TABLES; ++j)
                 if (j < ntab) hpart[(warp * a.ntab_cap + j) * Gp + d] = hacc[j];
+        }
+        if (short_prog) {
+            if (k0 == OP_LINEAR) { gl[a0] += la0[0]; gl[a0 + 1] += la0[1]; gl[a0 + 2] += la0[2]; }
+            else if (k0 == OP_CONSTANT) gl[a0] += la0[0];
+            if (k1 == OP_LINEAR) { gl[a1] += la1[0]; gl[a1 + 1] += la1[1]; gl[a1 + 2] += la1[2]; }
+            else if (k1 == OP_CONSTANT) gl[a1] += la1[0];
+            if (kb == OP_CHANGEPOINT_TAB) { gl[ab] += cpa[0]; gl[ab + 1] += cpa[1]; }
         }
         __syncthreads();
         // ---- 4. table adjoints through the stationary sub-trees, once per (table, lag) -------------------------
