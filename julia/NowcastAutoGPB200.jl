@@ -126,4 +126,75 @@ function logml_batch(fl::Flat, t::Vector{Float64}, g, step::Float64, y::Vector{F
     return out
 end
 
+"""
+logML and its gradient w.r.t. every constrained hyperparameter and the noise, for K scenarios x P particles
+(what mcmc_parameters! differentiates, /root/reference/src/forecasting.jl:148,65). `theta_k` is `[total, K]`
+(K copies of the CSR theta vector), `noise_k` `[P, K]`, `y2` `[k, K]` scaled nowcast values (k may be 0).
+Returns `(logml [P,K], grad_theta [total,K], grad_noise [P,K])`.
+"""
+function logml_grad(fl::Flat, theta_k::Matrix{Float64}, noise_k::Matrix{Float64}, t::Vector{Float64}, g, step::Float64,
+        y2::Matrix{Float64})
+    K, P, total, k, n = size(theta_k, 2), fl.P, length(fl.theta), size(y2, 1), length(fl.y1)
+    logml = Matrix{Float64}(undef, P, K); gth = Matrix{Float64}(undef, total, K); gnz = Matrix{Float64}(undef, P, K)
+    info = Matrix{Int32}(undef, P, K)
+    GC.@preserve fl theta_k noise_k t g y2 logml gth gnz info begin
+        rc = ccall((:nagp_logml_grad, libnagp), Int32,
+            (Ptr{Cvoid}, Int64, Int64, Ptr{UInt8}, Ptr{Int64}, Ptr{Float64}, Ptr{Int64}, Int64, Ptr{Float64}, Int64,
+             Int64, Int64, Ptr{Float64}, Ptr{Int32}, Float64, Ptr{Float64}, Int64, Ptr{Float64},
+             Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
+            ctx(), K, P, fl.prog, fl.prog_off, theta_k, fl.theta_off, total, noise_k, P, n, k, t,
+            g === nothing ? C_NULL : g, step, fl.y1, 0, k == 0 ? C_NULL : y2, logml, gth, gnz, info)
+        rc < 0 && check(rc)      # > 0 only flags chains whose Gram is not PD: their logml is NaN, the sampler rejects
+    end
+    return logml, gth, gnz
+end
+
+"""
+`n_steps` HMC iterations (`n_leapfrog` stages of size `eps`) on the unconstrained hyperparameters of K x P chains,
+integrator on the device (nagp_hmc): the drop-in for `AutoGP.mcmc_parameters!(model, n_hmc)` on every scenario's
+copy at once (/root/reference/src/forecasting.jl:148,65). `z` `[total, K]` and `noise_z` `[P, K]` are updated in
+place; `slot_kind/slot_a/slot_b` describe z -> theta per slot (include/nagp.h) — to be filled from AutoGP's
+parameter transforms by the maintainer. Momenta and accept thresholds come from Julia's RNG, so a run is
+reproducible under `Random.seed!` exactly like the reference.
+"""
+function hmc!(fl::Flat, slot_kind::Vector{Int32}, slot_a::Vector{Float64}, slot_b::Vector{Float64},
+        noise_spec::Tuple{Int32, Float64, Float64}, z::Matrix{Float64}, noise_z::Matrix{Float64},
+        t::Vector{Float64}, g, step::Float64, y2::Matrix{Float64}; n_steps::Int, n_leapfrog::Int = 10, eps::Float64 = 0.02,
+        rng = Random.default_rng())
+    K, P, total, k, n = size(z, 2), fl.P, length(fl.theta), size(y2, 1), length(fl.y1)
+    mom = randn(rng, total, K, n_steps); mnz = randn(rng, P, K, n_steps); logu = log.(rand(rng, P, K, n_steps))
+    logml = Matrix{Float64}(undef, P, K); nacc = Matrix{Int32}(undef, P, K); info = Matrix{Int32}(undef, P, K)
+    GC.@preserve fl slot_kind slot_a slot_b z noise_z t g y2 mom mnz logu logml nacc info begin
+        rc = ccall((:nagp_hmc, libnagp), Int32,
+            (Ptr{Cvoid}, Int64, Int64, Ptr{UInt8}, Ptr{Int64}, Ptr{Int64}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64},
+             Int32, Float64, Float64, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Ptr{Float64}, Ptr{Int32}, Float64,
+             Ptr{Float64}, Int64, Ptr{Float64}, Int64, Int64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+             Ptr{Float64}, Ptr{Int32}, Ptr{Int32}),
+            ctx(), K, P, fl.prog, fl.prog_off, fl.theta_off, slot_kind, slot_a, slot_b,
+            noise_spec[1], noise_spec[2], noise_spec[3], z, noise_z, n, k, t, g === nothing ? C_NULL : g, step,
+            fl.y1, 0, k == 0 ? C_NULL : y2, n_steps, n_leapfrog, eps, mom, noise_spec[1] == 5 ? C_NULL : mnz, logu,
+            logml, nacc, info)
+        rc < 0 && check(rc)
+    end
+    return logml, nacc
+end
+
+"""
+The last host pass of forecast_with_nowcasts on the device: `inv_transformation.(x)` for the three built-in
+transformations of `get_transformations` (kind 1 "positive", 2 "percentage", 3 "boxcox" with (λ, offset, max)),
+in place, plus the per-date quantiles at `probs` (Julia's default definition). Returns the `(h, length(probs))` matrix.
+"""
+function forecast_summary!(x::Matrix{Float64}, kind::Integer, λ::Float64, offset::Float64, max_value::Float64,
+        probs::Vector{Float64} = [0.25, 0.5, 0.75])
+    h, N = size(x); nq = length(probs)
+    q = Matrix{Float64}(undef, nq, h)           # row-major [h, nq] on the C side
+    GC.@preserve x probs q begin
+        check(ccall((:nagp_forecast_summary, libnagp), Int32,
+            (Ptr{Cvoid}, Int32, Float64, Float64, Float64, Int64, Int64, Ptr{Float64}, Ptr{Float64}, Int64,
+             Ptr{Float64}, Ptr{Float64}),
+            ctx(), Int32(kind), λ, offset, max_value, h, N, x, x, nq, probs, q))
+    end
+    return permutedims(q)
+end
+
 end # module
