@@ -7,7 +7,7 @@ the CUDA library; the first device call does, and raises if `libnagp.so` or a GP
 from .tdata import TData, create_transformed_data, create_nowcast_data
 from .gpmodel import GPConfig, GPModel
 from .transformations import get_transformations
-from .api import make_and_fit_model, make_and_fit_models, forecast, forecast_with_nowcasts, forecast_with_nowcasts_sharded
+from .api import make_and_fit_model, make_and_fit_models, make_and_fit_models_sharded, forecast, forecast_with_nowcasts, forecast_with_nowcasts_sharded
 
 __all__ = ["TData", "GPModel", "GPConfig", "create_transformed_data", "make_and_fit_model", "forecast",
-           "forecast_with_nowcasts", "create_nowcast_data", "forecast_with_nowcasts_sharded", "get_transformations", "make_and_fit_models"]
+           "forecast_with_nowcasts", "create_nowcast_data", "forecast_with_nowcasts_sharded", "get_transformations", "make_and_fit_models", "make_and_fit_models_sharded"]

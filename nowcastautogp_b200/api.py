@@ -122,6 +122,27 @@ def make_and_fit_models(datas: Sequence[TData], *, n_particles: int = 1, smc_dat
     return models
 
 
+def make_and_fit_models_sharded(datas: Sequence[TData], *, seed: int = 0, engine=None, group=None, **kwargs) -> List[GPModel]:
+    """`make_and_fit_models` with the series split over the ranks of the current `torch.distributed` group (one
+    process per GPU): every rank fits its contiguous share in lockstep on its own device and the fitted models
+    travel as `to_dict()` payloads in one `all_gather_object`. Every rank returns all S models (bound to its own
+    engine), ready for `forecast_with_nowcasts_sharded`. Series s uses a generator derived from `(seed, s)`, so
+    the result does not depend on the number of ranks unless series share an observation order (`share_order`
+    couples the series of one rank; pass `share_order=False` for world-size-independent fits)."""
+    from .gpmodel import default_engine
+    from .sharding import sharded_fit
+    eng = default_engine() if engine is None else engine
+
+    def fit_local(idx: List[int]) -> List[dict]:
+        rng = np.random.default_rng([int(seed), int(idx[0])])
+        models = make_and_fit_models([datas[s] for s in idx], rng=rng, engine=eng, **kwargs)
+        return [m.to_dict() for m in models]
+
+    dicts = sharded_fit(fit_local, len(datas), group=group)
+    return [GPModel.from_dict(d, engine=eng, rng=np.random.default_rng([int(seed), 10 ** 6 + s]))
+            for s, d in enumerate(dicts)]
+
+
 def _apply(inv_transformation: Callable, x: np.ndarray, engine=None) -> np.ndarray:
     if inv_transformation is _identity:
         return x

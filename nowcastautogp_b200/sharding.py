@@ -118,3 +118,33 @@ def sharded_forecast(compute: Callable[[Slice], Tuple[np.ndarray, np.ndarray]], 
             logws[sl.series][sl.k0:sl.k1] = gl[r, off:off + kk]
             off += kk
     return draws, logws
+
+
+def sharded_fit(fit_local: Callable[[List[int]], List[dict]], n_series: int, group=None) -> List[dict]:
+    """Fit `n_series` independent series across the ranks of the current process group: rank r runs
+    `fit_local(series indices)` -> one serialised model (`GPModel.to_dict()`) per index on its contiguous share
+    (the same series-first split as the forecast: 53 series on 8 GPUs -> 7/7/7/7/7/6/6/6) and the dicts are
+    exchanged with one `all_gather_object` (a few KB per model: structures, z, weights — no bulk data). Returns the
+    `n_series` dicts in series order on every rank. No collective on the data path."""
+    import torch.distributed as dist
+
+    use_dist = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if use_dist else 1
+    rank = dist.get_rank(group) if use_dist else 0
+    parts = partition(n_series, 1, world)
+    mine = [sl.series for sl in parts[rank]]
+    local = fit_local(mine) if mine else []
+    if len(local) != len(mine):
+        raise ValueError("fit_local must return one model per series index")
+    if use_dist:
+        gathered: List = [None] * world
+        dist.all_gather_object(gathered, list(zip(mine, local)), group=group)
+    else:
+        gathered = [list(zip(mine, local))]
+    out: List = [None] * n_series
+    for chunk in gathered:
+        for s, d in chunk:
+            out[s] = d
+    if any(d is None for d in out):
+        raise RuntimeError("sharded_fit: a series was not fitted by any rank")
+    return out

@@ -171,3 +171,24 @@ def test_hmc_requests_merge():
     [th.join(timeout=30) for th in ths]
     assert all(o is not None and all(o) for o in out), out
     assert fake.calls == [("hmc", 2 + 3 + 4 + 5, 9)]
+
+
+@pytest.mark.gpu
+def test_sharded_fit_single_rank_roundtrips_models(engine):
+    """make_and_fit_models_sharded without a process group (world = 1): the models come back through their
+    `to_dict()` payloads and forecast as usual."""
+    import nowcastautogp_b200 as ng
+    rng = np.random.default_rng(4)
+    dates = np.arange(np.datetime64("2024-01-01"), np.datetime64("2024-02-10"))
+    datas = [ng.TData(dates, 15 + np.cos(np.arange(len(dates)) / (2.0 + s)) + 0.2 * rng.standard_normal(len(dates)),
+                      transformation=lambda v: v) for s in range(3)]
+    models = ng.make_and_fit_models_sharded(datas, seed=3, engine=engine, n_particles=3, smc_data_proportion=0.5,
+                                            n_mcmc=2, n_hmc=1)
+    assert len(models) == 3 and all(m.n_obs == len(dates) for m in models)
+    again = ng.make_and_fit_models_sharded(datas, seed=3, engine=engine, n_particles=3, smc_data_proportion=0.5,
+                                           n_mcmc=2, n_hmc=1)
+    for a, b in zip(models, again):                      # seeded: reproducible
+        assert [p.prog for p in a.particles] == [p.prog for p in b.particles]
+        assert np.array_equal(a.log_weights, b.log_weights)
+    x = ng.forecast(models[2], dates[-1] + np.arange(1, 4), 8)
+    assert x.shape == (3, 8) and np.isfinite(x).all()

@@ -7,7 +7,7 @@ import socket
 import numpy as np
 import pytest
 
-from nowcastautogp_b200.sharding import Slice, partition, sharded_forecast
+from nowcastautogp_b200.sharding import Slice, partition, sharded_fit, sharded_forecast
 
 
 def _pairs(parts):
@@ -104,3 +104,50 @@ def test_sharded_forecast_gloo_world2(S, ks):
     owned = sorted(c for _, _, calls in res for c in calls)
     want = sorted((sl.series, sl.k0, sl.k1) for part in partition(S, ks, world) for sl in part)
     assert owned == want                                     # each rank computed only its own slices
+
+
+def _fit_worker(rank, world, port, S, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        seen = []
+
+        def fit_local(idx):
+            seen.extend(idx)
+            return [{"series": s, "payload": [s * 1.5, "z" * s]} for s in idx]
+
+        out = sharded_fit(fit_local, S)
+        q.put((rank, [d["series"] for d in out] == list(range(S)) and out[S - 1]["payload"] == [(S - 1) * 1.5, "z" * (S - 1)],
+               seen))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("S", [5, 2, 1])
+def test_sharded_fit_gloo_world2(S):
+    import torch.multiprocessing as mp
+    with socket.socket() as s_:
+        s_.bind(("127.0.0.1", 0))
+        port = s_.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world = 2
+    procs = [ctx.Process(target=_fit_worker, args=(r, world, port, S, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res)                       # every rank holds all S models in series order
+    owned = sorted(s for _, _, seen in res for s in seen)
+    assert owned == list(range(S))                           # each series fitted by exactly one rank
+
+
+def test_sharded_fit_single_process():
+    out = sharded_fit(lambda idx: [{"s": s} for s in idx], 4)
+    assert [d["s"] for d in out] == [0, 1, 2, 3]
+    with pytest.raises(ValueError):
+        sharded_fit(lambda idx: [], 2)
