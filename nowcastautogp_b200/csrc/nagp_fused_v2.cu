@@ -5,9 +5,16 @@
 // (tile-packed, 512 B each). The factorisation is left-looking by tile column: every warp owns the
 // tiles I == warp (mod 8) of the current column, accumulates sum_P L_IP L_JP^T with DMMA
 // (mma.sync m8n8k4 f64, accumulators in registers, operands fetched as one 16-byte LDS per lane
-// from a fragment-major tile layout), the warp owning the diagonal tile factors it in registers
+// from the row-major tile), the warp owning the diagonal tile factors it in registers
 // with shuffles while building its inverse by the same row operations, and the column's
-// triangular solve is one more DMMA pair against that inverse. The observation vector rides along
+// triangular solve is one more DMMA pair against that inverse.
+//
+// One tile layout serves as A operand, B operand and accumulator: a sum over k may run in any order, so
+// the two k-chunks of a DMMA pair are taken as the even columns (k-slot t <-> column 2t) and the odd
+// columns (k-slot t <-> column 2t+1) of the tile instead of columns 0-3 and 4-7. Lane (g, t) then needs
+// elements (g, 2t) and (g, 2t+1) of a tile as operand — the very pair it holds as accumulator — so tiles
+// are plain row-major, every fragment is one 16-byte access at lane * 16, and no value ever moves
+// between lanes on its way from accumulator to operand. The observation vector rides along
 // as a virtual tile row, so z = L^-1 y needs no separate solve.
 //
 // FP64 has no tcgen05/UMMA kind on sm_100a, so DMMA is the tensor path for this workload; measured
@@ -252,8 +259,6 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
         // warps already accumulate column J+1 over P < J (every term that does not need column J).
         const int lr = lane >> 2, lj = lane & 3;
         const int oi0 = op_idx(lr, 2 * lj), oi1 = op_idx(lr, 2 * lj + 1);
-        const int cv0 = (lane & ~3) + (lj >> 1), cv1 = cv0 + 2;
-        const bool odd = lane & 1;
         const int nreg = warp < nt ? (nt - 1 - warp) / kW2 + 1 : 0;   // regular rows of this warp
         const int Ilast = warp + (nreg - 1) * kW2;
         const bool has_y = (warp == nt % kW2);
@@ -290,14 +295,14 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
             default: break;
             }
             if (has_y) {
-                const uint32_t yp = yv_a + lj * 8;
+                const uint32_t yp = yv_a + lj * 16;
 #pragma unroll 2
                 for (int P = P0; P < P1; ++P) {
                     const double2 bf = lds128(bp + (uint32_t)P * 512u);
-                    const double a0 = lr == 0 ? lds64(yp + P * 64) : 0.0;
-                    const double a1 = lr == 0 ? lds64(yp + P * 64 + 32) : 0.0;
-                    dmma(yacc[0][0], yacc[0][1], a0, bf.x);
-                    dmma(yacc[1][0], yacc[1][1], a1, bf.y);
+                    double2 af = lds128(yp + P * 64);
+                    if (lr != 0) af.x = af.y = 0.0;
+                    dmma(yacc[0][0], yacc[0][1], af.x, bf.x);
+                    dmma(yacc[1][0], yacc[1][1], af.y, bf.y);
                 }
             }
         };
@@ -322,10 +327,10 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                 accn[u][0][0] = accn[u][0][1] = accn[u][1][0] = accn[u][1][1] = 0.0;
             }
             if (has_y) {
-                const double y0 = lr == 0 ? lds64(yv_a + (J * 8 + 2 * lj) * 8) : 0.0;
-                const double y1v = lr == 0 ? lds64(yv_a + (J * 8 + 2 * lj + 1) * 8) : 0.0;
-                cy[0] = y0 - (yacc[0][0] + yacc[1][0]);
-                cy[1] = y1v - (yacc[0][1] + yacc[1][1]);
+                double2 yj = lds128(yv_a + (J * 8 + 2 * lj) * 8);
+                if (lr != 0) yj.x = yj.y = 0.0;
+                cy[0] = yj.x - (yacc[0][0] + yacc[1][0]);
+                cy[1] = yj.y - (yacc[0][1] + yacc[1][1]);
                 yacc[0][0] = yacc[0][1] = yacc[1][0] = yacc[1][1] = 0.0;
             }
             DBG_T(J, 1);
@@ -338,10 +343,8 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                 const int bad = chol8_inv(d0, d1, w0, w1, lane, q - J * 8, piv);
 #endif
                 const uint32_t dt = tiles_a + (uint32_t)((tri(J) + J) * 512);
-                sts64(dt + oi0 * 8, d0);
-                sts64(dt + oi1 * 8, d1);
-                sts64(invL_a + oi0 * 8, w0);
-                sts64(invL_a + oi1 * 8, w1);
+                sts128(dt + lane * 16, d0, d1);
+                sts128(invL_a + lane * 16, w0, w1);
                 if (KEEP && a.Wkeep) {
                     double *wk = a.Wkeep + ((size_t)b * nt + J) * 64;
                     wk[oi0] = w0; wk[oi1] = w1;
@@ -376,26 +379,18 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
 #pragma unroll
                 for (int u = 0; u < kMaxTilesPerWarp; ++u) {
                     if (u < nsolve) {
-                        const double v00 = shfl(c[u][0], cv0), v01 = shfl(c[u][1], cv0);
-                        const double v10 = shfl(c[u][0], cv1), v11 = shfl(c[u][1], cv1);
+                        // the accumulator pair (g, 2t), (g, 2t+1) is this lane's A fragment of both k-chunks
                         double x0 = 0.0, x1 = 0.0;
-                        dmma(x0, x1, odd ? v01 : v00, ib.x);
-                        dmma(x0, x1, odd ? v11 : v10, ib.y);
-                        const uint32_t dt = rowa[u] - lane * 16 + joff;
-                        sts64(dt + oi0 * 8, x0);
-                        sts64(dt + oi1 * 8, x1);
+                        dmma(x0, x1, c[u][0], ib.x);
+                        dmma(x0, x1, c[u][1], ib.y);
+                        sts128(rowa[u] + joff, x0, x1);
                     }
                 }
                 if (has_y) {
-                    const double v00 = shfl(cy[0], cv0), v01 = shfl(cy[1], cv0);
-                    const double v10 = shfl(cy[0], cv1), v11 = shfl(cy[1], cv1);
                     double x0 = 0.0, x1 = 0.0;
-                    dmma(x0, x1, odd ? v01 : v00, ib.x);
-                    dmma(x0, x1, odd ? v11 : v10, ib.y);
-                    if (lr == 0) {
-                        sts64(yv_a + (J * 8 + 2 * lj) * 8, x0);
-                        sts64(yv_a + (J * 8 + 2 * lj + 1) * 8, x1);
-                    }
+                    dmma(x0, x1, cy[0], ib.x);
+                    dmma(x0, x1, cy[1], ib.y);
+                    if (lr == 0) sts128(yv_a + (J * 8 + 2 * lj) * 8, x0, x1);
                 }
             }
             DBG_T(J, 4);
@@ -406,10 +401,14 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
         DBG_G(4);
 
         if (KEEP && a.Lkeep && !s_info) {
-            // keep the factor for the gradient kernel: tiles as they are (operand layout), z padded to Q
+            // keep the factor for the gradient kernel in its fragment-major tile layout (op_idx: columns c and
+            // c+4 of a row adjacent), z padded to Q
             double *Lo = a.Lkeep + (size_t)b * ((size_t)ntiles * 64);
-            for (int i = tid; i < ntiles * 32; i += kT2)
-                reinterpret_cast<double2 *>(Lo)[i] = reinterpret_cast<const double2 *>(tiles)[i];
+            for (int i = tid; i < ntiles * 32; i += kT2) {
+                const int tile = i >> 5, e = i & 31, r = e >> 2, cq = e & 3;
+                const double *src = tiles + tile * 64 + r * 8 + cq;
+                reinterpret_cast<double2 *>(Lo)[i] = make_double2(src[0], src[4]);
+            }
             double *zo = a.zkeep + (size_t)b * Q;
             for (int i = tid; i < Q; i += kT2) zo[i] = yv[i];
         }
@@ -426,7 +425,7 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
 
         // element (i, j), i >= j, of the factor
         auto Lel = [&](int i, int j) {
-            return tiles[(tri(i >> 3) + (j >> 3)) * 64 + op_idx(i & 7, j & 7)];
+            return tiles[(tri(i >> 3) + (j >> 3)) * 64 + (i & 7) * 8 + (j & 7)];
         };
 
         // ---- logML(n), logML(m) ----------------------------------------------------------------------

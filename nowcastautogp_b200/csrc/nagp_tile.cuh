@@ -144,10 +144,84 @@ __device__ __forceinline__ void tree_eval4(const TreeProgram &tp, const EvalCtx 
 }
 
 
+#ifndef NAGP_CHOL8_OLD
+#define NAGP_CHOL8_OLD 0   // 1: the first (rsqrt-on-the-chain) version, kept for A/B timing builds
+#endif
+
+// MUFU seeds (about 20 good bits: the instruction reads only the upper word of its operand) refined by one
+// third-order step each: enough for a result within an ulp or two, and the shortest dependent chain.
+__device__ __forceinline__ double rcp_seeded(double d)
+{
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    const double e = fma(-d, x, 1.0);
+    const double q = fma(e, e, e);
+    return fma(x, q, x);
+}
+__device__ __forceinline__ double rsqrt_seeded(double d)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double e = fma(-(y * y), d, 1.0);
+    const double t = fma(e, 0.375, 0.5);
+    return fma(t, y * e, y);
+}
+
 // In-register Cholesky of an 8x8 tile held in DMMA accumulator layout (lane (r = l>>2, j = l&3)
 // holds columns 2j, 2j+1 of row r), together with its inverse built by the same row operations
 // (L^-1 A = L^T, so the operations that reduce A to L^T turn I into L^-1).
 // Returns 0 or 1 + index of the first non-positive pivot among the first `nreal` rows.
+//
+// This is the serial chain of the tile-column factorisation (one warp, everybody else waits for it), so it is
+// written for dependent depth: per pivot the chain is shuffle(d) -> MUFU -> 3 FMA (1/d) -> 1 FMA (Schur
+// update). The products that do not need 1/d are formed while it is being computed, rows and columns that
+// must not change are masked through zero factors instead of selects on the result, the scaling by
+// 1/sqrt(d) (its own MUFU chain) happens off the chain, and the inverse is carried unscaled (row p of
+// L^-1 is scaled once at the end).
+#if !NAGP_CHOL8_OLD
+__device__ __forceinline__ int chol8_inv(double &c0, double &c1, double &w0, double &w1, int lane,
+                                         int nreal, double (&piv)[8])
+{
+    const int r = lane >> 2, j = lane & 3;
+    w0 = (r == 2 * j) ? 1.0 : 0.0;
+    w1 = (r == 2 * j + 1) ? 1.0 : 0.0;
+    double my_rinv = 0.0;
+    int bad = 0;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+        const int pl = p >> 1;
+        const double colv = (p & 1) ? c1 : c0;            // column p lives in the lanes j == pl
+        const double d = shfl(colv, p * 4 + pl);
+        piv[p] = d;
+        if (!(d > 0.0) && p < nreal && bad == 0) bad = p + 1;
+        const double rinv = rsqrt_seeded(d);
+        if (p < 7) {
+            const double arp = shfl(colv, r * 4 + pl);        // (r, p)
+            const double ac0 = shfl(colv, (2 * j) * 4 + pl);  // (2j, p)
+            const double ac1 = shfl(colv, (2 * j + 1) * 4 + pl);
+            const double wp0 = shfl(w0, p * 4 + j);           // unscaled row p of the inverse
+            const double wp1 = shfl(w1, p * 4 + j);
+            const double x = rcp_seeded(d);
+            const double am = r > p ? arp : 0.0;              // rows <= p do not change
+            const double u0 = am * (2 * j > p ? ac0 : 0.0);   // columns <= p do not change
+            const double u1 = am * (2 * j + 1 > p ? ac1 : 0.0);
+            const double v0 = am * wp0, v1 = am * wp1;
+            const double fin = r >= p ? colv * rinv : 0.0;
+            c0 = fma(-u0, x, c0);
+            c1 = fma(-u1, x, c1);
+            w0 = fma(-v0, x, w0);
+            w1 = fma(-v1, x, w1);
+            if (j == pl) { if (p & 1) c1 = fin; else c0 = fin; }
+        } else {
+            if (j == pl) c1 = r >= p ? colv * rinv : 0.0;
+        }
+        if (r == p) my_rinv = rinv;
+    }
+    w0 *= my_rinv;
+    w1 *= my_rinv;
+    return bad;
+}
+#else
 __device__ __forceinline__ int chol8_inv(double &c0, double &c1, double &w0, double &w1, int lane,
                                          int nreal, double (&piv)[8])
 {
@@ -181,6 +255,7 @@ __device__ __forceinline__ int chol8_inv(double &c0, double &c1, double &w0, dou
     }
     return bad;
 }
+#endif
 
 
 }  // namespace
