@@ -43,7 +43,7 @@ extern "C" int nagp_debug_read(long long *out, int count)
 {
     return (int)cudaMemcpyFromSymbol(out, g_nagp_dbg, sizeof(long long) * count);
 }
-#define DBG_T(J, ph) do { if (b == 0 && lane == 0) g_nagp_dbg[((J) * 8 + warp) * 8 + (ph)] = clock64(); } while (0)
+#define DBG_T(J, ph) do { if (b == 0 && lane == 0) g_nagp_dbg[((J) * 8 + dbg_w) * 8 + (ph)] = clock64(); } while (0)
 #define DBG_G(ph) do { if (b == 0 && tid == 0) g_nagp_dbg[8000 + (ph)] = clock64(); } while (0)
 #else
 #define DBG_T(J, ph) do { } while (0)
@@ -57,9 +57,28 @@ namespace {
 #ifndef NAGP_V2_WARPS
 #define NAGP_V2_WARPS 8
 #endif
+#ifndef NAGP_V2_PANEL
+#define NAGP_V2_PANEL 0   // 1: the diagonal chain runs on its own warp scheduler (see "panel schedule" below); 0: rotating owner
+#endif
 constexpr int kW2 = NAGP_V2_WARPS;      // warps per CTA of the tile kernel
 constexpr int kT2 = kW2 * 32;
-constexpr int kMaxTilesPerWarp = (29 + kW2 - 1) / kW2;   // ceil(nt / kW2), nt <= 29
+#if NAGP_V2_PANEL
+// Panel schedule: a dependent FP64 chain shares its scheduler's issue slots and FP64 pipe with whatever else
+// runs there (tools/chol8_bench2.cu: the 8x8 factorisation takes 1.2 k cycles next to idle warps or to busy
+// warps on the OTHER three schedulers, 1.8 k next to one DMMA-issuing warp on its own scheduler, 4.4 k next to
+// three), so the chain gets a scheduler to itself: one warp of scheduler 0 factors every diagonal tile and does nothing
+// else, the other warp of that scheduler sits the factorisation out, and the six warps of schedulers 1-3 own the tile
+// rows (roles are dealt by hardware warp slot at kernel start).
+static_assert(kW2 == 8, "the panel schedule assumes 8 warps: two per scheduler");
+#ifndef NAGP_V2_PANEL_ROWS
+#define NAGP_V2_PANEL_ROWS 6            // 6: the second warp of the chain's scheduler idles; 7: it owns rows too
+#endif
+constexpr int kNB = NAGP_V2_PANEL_ROWS; // row-owning warps
+#else
+constexpr int kNB = kW2;
+#endif
+constexpr int kTB = kNB * 32;
+constexpr int kMaxTilesPerWarp = (29 + kNB - 1) / kNB;   // ceil(nt / kNB), nt <= 29
 
 // DMMA inner loop of the left-looking update for NA tile rows of one warp: per P one 16-byte LDS for
 // the shared B fragment (tile (Jc, P)), and per row one 16-byte LDS + two DMMAs (one per k-chunk, on
@@ -80,6 +99,26 @@ __device__ __forceinline__ void kloop(double (&acc)[kMaxTilesPerWarp][2][2], uin
         }
     }
 }
+
+#if NAGP_V2_PANEL
+// Row owner, column J, its tile (J+1, J) in slot U: solve it, store it, add its square to the partial sum of
+// diagonal tile J+1 (operands straight from the accumulator registers) and put C_{J+1,J+1} in that tile's place
+// for the chain warp.
+template <int U>
+__device__ __forceinline__ void hand_over(const double (&c)[kMaxTilesPerWarp][2], double (&acc)[kMaxTilesPerWarp][2][2],
+                                          const uint32_t (&rowa)[kMaxTilesPerWarp], const double2 ib, int J)
+{
+    const double2 g2 = lds128(rowa[U] + (uint32_t)(J + 1) * 512u);
+    double x0 = 0.0, x1 = 0.0;
+    dmma(x0, x1, c[U][0], ib.x);
+    dmma(x0, x1, c[U][1], ib.y);
+    sts128(rowa[U] + (uint32_t)J * 512u, x0, x1);
+    dmma(acc[U][0][0], acc[U][0][1], x0, x0);
+    dmma(acc[U][1][0], acc[U][1][1], x1, x1);
+    sts128(rowa[U] + (uint32_t)(J + 1) * 512u, g2.x - (acc[U][0][0] + acc[U][1][0]), g2.y - (acc[U][0][1] + acc[U][1][1]));
+    acc[U][0][0] = acc[U][0][1] = acc[U][1][0] = acc[U][1][1] = 0.0;
+}
+#endif
 
 struct V2Layout {
     int nt;            // tile rows/cols of the matrix (rows padded to Q = 8 nt)
@@ -112,7 +151,7 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
     double *tiles = smem;
     double *yv = tiles + ntiles * 64;
     double *invL = yv + Q;
-    char *aux_s = reinterpret_cast<char *>(invL + 64);
+    char *aux_s = reinterpret_cast<char *>(invL + 128);   // two inverse-tile buffers
     char *aux_g = lay.scratch + (size_t)blockIdx.x * lay.scratch_stride;
     auto aux = [&](int i) { return (lay.aux_smem[i] ? aux_s : aux_g) + lay.aux_off[i]; };
     double *th = reinterpret_cast<double *>(aux(0));
@@ -121,6 +160,52 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
     double *sig = reinterpret_cast<double *>(aux(3));
     double *tab = reinterpret_cast<double *>(aux(4));
 
+#if NAGP_EXP == 9
+    if (lane == 0 && blockIdx.x < 600) {
+        unsigned smid, wid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+        if (smid == 0) {   // who lives on SM 0, and in which hardware warp slot
+            int slot = atomicAdd((int *)&g_nagp_dbg[8100], 1);
+            if (slot < 40) g_nagp_dbg[8101 + slot] = ((long long)blockIdx.x << 32) | (warp << 8) | wid;
+            g_nagp_dbg[8150] = blockIdx.x;
+        }
+    }
+#endif
+#if NAGP_V2_PANEL
+    // Roles by hardware scheduler, not by warp index: the hardware warp slot (%warpid; slot mod 4 = scheduler) is
+    // some permutation of the CTA's warps that differs between co-resident CTAs, and the point of the panel
+    // schedule is that the chain warps of BOTH resident CTAs share one scheduler that no row owner uses. Chain =
+    // first warp on scheduler 0, the other warp there idles, the remaining six own rows in order. (Only speed
+    // depends on this: any assignment of one chain warp and six row owners is correct.)
+    __shared__ int s_sched[kW2];
+    __shared__ int s_role[kW2];                 // -1 chain, -2 idle, else row-owner index
+    if (lane == 0) {
+        unsigned wid;
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+        s_sched[warp] = (int)(wid & 3u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int chain = -1, idle = -1;
+        for (int w = 0; w < kW2; ++w)
+            if (s_sched[w] == 0) { if (chain < 0) chain = w; else if (idle < 0) idle = w; }
+        if (chain < 0) chain = 0;
+        if (idle < 0) idle = (chain == kW2 - 1) ? kW2 - 2 : kW2 - 1;
+        int nb = 0;
+        if (kNB == kW2 - 1) idle = -1;
+        for (int w = 0; w < kW2; ++w) s_role[w] = (w == chain) ? -1 : (w == idle) ? -2 : nb++;
+    }
+    __syncthreads();
+    const int role = s_role[warp];
+#endif
+#if NAGP_EXP == 9
+#if NAGP_V2_PANEL
+    const int dbg_w = role == -1 ? 0 : role == -2 ? 4 : role < 3 ? role + 1 : role + 2;   // timeline row of this warp
+#else
+    const int dbg_w = warp;
+#endif
+#endif
     for (int I = tid; I < nt; I += kT2)
         for (int J = 0; J <= I; ++J) s_ti[tri(I) + J] = (unsigned char)I;
     // times are common to every instance of the launch
@@ -259,14 +344,20 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
         // warps already accumulate column J+1 over P < J (every term that does not need column J).
         const int lr = lane >> 2, lj = lane & 3;
         const int oi0 = op_idx(lr, 2 * lj), oi1 = op_idx(lr, 2 * lj + 1);
-        const int nreg = warp < nt ? (nt - 1 - warp) / kW2 + 1 : 0;   // regular rows of this warp
-        const int Ilast = warp + (nreg - 1) * kW2;
-        const bool has_y = (warp == nt % kW2);
+#if NAGP_V2_PANEL
+        const bool bulk = role >= 0;
+        const int bi = bulk ? role : kNB;   // row-owner index 0..5
+#else
+        const int bi = warp;
+#endif
+        const int nreg = bi < nt ? (nt - 1 - bi) / kNB + 1 : 0;   // regular rows of this warp
+        const int Ilast = bi + (nreg - 1) * kNB;
+        const bool has_y = (bi == nt % kNB);
         const uint32_t tiles_a = smem_addr(tiles), yv_a = smem_addr(yv), invL_a = smem_addr(invL);
         uint32_t rowa[kMaxTilesPerWarp];        // shared address of this lane's fragment in tile (I_u, 0)
 #pragma unroll
         for (int u = 0; u < kMaxTilesPerWarp; ++u) {
-            const int I = Ilast - u * kW2;
+            const int I = Ilast - u * kNB;
             rowa[u] = tiles_a + (uint32_t)(tri(I > 0 ? I : 0) * 512 + lane * 16);
         }
         double accn[kMaxTilesPerWarp][2][2];   // [slot][k-chunk chain][acc regs] partial sums of the current column
@@ -276,12 +367,13 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
         int pre_done = 0;                       // terms P < pre_done are already in accn / yacc
 
         // accumulate sum_{P0 <= P < P1} L_IP L_{Jc,P}^T for the owned rows I >= Jc (and the observation row)
-        auto accumulate = [&](int Jc, int P0, int P1) {
-#if NAGP_EXP == 2
+        // skip_top: leave out the topmost active row (a diagonal tile that was brought up to date early)
+        auto accumulate = [&](int Jc, int P0, int P1, bool skip_top) {
+#if NAGP_EXP == 2 || defined(NAGP_EXP_NOACC)
             return;
 #endif
             if (P0 >= P1) return;
-            const int NA = Ilast >= Jc ? (Ilast - Jc) / kW2 + 1 : 0;
+            const int NA = (Ilast >= Jc ? (Ilast - Jc) / kNB + 1 : 0) - (skip_top ? 1 : 0);
             const uint32_t bp = tiles_a + (uint32_t)(tri(Jc) * 512 + lane * 16);
             switch (NA) {
             case 1: kloop<(kMaxTilesPerWarp >= 1 ? 1 : 1)>(accn, bp, rowa, P0, P1); break;
@@ -307,12 +399,13 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
             }
         };
 
+#if !NAGP_V2_PANEL
         for (int J = 0; J < nt; ++J) {
             const bool owner = (warp == (J % kW2));
-            const int NA = Ilast >= J ? (Ilast - J) / kW2 + 1 : 0;   // active regular rows (I >= J)
+            const int NA = Ilast >= J ? (Ilast - J) / kNB + 1 : 0;   // active regular rows (I >= J)
             // (1) remaining terms of column J, (2) C = A_IJ - sum
             DBG_T(J, 0);
-            accumulate(J, pre_done, J);
+            accumulate(J, pre_done, J, false);
             double c[kMaxTilesPerWarp][2], cy[2] = {0.0, 0.0}, d0 = 0.0, d1 = 0.0;
             const uint32_t joff = (uint32_t)J * 512u;
 #pragma unroll
@@ -362,7 +455,7 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                 asm volatile("bar.sync 1, %0;" ::"n"(kT2) : "memory");
             } else {
                 // (4) lookahead: column J+1 over P < J
-                if (J + 1 < nt) accumulate(J + 1, 0, J);
+                if (J + 1 < nt) accumulate(J + 1, 0, J, false);
                 pre_done = J;
                 DBG_T(J, 2);
                 asm volatile("bar.sync 1, %0;" ::"n"(kT2) : "memory");
@@ -398,6 +491,119 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
             DBG_T(J, 5);
             if (s_info) break;
         }
+#else
+        // ---- panel schedule -----------------------------------------------------------------------------
+        // Named barriers: 1 = "inverse of diagonal tile J published" (chain warp arrives, row owners wait),
+        // 2 = "C_JJ is in its tile" (the owner of row J arrives, the chain warp waits), 3 = "tile (J+1, J) is
+        // written" among the row owners (its producer only arrives). Two inverse buffers: the chain may publish
+        // column J+1 while slow rows still solve column J.
+        if (role == -1) {
+            for (int J = 0; J < nt; ++J) {
+                if (J > 0) asm volatile("bar.sync 2, 64;" ::: "memory");
+                DBG_T(J, 1);
+                const uint32_t dt = tiles_a + (uint32_t)((tri(J) + J) * 512 + lane * 16);
+                const double2 cj = lds128(dt);
+                double d0 = cj.x, d1 = cj.y, w0, w1, piv[8];
+#if NAGP_EXP == 9
+                if (d0 == 123.456) DBG_T(J, 5);   // forces the load to complete before the stamp
+                DBG_T(J, 4);
+#endif
+                const int bad = chol8_inv(d0, d1, w0, w1, lane, q - J * 8, piv);
+#if NAGP_EXP == 9
+                if (w0 == 123.456) DBG_T(J, 5);
+                DBG_T(J, 3);
+#endif
+                sts128(dt, d0, d1);
+                sts128(invL_a + (uint32_t)((J & 1) * 512 + lane * 16), w0, w1);
+                if (KEEP && a.Wkeep) {
+                    double *wk = a.Wkeep + ((size_t)b * nt + J) * 64;
+                    wk[oi0] = w0; wk[oi1] = w1;
+                }
+                if (bad && lane == 0) s_info = J * 8 + bad;
+                __syncwarp();
+                DBG_T(J, 2);
+                asm volatile("bar.arrive 1, %0;" ::"n"(kTB + 32) : "memory");
+                if (bad) break;
+            }
+        } else if (bulk) {
+            for (int J = 0; J < nt; ++J) {
+                const int NA = Ilast >= J ? (Ilast - J) / kNB + 1 : 0;   // active regular rows (I >= J)
+                const bool own_diag = (J % kNB == bi);      // its tile went to the chain warp at the end of column J-1
+                const int nsolve = own_diag ? NA - 1 : NA;  // rows strictly below the diagonal
+                const uint32_t joff = (uint32_t)J * 512u;
+                DBG_T(J, 0);
+                // (1) remaining terms of column J, C = A_IJ - sum
+                accumulate(J, pre_done, J, own_diag);
+                double c[kMaxTilesPerWarp][2], cy[2] = {0.0, 0.0};
+#pragma unroll
+                for (int u = 0; u < kMaxTilesPerWarp; ++u) {
+                    c[u][0] = 0.0; c[u][1] = 0.0;
+                    if (u < nsolve) {
+                        const double2 g2 = lds128(rowa[u] + joff);
+                        c[u][0] = g2.x - (accn[u][0][0] + accn[u][1][0]);
+                        c[u][1] = g2.y - (accn[u][0][1] + accn[u][1][1]);
+                    }
+                    accn[u][0][0] = accn[u][0][1] = accn[u][1][0] = accn[u][1][1] = 0.0;
+                }
+                if (has_y) {
+                    double2 yj = lds128(yv_a + (J * 8 + 2 * lj) * 8);
+                    if (lr != 0) yj.x = yj.y = 0.0;
+                    cy[0] = yj.x - (yacc[0][0] + yacc[1][0]);
+                    cy[1] = yj.y - (yacc[0][1] + yacc[1][1]);
+                    yacc[0][0] = yacc[0][1] = yacc[1][0] = yacc[1][1] = 0.0;
+                }
+                DBG_T(J, 1);
+                // (2) lookahead: column J+1 over P < J, in the shadow of the diagonal factorisation
+                if (J + 1 < nt) accumulate(J + 1, 0, J, false);
+                pre_done = J;
+                DBG_T(J, 2);
+                asm volatile("bar.sync 1, %0;" ::"n"(kTB + 32) : "memory");
+                DBG_T(J, 3);
+                if (s_info) break;
+                // (3) triangular solve of the column: X = C * invL^T. The tile that heads the next column goes
+                //     first: its owner also folds it into the next diagonal tile and hands that to the chain warp.
+                const double2 ib = lds128(invL_a + (uint32_t)((J & 1) * 512 + lane * 16));
+                const bool owns_next = (J + 1 < nt) && ((J + 1) % kNB == bi);
+                int nrest = nsolve;
+                if (owns_next) {
+                    nrest = nsolve - 1;
+                    switch (nsolve) {
+                    case 1: hand_over<0>(c, accn, rowa, ib, J); break;
+                    case 2: hand_over<(kMaxTilesPerWarp >= 2 ? 1 : 0)>(c, accn, rowa, ib, J); break;
+                    case 3: hand_over<(kMaxTilesPerWarp >= 3 ? 2 : 0)>(c, accn, rowa, ib, J); break;
+                    case 4: hand_over<(kMaxTilesPerWarp >= 4 ? 3 : 0)>(c, accn, rowa, ib, J); break;
+                    case 5: hand_over<(kMaxTilesPerWarp >= 5 ? 4 : 0)>(c, accn, rowa, ib, J); break;
+                    case 6: hand_over<(kMaxTilesPerWarp >= 6 ? 5 : 0)>(c, accn, rowa, ib, J); break;
+                    default: break;
+                    }
+                    __syncwarp();
+                    asm volatile("bar.arrive 2, 64;" ::: "memory");
+                    asm volatile("bar.arrive 3, %0;" ::"n"(kTB) : "memory");
+                }
+#pragma unroll
+                for (int u = 0; u < kMaxTilesPerWarp; ++u) {
+                    if (u < nrest) {
+                        // the accumulator pair (g, 2t), (g, 2t+1) is this lane's A fragment of both k-chunks
+                        double x0 = 0.0, x1 = 0.0;
+                        dmma(x0, x1, c[u][0], ib.x);
+                        dmma(x0, x1, c[u][1], ib.y);
+                        sts128(rowa[u] + joff, x0, x1);
+                    }
+                }
+                if (has_y) {
+                    double x0 = 0.0, x1 = 0.0;
+                    dmma(x0, x1, cy[0], ib.x);
+                    dmma(x0, x1, cy[1], ib.y);
+                    if (lr == 0) sts128(yv_a + (J * 8 + 2 * lj) * 8, x0, x1);
+                }
+                DBG_T(J, 4);
+                if (J + 1 < nt && !owns_next) asm volatile("bar.sync 3, %0;" ::"n"(kTB) : "memory");
+                else __syncwarp();
+                DBG_T(J, 5);
+            }
+        }
+        __syncthreads();
+#endif
         DBG_G(4);
 
         if (KEEP && a.Lkeep && !s_info) {
@@ -500,7 +706,7 @@ void aux_sizes(int Q, int G, int ntheta_cap, int ntab_cap, int ncp_cap, size_t (
 
 }  // namespace
 
-int fused_v2_max_q() { return 8 * (kMaxTilesPerWarp * kW2 - 1); }
+int fused_v2_max_q() { return 8 * (kMaxTilesPerWarp * kNB - 1); }
 
 // Plans shared memory for the tile kernel: the tiles, yv and invL are mandatory; the aux arrays go
 // to shared memory in priority order while the CTA stays within `budget` bytes, else to global
@@ -510,7 +716,7 @@ V2Plan plan_fused_v2(int q, int G, int ntheta_cap, int ntab_cap, int ncp_cap, in
     V2Plan pl{};
     const int nt = (q + 7) / 8, Q = nt * 8;
     pl.nt = nt;
-    size_t base = ((size_t)(nt * (nt + 1) / 2) * 64 + Q + 64) * sizeof(double);
+    size_t base = ((size_t)(nt * (nt + 1) / 2) * 64 + Q + 128) * sizeof(double);
     size_t sz[5];
     aux_sizes(Q, G, ntheta_cap, ntab_cap, ncp_cap, sz);
     size_t total_aux = sz[0] + sz[1] + sz[2] + sz[3] + sz[4];
@@ -545,6 +751,9 @@ int fused_v2_grid(const V2Plan &pl, int64_t B, int num_sms)
         cudaGetLastError();
         per_sm = 1;
     }
+#if NAGP_EXP == 9
+    if (getenv("NAGP_V2_ONE_CTA")) per_sm = 1;       // timeline experiment: one resident matrix per SM
+#endif
     int64_t g = (int64_t)per_sm * num_sms;
     return (int)std::min<int64_t>(g, B);
 }

@@ -23,6 +23,51 @@ __global__ void bench(const double *A, double *L, double *W, long long *cyc, int
     if (lane == 0) { cyc[0] = (t1 - t0) / reps; cyc[1] = bad; }
 }
 
+// chol8_inv on warp 0 while the other warps of the CTA run a background load: mode 1 = DMMA only (independent
+// accumulator chains), 2 = LDS.128 only, 3 = LDS.128 + DMMA as in the tile kernel's inner loop. `mask` selects
+// which warps run the background (bit w); the rest exit at once.
+__global__ void bench_bg(const double *A, long long *cyc, int reps, int mode, unsigned mask, double *sink)
+{
+    __shared__ double sm[16 * 64 * 4];
+    __shared__ volatile int stop;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, r = lane >> 2, j = lane & 3;
+    for (int i = threadIdx.x; i < 16 * 64 * 4; i += blockDim.x) sm[i] = 1e-3 * (i & 7);
+    if (threadIdx.x == 0) stop = 0;
+    __syncthreads();
+    if (warp == 0) {
+        double a0 = A[r * 8 + 2 * j], a1 = A[r * 8 + 2 * j + 1];
+        double c0 = a0, c1 = a1, w0 = 0, w1 = 0, piv[8];
+        int bad = 0;
+        for (int i = 0; i < 20; ++i) { c0 = a0 + c0 * 1e-300; c1 = a1 + c1 * 1e-300; bad += chol8_inv(c0, c1, w0, w1, lane, 8, piv); }
+        long long t0 = clock64();
+        for (int i = 0; i < reps; ++i) {
+            c0 = a0 + c0 * 1e-300; c1 = a1 + c1 * 1e-300;
+            bad += chol8_inv(c0, c1, w0, w1, lane, 8, piv);
+        }
+        long long t1 = clock64();
+        __syncwarp();
+        if (lane == 0) { cyc[0] = (t1 - t0) / reps; cyc[1] = bad; stop = 1; }
+        sink[lane] = c0 + w0;
+    } else if ((mask >> warp) & 1u) {
+        double acc[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+        const uint32_t base = smem_addr(sm) + warp * 2048 + lane * 16;
+        double2 bf = make_double2(1e-3, 2e-3), af = make_double2(3e-3, 1e-3);
+        long long n = 0;
+        while (!stop) {
+#pragma unroll 2
+            for (int P = 0; P < 8; ++P) {
+                if (mode >= 2) { bf = lds128(base + (P & 3) * 512); af = lds128(base + ((P + 1) & 3) * 512); }
+                if (mode == 1 || mode == 3) {
+                    dmma(acc[0][0], acc[0][1], af.x, bf.x); dmma(acc[1][0], acc[1][1], af.y, bf.y);
+                    dmma(acc[2][0], acc[2][1], af.y, bf.x); dmma(acc[3][0], acc[3][1], af.x, bf.y);
+                } else { acc[0][0] += af.x + bf.y; }
+            }
+            ++n;
+        }
+        sink[32 + threadIdx.x] = acc[0][0] + acc[1][1] + acc[2][0] + acc[3][1] + (double)n;
+    }
+}
+
 int main()
 {
     double hA[64], hL[64], hW[64];
@@ -56,5 +101,20 @@ int main()
     }
     printf("chol8_inv (NAGP_CHOL8_OLD=%d): %lld cycles/call, bad=%lld, max |LL^T-A|/|A| = %.2e, max |WL-I| (cond <= 1e11) = %.2e, %s\n",
            NAGP_CHOL8_OLD, cycles, bad, worst1, worst2, cudaGetErrorString(cudaGetLastError()));
+    {
+        double *sink; cudaMalloc(&sink, 8192);
+        const char *mn[4] = {"idle", "DMMA", "LDS.128", "LDS.128+DMMA"};
+        struct { int threads; unsigned mask; const char *what; } cfg[] = {
+            {256, 0xfeu, "7 warps (all SMSPs)"}, {256, 0xeeu, "6 warps, none on the chain's SMSP"},
+            {256, 0x10u, "1 warp on the chain's SMSP"}, {512, 0xfffeu, "15 warps"}, {512, 0x1110u, "3 warps on the chain's SMSP"},
+            {512, 0xeeeeu, "12 warps, none on the chain's SMSP"}, {1024, 0xeeeeeeeeu, "24 warps, none on the chain's SMSP"}};
+        for (int mode = 0; mode < 4; ++mode)
+            for (auto &c : cfg) {
+                if (mode == 0 && c.mask != 0xfeu) continue;
+                bench_bg<<<1, c.threads>>>(A, cyc, 200, mode, mode == 0 ? 0u : c.mask, sink);
+                cudaMemcpy(hc, cyc, 16, cudaMemcpyDeviceToHost);
+                printf("  background %-13s on %-36s: %lld cycles/call (%s)\n", mn[mode], mode == 0 ? "-" : c.what, hc[0], cudaGetErrorString(cudaGetLastError()));
+            }
+    }
     return 0;
 }
