@@ -58,7 +58,7 @@ namespace {
 #define NAGP_V2_WARPS 8
 #endif
 #ifndef NAGP_V2_PANEL
-#define NAGP_V2_PANEL 0   // 1: the diagonal chain runs on its own warp scheduler (see "panel schedule" below); 0: rotating owner
+#define NAGP_V2_PANEL 1   // 1: the diagonal chain runs on its own warp scheduler (see "panel schedule" below); 0: rotating owner
 #endif
 constexpr int kW2 = NAGP_V2_WARPS;      // warps per CTA of the tile kernel
 constexpr int kT2 = kW2 * 32;
@@ -101,6 +101,31 @@ __device__ __forceinline__ void kloop(double (&acc)[kMaxTilesPerWarp][2][2], uin
 }
 
 #if NAGP_V2_PANEL
+// Inner loop of the panel schedule: as kloop, and with WY the warp that carries the observation vector also
+// adds L_{Jc,P} z_P to its per-lane partial sums (two FMAs on the B fragment it has loaded anyway; the four
+// lanes of a row are summed once per column).
+template <int NA, bool WY>
+__device__ __forceinline__ void kloop_p(double (&acc)[kMaxTilesPerWarp][2][2], double &ys0, double &ys1, uint32_t bp,
+                                        uint32_t yp, const uint32_t (&rowa)[kMaxTilesPerWarp], int P0, int P1)
+{
+#pragma unroll 2
+    for (int P = P0; P < P1; ++P) {
+        const uint32_t off = (uint32_t)P * 512u;
+        const double2 bf = lds128(bp + off);
+        if (WY) {
+            const double2 zf = lds128(yp + (uint32_t)P * 64u);
+            ys0 = fma(bf.x, zf.x, ys0);
+            ys1 = fma(bf.y, zf.y, ys1);
+        }
+#pragma unroll
+        for (int u = 0; u < NA; ++u) {
+            const double2 af = lds128(rowa[u] + off);
+            dmma(acc[u][0][0], acc[u][0][1], af.x, bf.x);
+            dmma(acc[u][1][0], acc[u][1][1], af.y, bf.y);
+        }
+    }
+}
+
 // Row owner, column J, its tile (J+1, J) in slot U: solve it, store it, add its square to the partial sum of
 // diagonal tile J+1 (operands straight from the accumulator registers) and put C_{J+1,J+1} in that tile's place
 // for the chain warp.
@@ -526,80 +551,124 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                 if (bad) break;
             }
         } else if (bulk) {
-            for (int J = 0; J < nt; ++J) {
-                const int NA = Ilast >= J ? (Ilast - J) / kNB + 1 : 0;   // active regular rows (I >= J)
-                const bool own_diag = (J % kNB == bi);      // its tile went to the chain warp at the end of column J-1
-                const int nsolve = own_diag ? NA - 1 : NA;  // rows strictly below the diagonal
-                const uint32_t joff = (uint32_t)J * 512u;
-                DBG_T(J, 0);
-                // (1) remaining terms of column J, C = A_IJ - sum
-                accumulate(J, pre_done, J, own_diag);
-                double c[kMaxTilesPerWarp][2], cy[2] = {0.0, 0.0};
+            // Entering column J a row owner holds, in registers, C = A_IJ - sum for its rows below diagonal J
+            // (c[u], and cyv for the observation row) and the partial sums of column J+1 over P < J (accn, ys).
+            // Per column: wait for the inverse, solve (the tile that heads the next column first: its owner folds
+            // it into the next diagonal tile and hands that to the chain warp), then with the solved tiles still in
+            // registers as A fragments add the last term of column J+1, form its C, and run the lookahead of column
+            // J+2 while the chain warp factors diagonal tile J+1.
+            const uint32_t yp = yv_a + lj * 16;
+            double c[kMaxTilesPerWarp][2], cyv = 0.0, ys0 = 0.0, ys1 = 0.0;
+            {
+                const int ns0 = (bi == 0) ? nreg - 1 : nreg;
 #pragma unroll
                 for (int u = 0; u < kMaxTilesPerWarp; ++u) {
-                    c[u][0] = 0.0; c[u][1] = 0.0;
-                    if (u < nsolve) {
-                        const double2 g2 = lds128(rowa[u] + joff);
-                        c[u][0] = g2.x - (accn[u][0][0] + accn[u][1][0]);
-                        c[u][1] = g2.y - (accn[u][0][1] + accn[u][1][1]);
-                    }
-                    accn[u][0][0] = accn[u][0][1] = accn[u][1][0] = accn[u][1][1] = 0.0;
+                    c[u][0] = c[u][1] = 0.0;
+                    if (u < ns0) { const double2 g2 = lds128(rowa[u]); c[u][0] = g2.x; c[u][1] = g2.y; }
                 }
+                if (has_y) cyv = lds64(yv_a + lr * 8);
+            }
+            auto lookahead = [&](int Jc, int P1) {
+#if NAGP_EXP == 2 || defined(NAGP_EXP_NOACC)
+                return;
+#endif
+                if (P1 <= 0) return;
+                const int NA = Ilast >= Jc ? (Ilast - Jc) / kNB + 1 : 0;
+                const uint32_t bp = tiles_a + (uint32_t)(tri(Jc) * 512 + lane * 16);
                 if (has_y) {
-                    double2 yj = lds128(yv_a + (J * 8 + 2 * lj) * 8);
-                    if (lr != 0) yj.x = yj.y = 0.0;
-                    cy[0] = yj.x - (yacc[0][0] + yacc[1][0]);
-                    cy[1] = yj.y - (yacc[0][1] + yacc[1][1]);
-                    yacc[0][0] = yacc[0][1] = yacc[1][0] = yacc[1][1] = 0.0;
+                    switch (NA) {
+                    case 0: kloop_p<0, true>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
+                    case 1: kloop_p<1, true>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
+                    case 2: kloop_p<(kMaxTilesPerWarp >= 2 ? 2 : 1), true>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
+                    case 3: kloop_p<(kMaxTilesPerWarp >= 3 ? 3 : 1), true>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
+                    case 4: kloop_p<(kMaxTilesPerWarp >= 4 ? 4 : 1), true>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
+                    case 5: kloop_p<(kMaxTilesPerWarp >= 5 ? 5 : 1), true>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
+                    default: break;
+                    }
+                } else {
+                    switch (NA) {
+                    case 1: kloop_p<1, false>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
+                    case 2: kloop_p<(kMaxTilesPerWarp >= 2 ? 2 : 1), false>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
+                    case 3: kloop_p<(kMaxTilesPerWarp >= 3 ? 3 : 1), false>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
+                    case 4: kloop_p<(kMaxTilesPerWarp >= 4 ? 4 : 1), false>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
+                    case 5: kloop_p<(kMaxTilesPerWarp >= 5 ? 5 : 1), false>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
+                    default: break;
+                    }
                 }
-                DBG_T(J, 1);
-                // (2) lookahead: column J+1 over P < J, in the shadow of the diagonal factorisation
-                if (J + 1 < nt) accumulate(J + 1, 0, J, false);
-                pre_done = J;
-                DBG_T(J, 2);
+            };
+            for (int J = 0; J < nt; ++J) {
+                const int NA = Ilast >= J ? (Ilast - J) / kNB + 1 : 0;   // active regular rows (I >= J)
+                const int nsolve = (J % kNB == bi) ? NA - 1 : NA;        // rows strictly below the diagonal
+                const uint32_t joff = (uint32_t)J * 512u;
+                const bool more = J + 1 < nt;
+                const bool owns_next = more && ((J + 1) % kNB == bi);
+                const int n2 = owns_next ? nsolve - 1 : nsolve;          // rows below diagonal J+1
+                DBG_T(J, 0);
                 asm volatile("bar.sync 1, %0;" ::"n"(kTB + 32) : "memory");
-                DBG_T(J, 3);
                 if (s_info) break;
-                // (3) triangular solve of the column: X = C * invL^T. The tile that heads the next column goes
-                //     first: its owner also folds it into the next diagonal tile and hands that to the chain warp.
+                // (1) triangular solve of the column: X = C * invL^T
                 const double2 ib = lds128(invL_a + (uint32_t)((J & 1) * 512 + lane * 16));
-                const bool owns_next = (J + 1 < nt) && ((J + 1) % kNB == bi);
-                int nrest = nsolve;
                 if (owns_next) {
-                    nrest = nsolve - 1;
                     switch (nsolve) {
                     case 1: hand_over<0>(c, accn, rowa, ib, J); break;
                     case 2: hand_over<(kMaxTilesPerWarp >= 2 ? 1 : 0)>(c, accn, rowa, ib, J); break;
                     case 3: hand_over<(kMaxTilesPerWarp >= 3 ? 2 : 0)>(c, accn, rowa, ib, J); break;
                     case 4: hand_over<(kMaxTilesPerWarp >= 4 ? 3 : 0)>(c, accn, rowa, ib, J); break;
                     case 5: hand_over<(kMaxTilesPerWarp >= 5 ? 4 : 0)>(c, accn, rowa, ib, J); break;
-                    case 6: hand_over<(kMaxTilesPerWarp >= 6 ? 5 : 0)>(c, accn, rowa, ib, J); break;
                     default: break;
                     }
                     __syncwarp();
                     asm volatile("bar.arrive 2, 64;" ::: "memory");
-                    asm volatile("bar.arrive 3, %0;" ::"n"(kTB) : "memory");
                 }
+                double x[kMaxTilesPerWarp][2];
 #pragma unroll
                 for (int u = 0; u < kMaxTilesPerWarp; ++u) {
-                    if (u < nrest) {
+                    x[u][0] = x[u][1] = 0.0;
+                    if (u < n2) {
                         // the accumulator pair (g, 2t), (g, 2t+1) is this lane's A fragment of both k-chunks
-                        double x0 = 0.0, x1 = 0.0;
-                        dmma(x0, x1, c[u][0], ib.x);
-                        dmma(x0, x1, c[u][1], ib.y);
-                        sts128(rowa[u] + joff, x0, x1);
+                        dmma(x[u][0], x[u][1], c[u][0], ib.x);
+                        dmma(x[u][0], x[u][1], c[u][1], ib.y);
+                        sts128(rowa[u] + joff, x[u][0], x[u][1]);
                     }
                 }
                 if (has_y) {
-                    double x0 = 0.0, x1 = 0.0;
-                    dmma(x0, x1, cy[0], ib.x);
-                    dmma(x0, x1, cy[1], ib.y);
-                    if (lr == 0) sts128(yv_a + (J * 8 + 2 * lj) * 8, x0, x1);
+                    // z_J = invL * cy: lane (g, t) has row g of the inverse at columns 2t, 2t+1
+                    const double ca = shfl(cyv, (2 * lj) * 4), cb = shfl(cyv, (2 * lj + 1) * 4);
+                    double part = fma(ib.y, cb, ib.x * ca);
+                    part += __shfl_xor_sync(kFull, part, 1);
+                    part += __shfl_xor_sync(kFull, part, 2);
+                    if (lj == 0) sts64(yv_a + (J * 8 + lr) * 8, part);
                 }
                 DBG_T(J, 4);
-                if (J + 1 < nt && !owns_next) asm volatile("bar.sync 3, %0;" ::"n"(kTB) : "memory");
-                else __syncwarp();
-                DBG_T(J, 5);
+                if (!more) break;
+                asm volatile("bar.sync 3, %0;" ::"n"(kTB) : "memory");   // tile (J+1, J) and the rest of column J are written
+                // (2) last term of column J+1 (A fragments = the solved tiles, still in registers) and its C
+                const double2 bf = lds128(tiles_a + (uint32_t)((tri(J + 1) + J) * 512 + lane * 16));
+                const uint32_t j1off = joff + 512u;
+#pragma unroll
+                for (int u = 0; u < kMaxTilesPerWarp; ++u) {
+                    c[u][0] = c[u][1] = 0.0;
+                    if (u < n2) {
+                        const double2 g2 = lds128(rowa[u] + j1off);
+                        dmma(accn[u][0][0], accn[u][0][1], x[u][0], bf.x);
+                        dmma(accn[u][1][0], accn[u][1][1], x[u][1], bf.y);
+                        c[u][0] = g2.x - (accn[u][0][0] + accn[u][1][0]);
+                        c[u][1] = g2.y - (accn[u][0][1] + accn[u][1][1]);
+                        accn[u][0][0] = accn[u][0][1] = accn[u][1][0] = accn[u][1][1] = 0.0;
+                    }
+                }
+                if (has_y) {
+                    const double2 zf = lds128(yp + (uint32_t)J * 64u);
+                    double sy = fma(bf.y, zf.y, ys1) + fma(bf.x, zf.x, ys0);
+                    sy += __shfl_xor_sync(kFull, sy, 1);
+                    sy += __shfl_xor_sync(kFull, sy, 2);
+                    cyv = lds64(yv_a + ((J + 1) * 8 + lr) * 8) - sy;
+                    ys0 = ys1 = 0.0;
+                }
+                DBG_T(J, 1);
+                // (3) lookahead: column J+2 over P <= J, in the shadow of the factorisation of diagonal tile J+1
+                if (J + 2 < nt) lookahead(J + 2, J + 1);
+                DBG_T(J, 2);
             }
         }
         __syncthreads();

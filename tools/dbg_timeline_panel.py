@@ -23,22 +23,9 @@ t = d[:20 * 64].reshape(20, 8, 8)[:, :, :6]
 pub = t[:, 0, 2]
 print("publish-to-publish (chain period):", np.diff(pub))
 bw = [1, 2, 3, 5, 6, 7]
+print("col | chain warp: wait for C + load, factor, store+publish | row owners (median): wait inverse + solve, wait rows + last term + C, lookahead, total")
 for J in range(20):
-    wait = t[J, 0, 1] - (t[J - 1, 0, 2] if J else t[J, 0, 1])
-    chol = t[J, 0, 2] - t[J, 0, 1]
-    own = bw[(J + 1) % 6]
-    hand = (t[J + 1, 0, 1] - t[J, own, 3]) if J < 19 else 0
     med = lambda a, b_: np.median([t[J, x, b_] - t[J, x, a] for x in bw])
-    print(f"{J:2d} | chain: wait {wait:5d} chol {chol:5d} | owner of next row: inverse seen -> chain has C {hand:5d} | rows (median): "
-          f"finish+C {med(0,1):5.0f} lookahead {med(1,2):5.0f} wait-inverse {med(2,3):5.0f} solve {med(3,4):5.0f} wait-rows {med(4,5):5.0f}")
-
-n = int(d[8100])
-print("SM 0 residents (block, warp, hardware warp slot):", sorted(((int(v) >> 32), (int(v) >> 8) & 0xff, int(v) & 0xff) for v in d[8101:8101 + min(n, 40)]))
-print("chain warp, per column [after barrier -> tile loaded -> factored -> stored+published]:")
-for J in range(20):
-    print("   ", J, int(t[J, 0, 4] - t[J, 0, 1]), int(t[J, 0, 3] - t[J, 0, 4]), int(t[J, 0, 2] - t[J, 0, 3]))
-t0 = t[0, 0, 1]
-for J in range(4):
-    print("col", J, "chain [C, published]:", (t[J, 0, 1:3] - t0).tolist())
-    for x in bw:
-        print("    row warp", x, "[top, C, lookahead done, inverse seen, solved, rows seen]:", (t[J, x, :6] - t0).tolist())
+    nxt = np.median([t[J + 1, x, 0] - t[J, x, 0] for x in bw]) if J < 19 else 0
+    print(f"{J:2d} | {int(t[J,0,4]-t[J,0,1]):5d} {int(t[J,0,3]-t[J,0,4]):5d} {int(t[J,0,2]-t[J,0,3]):4d} | "
+          f"{med(0,4):6.0f} {med(4,1):6.0f} {med(1,2):6.0f} {nxt:6.0f}")
