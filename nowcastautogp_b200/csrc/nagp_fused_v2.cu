@@ -605,7 +605,12 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                 const int n2 = owns_next ? nsolve - 1 : nsolve;          // rows below diagonal J+1
                 DBG_T(J, 0);
                 asm volatile("bar.sync 1, %0;" ::"n"(kTB + 32) : "memory");
-                if (s_info) break;
+                // The chain warp can already be factoring tile J+1 (it only needs the hand-over of one row owner): a
+                // failure it flags there must not make a late row owner leave one column before the others.
+                {
+                    const int fl = s_info;
+                    if (fl && ((fl - 1) >> 3) <= J) break;
+                }
                 // (1) triangular solve of the column: X = C * invL^T
                 const double2 ib = lds128(invL_a + (uint32_t)((J & 1) * 512 + lane * 16));
                 if (owns_next) {
