@@ -459,7 +459,7 @@ def main():
                          "peak": peak_tf, "peak_source": "profiles/r01_fp64_peak.json (DMMA m8n8k4 measured on this "
                          "pool's B200; MEASURED_PEAKS.json has no FP64 entry)", "unit": "TFLOP/s",
                          "frac": achieved / peak_tf,
-                         "traffic": 2542592, "traffic_source": "profiles/r01_v2_fused_summary.csv: dram__bytes_read.sum + "
+                         "traffic": 2084608, "traffic_source": "profiles/r01_v2g_panel_summary.csv: dram__bytes_read.sum + "
                          "dram__bytes_write.sum of one launch (bytes; the Gram and the factor never leave shared memory)",
                          "kernel_ms": ms_kernel,
                          "flops_per_launch": fl},
