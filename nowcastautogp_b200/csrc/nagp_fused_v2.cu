@@ -301,7 +301,29 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
         EvalCtx cx;
         cx.th = th; cx.tt = tt; cx.tab = tab; cx.sig = sig;
         cx.step = a.step; cx.G = G; cx.Q = Q; cx.grid = a.g != nullptr;
-        {
+        if (single_table) {
+            // One stationary leaf (most particles of a fitted ensemble): an entry is a table look-up by lag. One tile per
+            // warp and iteration, four iterations in flight: the loop is a chain of dependent shared-memory loads
+            // (tile index -> grid indices -> table) and nothing else.
+            const int gr = lane >> 2, gc = (lane & 3) * 2;
+#pragma unroll 4
+            for (int tix = warp; tix < ntiles; tix += kW2) {
+                const int I = s_ti[tix], J = tix - tri(I);
+                const int i = I * 8 + gr, j0 = J * 8 + gc;
+                const int gi = gg[i];
+                const int2 gj = *reinterpret_cast<const int2 *>(gg + j0);
+                const int l0 = gi - gj.x, l1 = gi - gj.y;
+                double v0 = tab[l0 < 0 ? -l0 : l0], v1 = tab[l1 < 0 ? -l1 : l1];
+                if (!(I > J && I * 8 + 7 < q)) {        // diagonal tile or padding
+                    const bool ri = i < q;
+                    if (!(ri && j0 < q)) v0 = (i == j0) ? 1.0 : 0.0;
+                    else if (i == j0) v0 += (i < m) ? d_lo : d_hi;
+                    if (!(ri && j0 + 1 < q)) v1 = (i == j0 + 1) ? 1.0 : 0.0;
+                    else if (i == j0 + 1) v1 += (i < m) ? d_lo : d_hi;
+                }
+                *reinterpret_cast<double2 *>(tiles + tix * 64 + lane * 2) = make_double2(v0, v1);
+            }
+        } else {
             const int gr = lane >> 2, gc = (lane & 3) * 2;
             for (int t0 = warp * 2; t0 < ntiles; t0 += kW2 * 2) {
                 int ii[4], jj[4], lag[4], tixs[2];
@@ -331,12 +353,7 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                     for (int x = 0; x < 4; ++x) out[x] = 0.0;
                 } else
 #endif
-                if (single_table) {
-#pragma unroll
-                    for (int x = 0; x < 4; ++x) out[x] = tab[lag[x]];
-                } else {
-                    tree_eval4(tp, cx, ii, jj, lag, out);
-                }
+                tree_eval4(tp, cx, ii, jj, lag, out);
                 if (!interior) {
 #pragma unroll
                     for (int x = 0; x < 4; ++x) {
