@@ -537,8 +537,12 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
         // ---- panel schedule -----------------------------------------------------------------------------
         // Named barriers: 1 = "inverse of diagonal tile J published" (chain warp arrives, row owners wait),
         // 2 = "C_JJ is in its tile" (the owner of row J arrives, the chain warp waits), 3 = "tile (J+1, J) is
-        // written" among the row owners (its producer only arrives). Two inverse buffers: the chain may publish
-        // column J+1 while slow rows still solve column J.
+        // written" and 4 = "tile (J+2, J) is written" among the row owners (the producer only arrives, the other
+        // five wait: nobody waits for a whole column of somebody else's rows; everything else written in column J
+        // is first read after barrier 1 of column J+1, which all row owners reach after their stores). A producer
+        // meets its barrier next as a waiting member after barrier 1 of the next column, by which time the phase
+        // it arrived in is complete. Two inverse buffers: the chain may publish column J+1 while slow rows still
+        // solve column J.
         if (role == -1) {
             for (int J = 0; J < nt; ++J) {
                 if (J > 0) asm volatile("bar.sync 2, 64;" ::: "memory");
@@ -641,16 +645,23 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                     }
                     __syncwarp();
                     asm volatile("bar.arrive 2, 64;" ::: "memory");
+                    asm volatile("bar.arrive 3, %0;" ::"n"(kTB) : "memory");    // tile (J+1, J) is written
                 }
+                // topmost row first: the owner of row J+2 releases the others' lookahead as soon as tile (J+2, J) is stored
+                const bool owns_next2 = (J + 2 < nt) && ((J + 2) % kNB == bi);
                 double x[kMaxTilesPerWarp][2];
 #pragma unroll
-                for (int u = 0; u < kMaxTilesPerWarp; ++u) {
+                for (int u = kMaxTilesPerWarp - 1; u >= 0; --u) {
                     x[u][0] = x[u][1] = 0.0;
                     if (u < n2) {
                         // the accumulator pair (g, 2t), (g, 2t+1) is this lane's A fragment of both k-chunks
                         dmma(x[u][0], x[u][1], c[u][0], ib.x);
                         dmma(x[u][0], x[u][1], c[u][1], ib.y);
                         sts128(rowa[u] + joff, x[u][0], x[u][1]);
+                        if (owns_next2 && u == n2 - 1) {
+                            __syncwarp();
+                            asm volatile("bar.arrive 4, %0;" ::"n"(kTB) : "memory");
+                        }
                     }
                 }
                 if (has_y) {
@@ -663,7 +674,8 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                 }
                 DBG_T(J, 4);
                 if (!more) break;
-                asm volatile("bar.sync 3, %0;" ::"n"(kTB) : "memory");   // tile (J+1, J) and the rest of column J are written
+                if (!owns_next) asm volatile("bar.sync 3, %0;" ::"n"(kTB) : "memory");   // tile (J+1, J) is written (its owner only arrives)
+                else __syncwarp();
                 // (2) last term of column J+1 (A fragments = the solved tiles, still in registers) and its C
                 const double2 bf = lds128(tiles_a + (uint32_t)((tri(J + 1) + J) * 512 + lane * 16));
                 const uint32_t j1off = joff + 512u;
@@ -689,7 +701,10 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                 }
                 DBG_T(J, 1);
                 // (3) lookahead: column J+2 over P <= J, in the shadow of the factorisation of diagonal tile J+1
-                if (J + 2 < nt) lookahead(J + 2, J + 1);
+                if (J + 2 < nt) {
+                    if (!owns_next2) asm volatile("bar.sync 4, %0;" ::"n"(kTB) : "memory");   // tile (J+2, J) is written
+                    lookahead(J + 2, J + 1);
+                }
                 DBG_T(J, 2);
             }
         }
