@@ -2,20 +2,21 @@
 // logML / predictive moments, one persistent CTA stream of (scenario, particle) instances.
 //
 // Layout: the lower triangle of the joint q x q Gram lives in shared memory as 8x8 FP64 tiles
-// (tile-packed, 512 B each). The factorisation is left-looking by tile column: every warp owns the
-// tiles I == warp (mod 8) of the current column, accumulates sum_P L_IP L_JP^T with DMMA
-// (mma.sync m8n8k4 f64, accumulators in registers, operands fetched as one 16-byte LDS per lane
-// from the row-major tile), the warp owning the diagonal tile factors it in registers
-// with shuffles while building its inverse by the same row operations, and the column's
-// triangular solve is one more DMMA pair against that inverse.
+// (tile-packed, 512 B each). The factorisation is left-looking by tile column on DMMA (mma.sync m8n8k4 f64,
+// accumulators in registers, operands fetched as one 16-byte LDS per lane from the row-major tile). Panel
+// schedule (default): one chain warp per CTA, alone with an idle warp on hardware scheduler 0, factors every
+// diagonal tile in registers with shuffles while building its inverse by the same row operations; six row-owning
+// warps accumulate sum_P L_IP L_JP^T with one column of lookahead, solve their tiles of the column with one DMMA
+// pair against that inverse, and add the last term of the next column with the solved tiles still in registers.
+// (NAGP_V2_PANEL=0 builds the earlier schedule: eight row owners, the owner of a diagonal tile factors it.)
 //
 // One tile layout serves as A operand, B operand and accumulator: a sum over k may run in any order, so
 // the two k-chunks of a DMMA pair are taken as the even columns (k-slot t <-> column 2t) and the odd
 // columns (k-slot t <-> column 2t+1) of the tile instead of columns 0-3 and 4-7. Lane (g, t) then needs
 // elements (g, 2t) and (g, 2t+1) of a tile as operand — the very pair it holds as accumulator — so tiles
 // are plain row-major, every fragment is one 16-byte access at lane * 16, and no value ever moves
-// between lanes on its way from accumulator to operand. The observation vector rides along
-// as a virtual tile row, so z = L^-1 y needs no separate solve.
+// between lanes on its way from accumulator to operand. The observation vector is carried by one row owner
+// (two FMAs per term on the B fragment it has loaded anyway), so z = L^-1 y needs no separate solve.
 //
 // FP64 has no tcgen05/UMMA kind on sm_100a, so DMMA is the tensor path for this workload; measured
 // DMMA peak on this pool's B200: 37.1 TFLOP/s (profiles/r01_fp64_peak.json).
