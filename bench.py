@@ -69,7 +69,15 @@ def clocks_sampler_start():
     return p, f.name
 
 
-def clocks_sampler_stop(p, path, dev_index):
+def _sample_lines(path):
+    try:
+        with open(path) as fh:
+            return sum(1 for _ in fh)
+    except OSError:
+        return 0
+
+
+def clocks_sampler_stop(p, path, dev_index, skip_lines=0):
     out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
     if p is None:
         return out
@@ -81,7 +89,9 @@ def clocks_sampler_stop(p, path, dev_index):
     sm, reasons, mx = [], set(), None
     names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
     try:
-        for line in open(path):
+        for ln, line in enumerate(open(path)):
+            if ln < skip_lines:
+                continue
             parts = [x.strip() for x in line.split(",")]
             if len(parts) < 9 or parts[0] != str(dev_index):
                 continue
@@ -292,11 +302,26 @@ def main():
             ms = float(t_.item())
         return ms
 
+    # clocks: nvidia-smi samples every 100 ms and needs a moment to start, the timed region is tens of ms. Wait for
+    # its first line (idle), time the steps, then keep rank 0's GPU under the same kernel until a few samples have
+    # been taken under load; only samples from the start of the timed region on are used.
     sampler, spath = clocks_sampler_start() if rank == 0 else (None, None)
+    skip = 0
+    if sampler is not None:
+        t_wait = time.time() + 3.0
+        while _sample_lines(spath) == 0 and time.time() < t_wait:
+            time.sleep(0.02)
+        skip = _sample_lines(spath)
     l0 = eng.launch_count
     ms_step = timed(step_device, args.steps, args.warmup)
     launches = (eng.launch_count - l0) // (args.steps + args.warmup) * args.steps
-    clocks = clocks_sampler_stop(sampler, spath, local_rank) if rank == 0 else None
+    if sampler is not None:
+        n_dev = max(1, torch.cuda.device_count())
+        t_wait = time.time() + 1.5
+        while _sample_lines(spath) < skip + 3 * n_dev and time.time() < t_wait:
+            kernel_only()
+            torch.cuda.synchronize()
+    clocks = clocks_sampler_stop(sampler, spath, local_rank, skip) if rank == 0 else None
     ms_kernel = timed(kernel_only, args.steps, 1)
     if args.only_value:
         if rank == 0:

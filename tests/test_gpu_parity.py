@@ -196,3 +196,32 @@ def test_bad_program_rejected(engine):
     ens.prog[0] = 6  # Plus with empty stack
     with pytest.raises(NagpError):
         engine.logml_batch(ens, np.linspace(0, 1, 5), np.zeros(5))
+
+
+def test_failures_in_later_tile_columns_mixed_batch(veng, oracle):
+    # Half of a large batch fails (negative "noise" makes the Gram indefinite) somewhere inside the factorisation,
+    # the other half is fine: every instance must report the oracle's leading-minor index or the oracle's value,
+    # and the kernel must get through the batch (two resident matrices per SM, failures flagged by the chain warp
+    # while the row owners are a column behind).
+    n, P, K = 150, 32, 12
+    w = syn.make_workload(n, 1, 9, K, P, seed=77)
+    theta_k, noise_k = syn.perturbed_theta(w.ens, K, seed=5)
+    noise_k = np.array(noise_k, copy=True)
+    noise_k[:, 1::2] = -0.02 - 0.01 * np.arange(P // 2)[None, :]
+    got = veng.forecast_instances(w.ens, n, 1, 9, w.t, w.y1, w.y2, w.logw0, w.ya, w.yb, g=w.g, step=w.step,
+                                  theta=theta_k, noise=noise_k)
+    info = np.asarray(got["info"]).reshape(K, P)
+    assert (info[:, 0::2] == 0).all()
+    assert (info[:, 1::2] > 0).all() and (info[:, 1::2] > 8).any()      # some fail beyond the first tile column
+    logw = np.asarray(got["logw"]).reshape(K, P)
+    assert np.isnan(logw[:, 1::2]).all() and np.isfinite(logw[:, 0::2]).all()
+    for s in (0, K - 1):
+        y = np.concatenate([w.y1, w.y2[s]])
+        for p in range(P):
+            prog, _ = kn.flatten(w.trees[p])
+            off = w.ens.theta_off
+            r = oracle.instance_joint(prog, theta_k[s, off[p]:off[p + 1]], noise_k[s, p], n, 1, 9, w.t, y, w.ya, w.yb,
+                                      g=w.g, step=w.step)
+            assert r["info"] == info[s, p], (s, p)
+            if r["info"] == 0:
+                assert rel(logw[s, p], w.logw0[p] + r["logml_m"] - r["logml_n"]) < RTOL
