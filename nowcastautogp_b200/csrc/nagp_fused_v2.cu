@@ -80,13 +80,18 @@ constexpr int kNB = kW2;
 #endif
 constexpr int kTB = kNB * 32;
 constexpr int kMaxTilesPerWarp = (29 + kNB - 1) / kNB;   // ceil(nt / kNB), nt <= 29
+// The kernel is instantiated per KM = register slots (tile rows) per row-owning warp: the full size and, for matrices
+// of at most 4 kNB tile rows (q <= 192 in the panel schedule: every weekly-series workload), a 4-slot build whose
+// accumulator / C / solved-tile arrays take 16 registers less (5.59 -> 5.43 ms: at 128 registers that is the
+// difference between the scheduler having room to hoist loads and not).
+constexpr int kSmallTilesPerWarp = kMaxTilesPerWarp < 4 ? kMaxTilesPerWarp : 4;
 
 // DMMA inner loop of the left-looking update for NA tile rows of one warp: per P one 16-byte LDS for
 // the shared B fragment (tile (Jc, P)), and per row one 16-byte LDS + two DMMAs (one per k-chunk, on
 // separate accumulator chains).
-template <int NA>
-__device__ __forceinline__ void kloop(double (&acc)[kMaxTilesPerWarp][2][2], uint32_t bp,
-                                      const uint32_t (&rowa)[kMaxTilesPerWarp], int P0, int P1)
+template <int KM, int NA>
+__device__ __forceinline__ void kloop(double (&acc)[KM][2][2], uint32_t bp,
+                                      const uint32_t (&rowa)[KM], int P0, int P1)
 {
 #pragma unroll 2
     for (int P = P0; P < P1; ++P) {
@@ -105,9 +110,9 @@ __device__ __forceinline__ void kloop(double (&acc)[kMaxTilesPerWarp][2][2], uin
 // Inner loop of the panel schedule: as kloop, and with WY the warp that carries the observation vector also
 // adds L_{Jc,P} z_P to its per-lane partial sums (two FMAs on the B fragment it has loaded anyway; the four
 // lanes of a row are summed once per column).
-template <int NA, bool WY>
-__device__ __forceinline__ void kloop_p(double (&acc)[kMaxTilesPerWarp][2][2], double &ys0, double &ys1, uint32_t bp,
-                                        uint32_t yp, const uint32_t (&rowa)[kMaxTilesPerWarp], int P0, int P1)
+template <int KM, int NA, bool WY>
+__device__ __forceinline__ void kloop_p(double (&acc)[KM][2][2], double &ys0, double &ys1, uint32_t bp,
+                                        uint32_t yp, const uint32_t (&rowa)[KM], int P0, int P1)
 {
 #pragma unroll 2
     for (int P = P0; P < P1; ++P) {
@@ -130,9 +135,9 @@ __device__ __forceinline__ void kloop_p(double (&acc)[kMaxTilesPerWarp][2][2], d
 // Row owner, column J, its tile (J+1, J) in slot U: solve it, store it, add its square to the partial sum of
 // diagonal tile J+1 (operands straight from the accumulator registers) and put C_{J+1,J+1} in that tile's place
 // for the chain warp.
-template <int U>
-__device__ __forceinline__ void hand_over(const double (&c)[kMaxTilesPerWarp][2], double (&acc)[kMaxTilesPerWarp][2][2],
-                                          const uint32_t (&rowa)[kMaxTilesPerWarp], const double2 ib, int J)
+template <int KM, int U>
+__device__ __forceinline__ void hand_over(const double (&c)[KM][2], double (&acc)[KM][2][2],
+                                          const uint32_t (&rowa)[KM], const double2 ib, int J)
 {
     const double2 g2 = lds128(rowa[U] + (uint32_t)(J + 1) * 512u);
     double x0 = 0.0, x1 = 0.0;
@@ -157,7 +162,7 @@ struct V2Layout {
 
 // KEEP: also write the factor, z and the inverse diagonal tiles to HBM for the gradient kernel (a separate
 // instantiation, so the forecast path does not carry that code: it measured 4 % slower with it inline).
-template <bool KEEP>
+template <bool KEEP, int KM>
 __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, const V2Layout lay)
 {
     extern __shared__ __align__(16) double smem[];
@@ -397,16 +402,16 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
         const int Ilast = bi + (nreg - 1) * kNB;
         const bool has_y = (bi == nt % kNB);
         const uint32_t tiles_a = smem_addr(tiles), yv_a = smem_addr(yv), invL_a = smem_addr(invL);
-        uint32_t rowa[kMaxTilesPerWarp];        // shared address of this lane's fragment in tile (I_u, 0)
+        uint32_t rowa[KM];        // shared address of this lane's fragment in tile (I_u, 0)
 #pragma unroll
-        for (int u = 0; u < kMaxTilesPerWarp; ++u) {
+        for (int u = 0; u < KM; ++u) {
             const int I = Ilast - u * kNB;
             rowa[u] = tiles_a + (uint32_t)(tri(I > 0 ? I : 0) * 512 + lane * 16);
         }
-        double accn[kMaxTilesPerWarp][2][2];   // [slot][k-chunk chain][acc regs] partial sums of the current column
+        double accn[KM][2][2];   // [slot][k-chunk chain][acc regs] partial sums of the current column
         double yacc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
-        for (int u = 0; u < kMaxTilesPerWarp; ++u) { accn[u][0][0] = accn[u][0][1] = accn[u][1][0] = accn[u][1][1] = 0.0; }
+        for (int u = 0; u < KM; ++u) { accn[u][0][0] = accn[u][0][1] = accn[u][1][0] = accn[u][1][1] = 0.0; }
         int pre_done = 0;                       // terms P < pre_done are already in accn / yacc
 
         // accumulate sum_{P0 <= P < P1} L_IP L_{Jc,P}^T for the owned rows I >= Jc (and the observation row)
@@ -419,14 +424,14 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
             const int NA = (Ilast >= Jc ? (Ilast - Jc) / kNB + 1 : 0) - (skip_top ? 1 : 0);
             const uint32_t bp = tiles_a + (uint32_t)(tri(Jc) * 512 + lane * 16);
             switch (NA) {
-            case 1: kloop<(kMaxTilesPerWarp >= 1 ? 1 : 1)>(accn, bp, rowa, P0, P1); break;
-            case 2: kloop<(kMaxTilesPerWarp >= 2 ? 2 : 1)>(accn, bp, rowa, P0, P1); break;
-            case 3: kloop<(kMaxTilesPerWarp >= 3 ? 3 : 1)>(accn, bp, rowa, P0, P1); break;
-            case 4: kloop<(kMaxTilesPerWarp >= 4 ? 4 : 1)>(accn, bp, rowa, P0, P1); break;
-            case 5: kloop<(kMaxTilesPerWarp >= 5 ? 5 : 1)>(accn, bp, rowa, P0, P1); break;
-            case 6: kloop<(kMaxTilesPerWarp >= 6 ? 6 : 1)>(accn, bp, rowa, P0, P1); break;
-            case 7: kloop<(kMaxTilesPerWarp >= 7 ? 7 : 1)>(accn, bp, rowa, P0, P1); break;
-            case 8: kloop<(kMaxTilesPerWarp >= 8 ? 8 : 1)>(accn, bp, rowa, P0, P1); break;
+            case 1: kloop<KM, (KM >= 1 ? 1 : 1)>(accn, bp, rowa, P0, P1); break;
+            case 2: kloop<KM, (KM >= 2 ? 2 : 1)>(accn, bp, rowa, P0, P1); break;
+            case 3: kloop<KM, (KM >= 3 ? 3 : 1)>(accn, bp, rowa, P0, P1); break;
+            case 4: kloop<KM, (KM >= 4 ? 4 : 1)>(accn, bp, rowa, P0, P1); break;
+            case 5: kloop<KM, (KM >= 5 ? 5 : 1)>(accn, bp, rowa, P0, P1); break;
+            case 6: kloop<KM, (KM >= 6 ? 6 : 1)>(accn, bp, rowa, P0, P1); break;
+            case 7: kloop<KM, (KM >= 7 ? 7 : 1)>(accn, bp, rowa, P0, P1); break;
+            case 8: kloop<KM, (KM >= 8 ? 8 : 1)>(accn, bp, rowa, P0, P1); break;
             default: break;
             }
             if (has_y) {
@@ -449,10 +454,10 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
             // (1) remaining terms of column J, (2) C = A_IJ - sum
             DBG_T(J, 0);
             accumulate(J, pre_done, J, false);
-            double c[kMaxTilesPerWarp][2], cy[2] = {0.0, 0.0}, d0 = 0.0, d1 = 0.0;
+            double c[KM][2], cy[2] = {0.0, 0.0}, d0 = 0.0, d1 = 0.0;
             const uint32_t joff = (uint32_t)J * 512u;
 #pragma unroll
-            for (int u = 0; u < kMaxTilesPerWarp; ++u) {
+            for (int u = 0; u < KM; ++u) {
                 c[u][0] = 0.0; c[u][1] = 0.0;
                 if (u < NA) {
                     const double2 g2 = lds128(rowa[u] + joff);
@@ -513,7 +518,7 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                 const double2 ib = lds128(invL_a + lane * 16);
                 const int nsolve = owner ? NA - 1 : NA;   // rows strictly below the diagonal
 #pragma unroll
-                for (int u = 0; u < kMaxTilesPerWarp; ++u) {
+                for (int u = 0; u < KM; ++u) {
                     if (u < nsolve) {
                         // the accumulator pair (g, 2t), (g, 2t+1) is this lane's A fragment of both k-chunks
                         double x0 = 0.0, x1 = 0.0;
@@ -580,11 +585,11 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
             // registers as A fragments add the last term of column J+1, form its C, and run the lookahead of column
             // J+2 while the chain warp factors diagonal tile J+1.
             const uint32_t yp = yv_a + lj * 16;
-            double c[kMaxTilesPerWarp][2], cyv = 0.0, ys0 = 0.0, ys1 = 0.0;
+            double c[KM][2], cyv = 0.0, ys0 = 0.0, ys1 = 0.0;
             {
                 const int ns0 = (bi == 0) ? nreg - 1 : nreg;
 #pragma unroll
-                for (int u = 0; u < kMaxTilesPerWarp; ++u) {
+                for (int u = 0; u < KM; ++u) {
                     c[u][0] = c[u][1] = 0.0;
                     if (u < ns0) { const double2 g2 = lds128(rowa[u]); c[u][0] = g2.x; c[u][1] = g2.y; }
                 }
@@ -599,21 +604,21 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                 const uint32_t bp = tiles_a + (uint32_t)(tri(Jc) * 512 + lane * 16);
                 if (has_y) {
                     switch (NA) {
-                    case 0: kloop_p<0, true>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
-                    case 1: kloop_p<1, true>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
-                    case 2: kloop_p<(kMaxTilesPerWarp >= 2 ? 2 : 1), true>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
-                    case 3: kloop_p<(kMaxTilesPerWarp >= 3 ? 3 : 1), true>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
-                    case 4: kloop_p<(kMaxTilesPerWarp >= 4 ? 4 : 1), true>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
-                    case 5: kloop_p<(kMaxTilesPerWarp >= 5 ? 5 : 1), true>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
+                    case 0: kloop_p<KM, 0, true>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
+                    case 1: kloop_p<KM, 1, true>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
+                    case 2: kloop_p<KM, (KM >= 2 ? 2 : 1), true>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
+                    case 3: kloop_p<KM, (KM >= 3 ? 3 : 1), true>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
+                    case 4: kloop_p<KM, (KM >= 4 ? 4 : 1), true>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
+                    case 5: kloop_p<KM, (KM >= 5 ? 5 : 1), true>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
                     default: break;
                     }
                 } else {
                     switch (NA) {
-                    case 1: kloop_p<1, false>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
-                    case 2: kloop_p<(kMaxTilesPerWarp >= 2 ? 2 : 1), false>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
-                    case 3: kloop_p<(kMaxTilesPerWarp >= 3 ? 3 : 1), false>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
-                    case 4: kloop_p<(kMaxTilesPerWarp >= 4 ? 4 : 1), false>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
-                    case 5: kloop_p<(kMaxTilesPerWarp >= 5 ? 5 : 1), false>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
+                    case 1: kloop_p<KM, 1, false>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
+                    case 2: kloop_p<KM, (KM >= 2 ? 2 : 1), false>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
+                    case 3: kloop_p<KM, (KM >= 3 ? 3 : 1), false>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
+                    case 4: kloop_p<KM, (KM >= 4 ? 4 : 1), false>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
+                    case 5: kloop_p<KM, (KM >= 5 ? 5 : 1), false>(accn, ys0, ys1, bp, yp, rowa, 0, P1); break;
                     default: break;
                     }
                 }
@@ -637,11 +642,11 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                 const double2 ib = lds128(invL_a + (uint32_t)((J & 1) * 512 + lane * 16));
                 if (owns_next) {
                     switch (nsolve) {
-                    case 1: hand_over<0>(c, accn, rowa, ib, J); break;
-                    case 2: hand_over<(kMaxTilesPerWarp >= 2 ? 1 : 0)>(c, accn, rowa, ib, J); break;
-                    case 3: hand_over<(kMaxTilesPerWarp >= 3 ? 2 : 0)>(c, accn, rowa, ib, J); break;
-                    case 4: hand_over<(kMaxTilesPerWarp >= 4 ? 3 : 0)>(c, accn, rowa, ib, J); break;
-                    case 5: hand_over<(kMaxTilesPerWarp >= 5 ? 4 : 0)>(c, accn, rowa, ib, J); break;
+                    case 1: hand_over<KM, 0>(c, accn, rowa, ib, J); break;
+                    case 2: hand_over<KM, (KM >= 2 ? 1 : 0)>(c, accn, rowa, ib, J); break;
+                    case 3: hand_over<KM, (KM >= 3 ? 2 : 0)>(c, accn, rowa, ib, J); break;
+                    case 4: hand_over<KM, (KM >= 4 ? 3 : 0)>(c, accn, rowa, ib, J); break;
+                    case 5: hand_over<KM, (KM >= 5 ? 4 : 0)>(c, accn, rowa, ib, J); break;
                     default: break;
                     }
                     __syncwarp();
@@ -650,9 +655,9 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                 }
                 // topmost row first: the owner of row J+2 releases the others' lookahead as soon as tile (J+2, J) is stored
                 const bool owns_next2 = (J + 2 < nt) && ((J + 2) % kNB == bi);
-                double x[kMaxTilesPerWarp][2];
+                double x[KM][2];
 #pragma unroll
-                for (int u = kMaxTilesPerWarp - 1; u >= 0; --u) {
+                for (int u = KM - 1; u >= 0; --u) {
                     x[u][0] = x[u][1] = 0.0;
                     if (u < n2) {
                         // the accumulator pair (g, 2t), (g, 2t+1) is this lane's A fragment of both k-chunks
@@ -681,7 +686,7 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                 const double2 bf = lds128(tiles_a + (uint32_t)((tri(J + 1) + J) * 512 + lane * 16));
                 const uint32_t j1off = joff + 512u;
 #pragma unroll
-                for (int u = 0; u < kMaxTilesPerWarp; ++u) {
+                for (int u = 0; u < KM; ++u) {
                     c[u][0] = c[u][1] = 0.0;
                     if (u < n2) {
                         const double2 g2 = lds128(rowa[u] + j1off);
@@ -829,7 +834,7 @@ V2Plan plan_fused_v2(int q, int G, int ntheta_cap, int ntab_cap, int ncp_cap, in
     size_t total_aux = sz[0] + sz[1] + sz[2] + sz[3] + sz[4];
     cudaFuncAttributes fa{};
     size_t static_smem = 2560 + 1024;
-    if (cudaFuncGetAttributes(&fa, fused_v2_kernel<true>) == cudaSuccess) static_smem = fa.sharedSizeBytes + 1024;   // + per-CTA reservation
+    if (cudaFuncGetAttributes(&fa, fused_v2_kernel<true, kMaxTilesPerWarp>) == cudaSuccess) static_smem = fa.sharedSizeBytes + 1024;   // + per-CTA reservation
     else cudaGetLastError();
     // budget: 2 CTAs/SM if the mandatory part allows it, else everything the opt-in limit gives
     size_t two = (size_t)smem_per_sm / 2;
@@ -852,8 +857,8 @@ V2Plan plan_fused_v2(int q, int G, int ntheta_cap, int ntab_cap, int ncp_cap, in
 int fused_v2_grid(const V2Plan &pl, int64_t B, int num_sms)
 {
     int per_sm = 0;
-    cudaFuncSetAttribute(fused_v2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_v2_kernel<true>, kT2, pl.smem_bytes) != cudaSuccess ||
+    cudaFuncSetAttribute(fused_v2_kernel<true, kMaxTilesPerWarp>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_v2_kernel<true, kMaxTilesPerWarp>, kT2, pl.smem_bytes) != cudaSuccess ||
         per_sm < 1) {
         cudaGetLastError();
         per_sm = 1;
@@ -877,11 +882,12 @@ cudaError_t launch_fused_v2(const FusedArgs &a, const V2Plan &pl, char *scratch,
     lay.scratch_stride = pl.scratch_stride;
     lay.scratch = scratch;
     const bool keep = a.Lkeep != nullptr;
-    cudaError_t e = keep ? cudaFuncSetAttribute(fused_v2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes)
-                         : cudaFuncSetAttribute(fused_v2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
+    const bool small = pl.nt <= kSmallTilesPerWarp * kNB;      // fewer register slots per row owner suffice
+    auto kern = keep ? (small ? fused_v2_kernel<true, kSmallTilesPerWarp> : fused_v2_kernel<true, kMaxTilesPerWarp>)
+                     : (small ? fused_v2_kernel<false, kSmallTilesPerWarp> : fused_v2_kernel<false, kMaxTilesPerWarp>);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (e != cudaSuccess) return e;
-    if (keep) fused_v2_kernel<true><<<grid, kT2, pl.smem_bytes, stream>>>(a, lay);
-    else fused_v2_kernel<false><<<grid, kT2, pl.smem_bytes, stream>>>(a, lay);
+    kern<<<grid, kT2, pl.smem_bytes, stream>>>(a, lay);
     return cudaGetLastError();
 }
 

@@ -1,2 +1,3 @@
+for K in 9 50; do timeout 15 python tools/hang_probe.py $K 2>&1 | tail -1; done
 timeout 40 python bench.py --steps 10 --warmup 3 --only-value
-timeout 200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_edges.py -x -q 2>&1 | tail -2
+timeout 400 python -m pytest tests -x -q -m gpu 2>&1 | tail -2
