@@ -4,9 +4,9 @@
 // Layout: the lower triangle of the joint q x q Gram lives in shared memory as 8x8 FP64 tiles
 // (tile-packed, 512 B each). The factorisation is left-looking by tile column on DMMA (mma.sync m8n8k4 f64,
 // accumulators in registers, operands fetched as one 16-byte LDS per lane from the row-major tile). Panel
-// schedule (default): one chain warp per CTA, alone with an idle warp on hardware scheduler 0, factors every
-// diagonal tile in registers with shuffles while building its inverse by the same row operations; six row-owning
-// warps accumulate sum_P L_IP L_JP^T with one column of lookahead, solve their tiles of the column with one DMMA
+// schedule (default): one chain warp per CTA, on hardware scheduler 0 (shared with the other resident CTA's chain
+// warp), factors every diagonal tile in registers with shuffles while building its inverse by the same row
+// operations; seven row-owning warps accumulate sum_P L_IP L_JP^T with one column of lookahead, solve their tiles of the column with one DMMA
 // pair against that inverse, and add the last term of the next column with the solved tiles still in registers.
 // (NAGP_V2_PANEL=0 builds the earlier schedule: eight row owners, the owner of a diagonal tile factors it.)
 //
@@ -67,12 +67,14 @@ constexpr int kT2 = kW2 * 32;
 // Panel schedule: a dependent FP64 chain shares its scheduler's issue slots and FP64 pipe with whatever else
 // runs there (tools/chol8_bench2.cu: the 8x8 factorisation takes 1.2 k cycles next to idle warps or to busy
 // warps on the OTHER three schedulers, 1.8 k next to one DMMA-issuing warp on its own scheduler, 4.4 k next to
-// three), so the chain gets a scheduler to itself: one warp of scheduler 0 factors every diagonal tile and does nothing
-// else, the other warp of that scheduler sits the factorisation out, and the six warps of schedulers 1-3 own the tile
-// rows (roles are dealt by hardware warp slot at kernel start).
+// three), so the chain is kept away from the row owners as far as possible: one warp of scheduler 0 factors every
+// diagonal tile and does nothing else, the six warps of schedulers 1-3 own tile rows, and so does the chain's scheduler
+// mate (NAGP_V2_PANEL_ROWS=6 leaves that warp idle: same speed at equal register budget, but seven row owners need
+// only three register slots each at 21 tile rows). Roles are dealt by hardware warp slot at kernel start, so the chain
+// warps of both resident CTAs sit on the same scheduler.
 static_assert(kW2 == 8, "the panel schedule assumes 8 warps: two per scheduler");
 #ifndef NAGP_V2_PANEL_ROWS
-#define NAGP_V2_PANEL_ROWS 6            // 6: the second warp of the chain's scheduler idles; 7: it owns rows too
+#define NAGP_V2_PANEL_ROWS 7            // 6: the second warp of the chain's scheduler idles; 7: it owns rows too
 #endif
 constexpr int kNB = NAGP_V2_PANEL_ROWS; // row-owning warps
 #else
@@ -80,11 +82,12 @@ constexpr int kNB = kW2;
 #endif
 constexpr int kTB = kNB * 32;
 constexpr int kMaxTilesPerWarp = (29 + kNB - 1) / kNB;   // ceil(nt / kNB), nt <= 29
-// The kernel is instantiated per KM = register slots (tile rows) per row-owning warp: the full size and, for matrices
-// of at most 4 kNB tile rows (q <= 192 in the panel schedule: every weekly-series workload), a 4-slot build whose
-// accumulator / C / solved-tile arrays take 16 registers less (5.59 -> 5.43 ms: at 128 registers that is the
-// difference between the scheduler having room to hoist loads and not).
-constexpr int kSmallTilesPerWarp = kMaxTilesPerWarp < 4 ? kMaxTilesPerWarp : 4;
+// The kernel is instantiated per KM = register slots (tile rows) per row-owning warp, 3, 4 and the full size: the
+// accumulator / C / solved-tile arrays of a slot take 16 registers, and at 128 registers that is the difference
+// between ptxas having room to hoist loads and not (six row owners: 5 slots 5.59 ms, 4 slots 5.43 ms; seven row
+// owners with 3 slots — 21 tile rows, q <= 168: the weekly-series workloads — 116 registers, 5.34 ms).
+constexpr int kSlots3 = kMaxTilesPerWarp < 3 ? kMaxTilesPerWarp : 3;
+constexpr int kSlots4 = kMaxTilesPerWarp < 4 ? kMaxTilesPerWarp : 4;
 
 // DMMA inner loop of the left-looking update for NA tile rows of one warp: per P one 16-byte LDS for
 // the shared B fragment (tile (Jc, P)), and per row one 16-byte LDS + two DMMAs (one per k-chunk, on
@@ -882,9 +885,11 @@ cudaError_t launch_fused_v2(const FusedArgs &a, const V2Plan &pl, char *scratch,
     lay.scratch_stride = pl.scratch_stride;
     lay.scratch = scratch;
     const bool keep = a.Lkeep != nullptr;
-    const bool small = pl.nt <= kSmallTilesPerWarp * kNB;      // fewer register slots per row owner suffice
-    auto kern = keep ? (small ? fused_v2_kernel<true, kSmallTilesPerWarp> : fused_v2_kernel<true, kMaxTilesPerWarp>)
-                     : (small ? fused_v2_kernel<false, kSmallTilesPerWarp> : fused_v2_kernel<false, kMaxTilesPerWarp>);
+    const int need = (pl.nt + kNB - 1) / kNB;                  // tile rows per row-owning warp
+    auto kern = keep ? (need <= kSlots3 ? fused_v2_kernel<true, kSlots3>
+                        : need <= kSlots4 ? fused_v2_kernel<true, kSlots4> : fused_v2_kernel<true, kMaxTilesPerWarp>)
+                     : (need <= kSlots3 ? fused_v2_kernel<false, kSlots3>
+                        : need <= kSlots4 ? fused_v2_kernel<false, kSlots4> : fused_v2_kernel<false, kMaxTilesPerWarp>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (e != cudaSuccess) return e;
     kern<<<grid, kT2, pl.smem_bytes, stream>>>(a, lay);
