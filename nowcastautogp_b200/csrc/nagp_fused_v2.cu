@@ -598,12 +598,11 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                 }
                 if (has_y) cyv = lds64(yv_a + lr * 8);
             }
-            auto lookahead = [&](int Jc, int P1) {
+            auto lookahead = [&](int Jc, int P1, int NA) {     // NA: this warp's rows I >= Jc
 #if NAGP_EXP == 2 || defined(NAGP_EXP_NOACC)
                 return;
 #endif
                 if (P1 <= 0) return;
-                const int NA = Ilast >= Jc ? (Ilast - Jc) / kNB + 1 : 0;
                 const uint32_t bp = tiles_a + (uint32_t)(tri(Jc) * 512 + lane * 16);
                 if (has_y) {
                     switch (NA) {
@@ -626,12 +625,15 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                     }
                 }
             };
-            for (int J = 0; J < nt; ++J) {
-                const int NA = Ilast >= J ? (Ilast - J) / kNB + 1 : 0;   // active regular rows (I >= J)
-                const int nsolve = (J % kNB == bi) ? NA - 1 : NA;        // rows strictly below the diagonal
+            // row bookkeeping without divisions: na = this warp's rows I >= J, ph = (bi - J) mod kNB (0: row J is mine,
+            // 1: row J+1, 2: row J+2)
+            int na = nreg, ph = bi;
+            for (int J = 0; J < nt; ++J, ph = (ph == 0 ? kNB - 1 : ph - 1)) {
+                const int nsolve = (ph == 0) ? na - 1 : na;              // rows strictly below the diagonal
+                if (ph == 0) --na;
                 const uint32_t joff = (uint32_t)J * 512u;
                 const bool more = J + 1 < nt;
-                const bool owns_next = more && ((J + 1) % kNB == bi);
+                const bool owns_next = more && ph == 1;
                 const int n2 = owns_next ? nsolve - 1 : nsolve;          // rows below diagonal J+1
                 DBG_T(J, 0);
                 asm volatile("bar.sync 1, %0;" ::"n"(kTB + 32) : "memory");
@@ -657,7 +659,7 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                     asm volatile("bar.arrive 3, %0;" ::"n"(kTB) : "memory");    // tile (J+1, J) is written
                 }
                 // topmost row first: the owner of row J+2 releases the others' lookahead as soon as tile (J+2, J) is stored
-                const bool owns_next2 = (J + 2 < nt) && ((J + 2) % kNB == bi);
+                const bool owns_next2 = (J + 2 < nt) && ph == 2;
                 double x[KM][2];
 #pragma unroll
                 for (int u = KM - 1; u >= 0; --u) {
@@ -712,7 +714,7 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                 // (3) lookahead: column J+2 over P <= J, in the shadow of the factorisation of diagonal tile J+1
                 if (J + 2 < nt) {
                     if (!owns_next2) asm volatile("bar.sync 4, %0;" ::"n"(kTB) : "memory");   // tile (J+2, J) is written
-                    lookahead(J + 2, J + 1);
+                    lookahead(J + 2, J + 1, n2);
                 }
                 DBG_T(J, 2);
             }
