@@ -333,13 +333,15 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                 *reinterpret_cast<double2 *>(tiles + tix * 64 + lane * 2) = make_double2(v0, v1);
             }
         } else {
+            // general trees: a warp interprets the compiled program for three tiles (6 entries per lane) at a time
+            // (two tiles: 5.27 ms, three: 5.21 ms, four: spills and a doubled value stack in local memory, slower)
+            constexpr int GT = 3, GW = 2 * GT;
             const int gr = lane >> 2, gc = (lane & 3) * 2;
-            for (int t0 = warp * 2; t0 < ntiles; t0 += kW2 * 2) {
-                int ii[4], jj[4], lag[4], tixs[2];
-                bool real[4];
-                bool interior = true;      // both tiles strictly below the diagonal and free of padding
+            for (int t0 = warp * GT; t0 < ntiles; t0 += kW2 * GT) {
+                int ii[GW], jj[GW], lag[GW], tixs[GT];
+                bool interior = true;      // all tiles strictly below the diagonal and free of padding
 #pragma unroll
-                for (int h2 = 0; h2 < 2; ++h2) {
+                for (int h2 = 0; h2 < GT; ++h2) {
                     const int tix = min(t0 + h2, ntiles - 1);
                     tixs[h2] = tix;
                     const int I = s_ti[tix], J = tix - tri(I);
@@ -352,27 +354,27 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                         jj[x] = J * 8 + gc + e;
                         const int lg = gi - gg[jj[x]];
                         lag[x] = lg < 0 ? -lg : lg;
-                        real[x] = ii[x] < q && jj[x] < q;
                     }
                 }
-                double out[4];
+                double out[GW];
 #if NAGP_EXP == 3
                 if (true) {
 #pragma unroll
-                    for (int x = 0; x < 4; ++x) out[x] = 0.0;
+                    for (int x = 0; x < GW; ++x) out[x] = 0.0;
                 } else
 #endif
-                tree_eval4(tp, cx, ii, jj, lag, out);
+                tree_evalw<GW>(tp, cx, ii, jj, lag, out);
                 if (!interior) {
 #pragma unroll
-                    for (int x = 0; x < 4; ++x) {
-                        if (!real[x]) out[x] = (ii[x] == jj[x]) ? 1.0 : 0.0;
+                    for (int x = 0; x < GW; ++x) {
+                        if (!(ii[x] < q && jj[x] < q)) out[x] = (ii[x] == jj[x]) ? 1.0 : 0.0;
                         else if (ii[x] == jj[x]) out[x] += (ii[x] < m) ? d_lo : d_hi;
                     }
                 }
-                *reinterpret_cast<double2 *>(tiles + tixs[0] * 64 + lane * 2) = make_double2(out[0], out[1]);
-                if (t0 + 1 < ntiles)
-                    *reinterpret_cast<double2 *>(tiles + tixs[1] * 64 + lane * 2) = make_double2(out[2], out[3]);
+#pragma unroll
+                for (int h2 = 0; h2 < GT; ++h2)
+                    if (t0 + h2 < ntiles)
+                        *reinterpret_cast<double2 *>(tiles + tixs[h2] * 64 + lane * 2) = make_double2(out[2 * h2], out[2 * h2 + 1]);
             }
         }
         {

@@ -54,8 +54,9 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-// 4-wide interpreter over arbitrary entries (ii[e], jj[e]): one lane evaluates its two accumulator-
-// layout entries of two tiles at once. The two top stack levels live in registers; deeper levels
+// W-wide interpreter over arbitrary entries (ii[e], jj[e]): one lane evaluates its two accumulator-
+// layout entries of W/2 tiles at once (op decoding is paid once per W entries; the W independent look-up and
+// arithmetic chains per op hide the shared-memory latency). The two top stack levels live in registers; deeper levels
 // (expression depth >= 3) go to local memory. Same formulas and evaluation order as tree_eval
 // (docs/KERNEL_SPEC.md §3).
 struct EvalCtx {
@@ -65,15 +66,16 @@ struct EvalCtx {
     bool grid;
 };
 
-__device__ __forceinline__ void tree_eval4(const TreeProgram &tp, const EvalCtx &cx, const int (&ii)[4],
-                                           const int (&jj)[4], const int (&lag)[4], double (&top)[4])
+template <int W>
+__device__ __forceinline__ void tree_evalw(const TreeProgram &tp, const EvalCtx &cx, const int (&ii)[W],
+                                           const int (&jj)[W], const int (&lag)[W], double (&top)[W])
 {
-    double st[MAX_STACK][4];
-    double sec[4];
+    double st[MAX_STACK][W];
+    double sec[W];
     int sp = 0;
     const int len = tp.clen;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) { top[e] = 0.0; sec[e] = 0.0; }
+    for (int e = 0; e < W; ++e) { top[e] = 0.0; sec[e] = 0.0; }
     for (int o = 0; o < len; ++o) {
         const uint32_t wd = tp.cword[o];
         const int op = wd & 0xff;
@@ -81,26 +83,26 @@ __device__ __forceinline__ void tree_eval4(const TreeProgram &tp, const EvalCtx 
         if (op <= OP_PERIODIC || op == OP_TABLE) {
             if (sp >= 2) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) st[sp - 2][e] = sec[e];
+                for (int e = 0; e < W; ++e) st[sp - 2][e] = sec[e];
             }
 #pragma unroll
-            for (int e = 0; e < 4; ++e) sec[e] = top[e];
+            for (int e = 0; e < W; ++e) sec[e] = top[e];
             ++sp;
             if (op == OP_TABLE) {
                 const double *tb = cx.tab + ((wd >> 8) & 0xffff) * cx.G;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) top[e] = tb[lag[e]];
+                for (int e = 0; e < W; ++e) top[e] = tb[lag[e]];
             } else if (op == OP_LINEAR) {
                 const double c0 = p[0], b0 = p[1], a0 = p[2];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) top[e] = fma(a0, (cx.tt[ii[e]] - c0) * (cx.tt[jj[e]] - c0), b0);
+                for (int e = 0; e < W; ++e) top[e] = fma(a0, (cx.tt[ii[e]] - c0) * (cx.tt[jj[e]] - c0), b0);
             } else if (op == OP_CONSTANT) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) top[e] = p[0];
+                for (int e = 0; e < W; ++e) top[e] = p[0];
             } else {
                 // stationary leaf evaluated directly (pairwise times, or no table slot left)
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
+                for (int e = 0; e < W; ++e) {
                     const double delta = cx.grid ? (double)lag[e] * cx.step : fabs(cx.tt[ii[e]] - cx.tt[jj[e]]);
                     double v;
                     if (op == OP_SQEXP) { double r = delta / p[0]; v = p[1] * exp(-0.5 * (r * r)); }
@@ -116,20 +118,20 @@ __device__ __forceinline__ void tree_eval4(const TreeProgram &tp, const EvalCtx 
             --sp;   // left operand is sec, right operand is top
             if (op == OP_PLUS) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) top[e] = sec[e] + top[e];
+                for (int e = 0; e < W; ++e) top[e] = sec[e] + top[e];
             } else if (op == OP_TIMES) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) top[e] = sec[e] * top[e];
+                for (int e = 0; e < W; ++e) top[e] = sec[e] * top[e];
             } else if (op == OP_CHANGEPOINT_TAB) {
                 const double *sg = cx.sig + (wd >> 24) * cx.Q;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
+                for (int e = 0; e < W; ++e) {
                     const double si = sg[ii[e]], sj = sg[jj[e]];
                     top[e] = ((1.0 - si) * (1.0 - sj)) * sec[e] + (si * sj) * top[e];
                 }
             } else {   // OP_CHANGEPOINT evaluated directly
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
+                for (int e = 0; e < W; ++e) {
                     const double si = 0.5 * (1.0 + tanh((cx.tt[ii[e]] - p[0]) / p[1]));
                     const double sj = 0.5 * (1.0 + tanh((cx.tt[jj[e]] - p[0]) / p[1]));
                     top[e] = ((1.0 - si) * (1.0 - sj)) * sec[e] + (si * sj) * top[e];
@@ -137,12 +139,18 @@ __device__ __forceinline__ void tree_eval4(const TreeProgram &tp, const EvalCtx 
             }
             if (sp >= 2) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) sec[e] = st[sp - 2][e];
+                for (int e = 0; e < W; ++e) sec[e] = st[sp - 2][e];
             }
         }
     }
 }
 
+
+__device__ __forceinline__ void tree_eval4(const TreeProgram &tp, const EvalCtx &cx, const int (&ii)[4],
+                                           const int (&jj)[4], const int (&lag)[4], double (&top)[4])
+{
+    tree_evalw<4>(tp, cx, ii, jj, lag, top);
+}
 
 #ifndef NAGP_CHOL8_OLD
 #define NAGP_CHOL8_OLD 0   // 1: the first (rsqrt-on-the-chain) version, kept for A/B timing builds

@@ -1,3 +1,2 @@
-echo "== 6-wide interpreter"; NAGP_LIB=gpurun_exp/libnagp_w6.so timeout 40 python bench.py --steps 10 --warmup 3 --only-value
-echo "== bookkeeping build"; timeout 40 python bench.py --steps 10 --warmup 3 --only-value
+timeout 40 python bench.py --steps 10 --warmup 3 --only-value
 timeout 400 python -m pytest tests -x -q -m gpu 2>&1 | tail -2
