@@ -495,7 +495,7 @@ def main():
                          "peak": peak_tf, "peak_source": "profiles/r01_fp64_peak.json (DMMA m8n8k4 measured on this "
                          "pool's B200; MEASURED_PEAKS.json has no FP64 entry)", "unit": "TFLOP/s",
                          "frac": achieved / peak_tf,
-                         "traffic": 1969152, "traffic_source": "profiles/r01_v2h_panel_summary.csv: dram__bytes_read.sum + "
+                         "traffic": 2722304, "traffic_source": "profiles/r01_v2i_final_summary.csv: dram__bytes_read.sum + "
                          "dram__bytes_write.sum of one launch (bytes; the Gram and the factor never leave shared memory, and the 23 MB of "
                          "outputs were still in L2 when the counter was read)",
                          "kernel_ms": ms_kernel,

@@ -1,2 +1,1 @@
-timeout 40 python bench.py --steps 10 --warmup 3 --only-value
-timeout 400 python -m pytest tests -x -q -m gpu 2>&1 | tail -2
+echo "== prefetch"; NAGP_LIB=gpurun_exp/libnagp_pf.so timeout 40 python bench.py --steps 10 --warmup 3 --only-value
