@@ -227,8 +227,9 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
         if (chain < 0) chain = 0;
         if (idle < 0) idle = (chain == kW2 - 1) ? kW2 - 2 : kW2 - 1;
         int nb = 0;
-        if (kNB == kW2 - 1) idle = -1;
-        for (int w = 0; w < kW2; ++w) s_role[w] = (w == chain) ? -1 : (w == idle) ? -2 : nb++;
+        // seven row owners: the chain's scheduler mate takes the last index, the one with the fewest tile rows
+        for (int w = 0; w < kW2; ++w)
+            s_role[w] = (w == chain) ? -1 : (w == idle) ? (kNB == kW2 - 1 ? kNB - 1 : -2) : nb++;
     }
     __syncthreads();
     const int role = s_role[warp];
