@@ -209,9 +209,10 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
 #if NAGP_V2_PANEL
     // Roles by hardware scheduler, not by warp index: the hardware warp slot (%warpid; slot mod 4 = scheduler) is
     // some permutation of the CTA's warps that differs between co-resident CTAs, and the point of the panel
-    // schedule is that the chain warps of BOTH resident CTAs share one scheduler that no row owner uses. Chain =
-    // first warp on scheduler 0, the other warp there idles, the remaining six own rows in order. (Only speed
-    // depends on this: any assignment of one chain warp and six row owners is correct.)
+    // schedule is that the chain warps of BOTH resident CTAs share one scheduler with as little row work as possible.
+    // Chain = first warp on scheduler 0; the other warp there is the last row owner (the one with the fewest tile
+    // rows) or idles (NAGP_V2_PANEL_ROWS=6); the remaining six own rows in order. (Only speed depends on this: any
+    // assignment of one chain warp and kNB row owners is correct.)
     __shared__ int s_sched[kW2];
     __shared__ int s_role[kW2];                 // -1 chain, -2 idle, else row-owner index
     if (lane == 0) {
