@@ -1,2 +1,2 @@
-# scratch runner for one-off GPU experiments (overwritten per experiment): the last one compared kernel builds
+# scratch runner for one-off GPU experiments (overwritten per experiment)
 timeout 40 python bench.py --steps 10 --warmup 3 --only-value
