@@ -154,6 +154,7 @@ def main():
     ap.add_argument("--skip-sanity", action="store_true", help="timing experiments with deliberately wrong kernels")
     ap.add_argument("--only-value", action="store_true", help="time only the device-resident step")
     ap.add_argument("--no-micro", action="store_true", help="skip the configs[2]/configs[4] micro-benchmarks")
+    ap.add_argument("--variant", type=int, default=0, help="factorisation kernel: 0 auto, 2 tile kernel, 3 slot kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -203,6 +204,7 @@ def main():
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
+    eng.set_variant(args.variant)
 
     w, theta_k, noise_k, zeta, u = make_inputs(rank)
     n, k, h, P, K, D = c["n"], c["k"], c["h"], c["P"], c["K"], c["D"]
@@ -325,7 +327,7 @@ def main():
     ms_kernel = timed(kernel_only, args.steps, 1)
     if args.only_value:
         if rank == 0:
-            print(json.dumps({"ms_per_step": ms_step, "kernel_ms": ms_kernel}))
+            print(json.dumps({"ms_per_step": ms_step, "kernel_ms": ms_kernel, "kernel": eng.last_kernel}))
         eng.close()
         return 0
     ms_e2e = timed(step_e2e, args.steps, args.warmup)

@@ -22,6 +22,7 @@ SIGNATURES = {
     "nagp_set_jitter": (_i32, [_vp, _f64]),
     "nagp_launch_count": (_i64, [_vp]),
     "nagp_set_variant": (_i32, [_vp, _i32]),
+    "nagp_last_kernel": (_i32, [_vp]),
     "nagp_logml_batch": (_i32, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _f64, _vp, _i64, _vp, _vp]),
     "nagp_forecast_instances": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _f64,
                                        _i64, _i64, _i64, _vp, _vp, _f64, _vp, _vp, _f64, _f64, _vp,

@@ -65,7 +65,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     # drop objects of sources that no longer exist
     for stale in set(glob.glob(os.path.join(OBJ, "*.o"))) - set(objs):
         os.remove(stale)
-    res = subprocess.run([NVCC] + ARCH + ["-shared", "-o", LIB] + objs, capture_output=True, text=True)
+    res = subprocess.run([NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-ldl"], capture_output=True, text=True)
     if res.returncode:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc failed linking libnagp.so")

@@ -11,10 +11,21 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "nagp_kernels.cuh"
 #include "nagp_tree.cuh"
 
 using namespace nagp;
+
+// One NVTX range per C-ABI entry point (SURVEY §5 tracing row): header-only NVTX v3, a no-op unless a profiler is attached.
+namespace {
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+}  // namespace
+#define NAGP_RANGE(name) NvtxRange nvtx_range__(name)
 
 namespace {
 
@@ -30,6 +41,7 @@ struct nagp_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     double jitter = 1e-5;
     int variant = 0;
+    int last_kernel = 0;
     int64_t launches = 0;
     int smem_optin = 0, smem_per_sm = 0, num_sms = 0;
     std::string err;
@@ -255,6 +267,39 @@ int32_t check_dims(nagp_ctx *ctx, int64_t n, int64_t k, int64_t h)
 int32_t run_fused(nagp_ctx *ctx, FusedArgs a, const int64_t *theta_off_host)
 {
     const int q = a.n + a.k + a.h;
+    // Slot kernel (three matrices in flight per SM, nagp_fused_v3.cu): selected with variant 3 wherever it applies — it needs
+    // host-compiled programs whose stationary leaves and changepoints are all tabulated, and no kept factor. It is
+    // parity-green but at 5.6 ms per 32 000 instances still behind the tile kernel (5.1 ms), so auto (variant 0) keeps the
+    // tile kernel.
+    if (ctx->variant == 3 && q <= fused_v3_max_q() && !a.Lkeep && (int64_t)ctx->compiled.size() == a.P) {
+        bool table_only = true;
+        int64_t nth = 1;
+        for (int64_t p = 0; p < a.P && table_only; ++p) {
+            const TreeProgram &tp = ctx->compiled[p];
+            nth = std::max(nth, theta_off_host[p + 1] - theta_off_host[p]);
+            for (int c = 0; c < tp.clen; ++c) {
+                const int op = tp.cop[c];
+                if (op == OP_SQEXP || op == OP_GAMMAEXP || op == OP_PERIODIC || op == OP_CHANGEPOINT) table_only = false;
+            }
+        }
+        if (table_only) {
+            V3Plan pl = plan_fused_v3(a.n, a.k, a.h, a.proj != nullptr || a.Ltail != nullptr, a.G,
+                                      (int)std::min<int64_t>(nth, MAX_THETA), a.ntab_cap, a.ncp_cap, ctx->smem_optin);
+            if (pl.ok) {
+                NAGP_TRY(stage_in(ctx, ctx->compiled.data(), ctx->compiled.size(), &a.compiled));
+                const int grid = fused_v3_grid(a.B, ctx->num_sms);
+                if (getenv("NAGP_DEBUG"))
+                    fprintf(stderr, "[nagp] slot kernel: q=%d nt=%d pool=%d slots lead=%d smem=%zu B grid=%d\n", q, pl.nt, pl.ns,
+                            pl.lead, pl.smem_bytes, grid);
+                unsigned long long *counter = nullptr;
+                NAGP_TRY(scratch(ctx, 1, &counter));
+                NAGP_CUDA(ctx, launch_fused_v3(a, pl, counter, grid, ctx->stream));
+                ctx->launches += 1;
+                ctx->last_kernel = 3;
+                return NAGP_OK;
+            }
+        }
+    }
     if (ctx->variant != 1 && q <= fused_v2_max_q()) {
         int64_t nth = 1;
         for (int64_t p = 0; p < a.P; ++p) nth = std::max(nth, theta_off_host[p + 1] - theta_off_host[p]);
@@ -274,6 +319,7 @@ int32_t run_fused(nagp_ctx *ctx, FusedArgs a, const int64_t *theta_off_host)
             NAGP_TRY(scratch(ctx, 1, &counter));
             NAGP_CUDA(ctx, launch_fused_v2(a, pl, scr, counter, grid, ctx->stream));
             ctx->launches += 1;
+            ctx->last_kernel = 2;
             return NAGP_OK;
         }
     }
@@ -296,11 +342,13 @@ int32_t run_fused(nagp_ctx *ctx, FusedArgs a, const int64_t *theta_off_host)
         NAGP_TRY(scratch(ctx, 1, &counter));
         NAGP_CUDA(ctx, launch_chol_large(a, pl, scr, Lws, 0, nullptr, counter, grid, ctx->stream));
         ctx->launches += 1;
+        ctx->last_kernel = 4;
         return NAGP_OK;
     }
     NAGP_TRY(fit_tables_v1(ctx, q, a.G, &a.ntab_cap, &a.ncp_cap));
     NAGP_CUDA(ctx, launch_fused_v1(a, ctx->stream));
     ctx->launches += 1;
+    ctx->last_kernel = 1;
     return NAGP_OK;
 }
 
@@ -365,9 +413,11 @@ int32_t nagp_set_jitter(nagp_ctx *ctx, double jitter)
 
 int64_t nagp_launch_count(const nagp_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int32_t nagp_last_kernel(const nagp_ctx *ctx) { return ctx ? ctx->last_kernel : 0; }
+
 int32_t nagp_set_variant(nagp_ctx *ctx, int32_t variant)
 {
-    if (!ctx || variant < 0 || variant > 2) return NAGP_E_ARG;
+    if (!ctx || variant < 0 || variant > 3) return NAGP_E_ARG;
     ctx->variant = variant;
     return NAGP_OK;
 }
@@ -377,6 +427,7 @@ int32_t nagp_logml_batch(nagp_ctx *ctx, int64_t B, const uint8_t *prog, const in
                          int64_t n, const double *t, const int32_t *g, double step,
                          const double *y, int64_t y_stride, double *logml, int32_t *info)
 {
+    NAGP_RANGE("nagp_logml_batch");
     if (!ctx) return NAGP_E_ARG;
     if (B <= 0 || !prog || !prog_off || !theta || !theta_off || !noise || !t || !y || !logml || !info)
         return fail(ctx, NAGP_E_ARG, "nagp_logml_batch: null or empty argument");
@@ -420,6 +471,7 @@ int32_t nagp_forecast_instances(nagp_ctx *ctx, int64_t K, int64_t P, const uint8
                                 double ya, double yb, const double *logw0, double *logw, double *mu,
                                 double *L, int32_t *info, double *logml_n, double *logml_m)
 {
+    NAGP_RANGE("nagp_forecast_instances");
     if (!ctx) return NAGP_E_ARG;
     if (K <= 0 || P <= 0 || !prog || !prog_off || !theta || !theta_off || !noise || !t || !y1 || !info ||
         (k > 0 && !y2) || ya == 0.0)
@@ -469,6 +521,7 @@ int32_t nagp_factor_store(nagp_ctx *ctx, int64_t P, const uint8_t *prog, const i
                           const int32_t *g, double step, const double *y1, double ya, double yb,
                           const double *logw0, nagp_factor **out, double *logml_n, int32_t *info)
 {
+    NAGP_RANGE("nagp_factor_store");
     if (!ctx) return NAGP_E_ARG;
     if (!out || P <= 0 || !prog || !prog_off || !theta || !theta_off || !noise || !t || !y1 || !info || ya == 0.0)
         return fail(ctx, NAGP_E_ARG, "nagp_factor_store: null or empty argument");
@@ -666,6 +719,7 @@ int32_t nagp_logml_grad(nagp_ctx *ctx, int64_t K, int64_t P, const uint8_t *prog
                         const int32_t *g, double step, const double *y1, int64_t y1_stride, const double *y2,
                         double *logml, double *grad_theta, double *grad_noise, int32_t *info)
 {
+    NAGP_RANGE("nagp_logml_grad");
     if (!ctx) return NAGP_E_ARG;
     if (K <= 0 || P <= 0 || !prog || !prog_off || !theta || !theta_off || !noise || !t || !y1 || !logml ||
         !grad_theta || !grad_noise || !info || (k > 0 && !y2) || n <= 0 || k < 0 || (y1_stride != 0 && y1_stride < n))
@@ -693,6 +747,7 @@ int32_t nagp_hmc(nagp_ctx *ctx, int64_t K, int64_t P, const uint8_t *prog, const
                  const double *momenta, const double *noise_momenta, const double *log_u,
                  double *logml, int32_t *n_accept, int32_t *info)
 {
+    NAGP_RANGE("nagp_hmc");
     if (!ctx) return NAGP_E_ARG;
     const bool learn_noise = noise_kind != 5;
     if (K <= 0 || P <= 0 || !prog || !prog_off || !theta_off || !slot_kind || !slot_a || !slot_b || !z || !noise_z ||
@@ -805,6 +860,7 @@ int32_t nagp_forecast_summary(nagp_ctx *ctx, int32_t kind, double lambda, double
                               int64_t h, int64_t N, const double *x, double *x_out,
                               int64_t nq, const double *probs, double *q)
 {
+    NAGP_RANGE("nagp_forecast_summary");
     if (!ctx) return NAGP_E_ARG;
     if (kind < 0 || kind > 3 || h <= 0 || N <= 0 || !x || nq < 0 || (nq > 0 && (!probs || !q)) || (!x_out && nq == 0))
         return fail(ctx, NAGP_E_ARG, "nagp_forecast_summary: bad argument");
@@ -841,6 +897,7 @@ int32_t nagp_factor_store_large(nagp_ctx *ctx, int64_t P, const uint8_t *prog, c
                                 int64_t n, int64_t capacity, const double *t, const int32_t *g, double step,
                                 const double *y, nagp_factor **out, double *logml, int32_t *info)
 {
+    NAGP_RANGE("nagp_factor_store_large");
     if (!ctx) return NAGP_E_ARG;
     if (!out || P <= 0 || !prog || !prog_off || !theta || !theta_off || !noise || !t || !y || !info || n <= 0)
         return fail(ctx, NAGP_E_ARG, "nagp_factor_store_large: null or empty argument");
@@ -914,6 +971,7 @@ int64_t nagp_factor_size(const nagp_factor *f) { return f ? f->n : -1; }
 int32_t nagp_factor_append(nagp_ctx *ctx, nagp_factor *f, int64_t k_new, const double *t_new, const int32_t *g_new,
                            const double *y_new, double *dlogml, double *logml, int32_t *info)
 {
+    NAGP_RANGE("nagp_factor_append");
     if (!ctx) return NAGP_E_ARG;
     if (!f || !f->appendable || k_new <= 0 || !t_new || !y_new || !info)
         return fail(ctx, NAGP_E_ARG, "nagp_factor_append: null argument or factor not appendable");
@@ -957,6 +1015,7 @@ int32_t nagp_factor_append(nagp_ctx *ctx, nagp_factor *f, int64_t k_new, const d
 
 int32_t nagp_append(nagp_ctx *ctx, const nagp_factor *f, int64_t K, const double *y2, double *logw, double *mu)
 {
+    NAGP_RANGE("nagp_append");
     if (!ctx) return NAGP_E_ARG;
     if (!f || K <= 0 || !logw || (f->k > 0 && !y2)) return fail(ctx, NAGP_E_ARG, "nagp_append: null or empty argument");
     if (f->appendable) return fail(ctx, NAGP_E_ARG, "nagp_append: factor was created by nagp_factor_store_large (use nagp_factor_append)");
@@ -977,6 +1036,7 @@ int32_t nagp_append(nagp_ctx *ctx, const nagp_factor *f, int64_t K, const double
 
 int32_t nagp_predict(nagp_ctx *ctx, const nagp_factor *f, double *mu, double *L)
 {
+    NAGP_RANGE("nagp_predict");
     if (!ctx) return NAGP_E_ARG;
     if (!f || f->appendable) return fail(ctx, NAGP_E_ARG, "nagp_predict: null or appendable-only factor");
     if (f->device != ctx->device) return fail(ctx, NAGP_E_ARG, "factor lives on another device");
@@ -1005,6 +1065,7 @@ int32_t nagp_predict(nagp_ctx *ctx, const nagp_factor *f, double *mu, double *L)
 
 int32_t nagp_ess(nagp_ctx *ctx, int64_t K, int64_t P, const double *logw, double *ess, double *w)
 {
+    NAGP_RANGE("nagp_ess");
     if (!ctx) return NAGP_E_ARG;
     if (K <= 0 || P <= 0 || !logw || !ess) return fail(ctx, NAGP_E_ARG, "nagp_ess: null or empty argument");
     NAGP_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1024,6 +1085,7 @@ int32_t nagp_draw(nagp_ctx *ctx, int64_t K, int64_t P, int64_t h, int64_t D, con
                   const int32_t *comp, const double *u, const double *u_res, double ess_thr,
                   const double *zeta, double *x, double *ess_out, int32_t *comp_out)
 {
+    NAGP_RANGE("nagp_draw");
     if (!ctx) return NAGP_E_ARG;
     if (K <= 0 || P <= 0 || h <= 0 || D <= 0 || !logw || !mu || !L || !zeta || !x || (!comp && !u))
         return fail(ctx, NAGP_E_ARG, "nagp_draw: null or empty argument");
@@ -1059,6 +1121,7 @@ int32_t nagp_forecast_with_nowcasts(nagp_ctx *ctx, int64_t K, int64_t P, int64_t
                                     double ess_thr, const double *zeta, double *x, double *logw_out,
                                     double *ess_out, int32_t *info)
 {
+    NAGP_RANGE("nagp_forecast_with_nowcasts");
     if (!ctx) return NAGP_E_ARG;
     if (K <= 0 || P <= 0 || D <= 0 || h <= 0 || !prog || !prog_off || !theta || !theta_off || !noise || !t ||
         !y1 || (k > 0 && !y2) || !zeta || !x || !info || (!comp && !u) || ya == 0.0)

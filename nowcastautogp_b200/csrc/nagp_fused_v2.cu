@@ -567,7 +567,11 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                 if (d0 == 123.456) DBG_T(J, 5);   // forces the load to complete before the stamp
                 DBG_T(J, 4);
 #endif
+#ifdef NAGP_V2_ROLLED_CHOL8
+                const int bad = chol8_inv_rolled(d0, d1, w0, w1, lane, q - J * 8); (void)piv;
+#else
                 const int bad = chol8_inv(d0, d1, w0, w1, lane, q - J * 8, piv);
+#endif
 #if NAGP_EXP == 9
                 if (w0 == 123.456) DBG_T(J, 5);
                 DBG_T(J, 3);

@@ -65,6 +65,24 @@ int fused_v2_grid(const V2Plan &pl, int64_t B, int num_sms);
 cudaError_t launch_fused_v2(const FusedArgs &a, const V2Plan &pl, char *scratch, unsigned long long *work_counter,
                             int grid, cudaStream_t stream);
 
+// Slot kernel (nagp_fused_v3.cu): three matrices in flight per SM in one role-specialised CTA, factor in a pool of
+// recycled tile slots, Gram on demand. Needs host-compiled programs whose stationary leaves are all tabulated.
+struct V3Plan {
+    int ok;
+    int nt, ns, lead, iep;       // tile rows, pool slots, Gram lead (columns), first tile row kept for the epilogue
+    int off_tt, off_gg, off_map, off_need, off_slots, slot_stride;
+    int o_ctrl, o_tp, o_yv, o_diag, o_inv, o_th, o_tab, o_sig, o_pool;   // inside a slot's region
+    size_t smem_bytes;
+    unsigned char smap[232];     // tile (I, P) -> pool slot, at tri(I) + P (nt <= 21)
+    unsigned char need[24];      // row-owner steps that must be complete before Gram column C may be written
+};
+int fused_v3_max_q();
+V3Plan plan_fused_v3(int n, int k, int h, bool tail_rows_from_n, int G, int ntheta_cap, int ntab_cap, int ncp_cap,
+                     int smem_optin);
+int fused_v3_grid(int64_t B, int num_sms);
+cudaError_t launch_fused_v3(const FusedArgs &a, const V3Plan &pl, unsigned long long *work_counter, int grid,
+                            cudaStream_t stream);
+
 // Large path (q beyond shared memory): factor in HBM as tile-packed operand-layout tiles.
 struct LargePlan {
     int ok;

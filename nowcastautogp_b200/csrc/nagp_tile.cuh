@@ -265,6 +265,48 @@ __device__ __forceinline__ int chol8_inv(double &c0, double &c1, double &w0, dou
 }
 #endif
 
+// 8x8 Cholesky + inverse of a tile in accumulator layout, same operations in the same order as chol8_inv
+// (nagp_tile.cuh) with the pivot loop rolled.
+__device__ __forceinline__ int chol8_inv_rolled(double &c0, double &c1, double &w0, double &w1, int lane, int nreal)
+{
+    const int r = lane >> 2, j = lane & 3;
+    w0 = (r == 2 * j) ? 1.0 : 0.0;
+    w1 = (r == 2 * j + 1) ? 1.0 : 0.0;
+    double my_rinv = 0.0;
+    int bad = 0;
+#pragma unroll 1
+    for (int p = 0; p < 8; ++p) {
+        const int pl = p >> 1;
+        const bool odd = p & 1;
+        const double colv = odd ? c1 : c0;                // column p lives in the lanes j == pl
+        const double d = shfl(colv, p * 4 + pl);
+        if (!(d > 0.0) && p < nreal && bad == 0) bad = p + 1;
+        const double rinv = rsqrt_seeded(d);
+        const double fin = r >= p ? colv * rinv : 0.0;
+        if (p < 7) {
+            const double arp = shfl(colv, r * 4 + pl);        // (r, p)
+            const double ac0 = shfl(colv, (2 * j) * 4 + pl);  // (2j, p)
+            const double ac1 = shfl(colv, (2 * j + 1) * 4 + pl);
+            const double wp0 = shfl(w0, p * 4 + j);           // unscaled row p of the inverse
+            const double wp1 = shfl(w1, p * 4 + j);
+            const double x = rcp_seeded(d);
+            const double am = r > p ? arp : 0.0;              // rows <= p do not change
+            const double u0 = am * (2 * j > p ? ac0 : 0.0);   // columns <= p do not change
+            const double u1 = am * (2 * j + 1 > p ? ac1 : 0.0);
+            const double v0 = am * wp0, v1 = am * wp1;
+            c0 = fma(-u0, x, c0);
+            c1 = fma(-u1, x, c1);
+            w0 = fma(-v0, x, w0);
+            w1 = fma(-v1, x, w1);
+        }
+        if (j == pl) { if (odd) c1 = fin; else c0 = fin; }
+        if (r == p) my_rinv = rinv;
+    }
+    w0 *= my_rinv;
+    w1 *= my_rinv;
+    return bad;
+}
+
 
 }  // namespace
 }  // namespace nagp

@@ -89,6 +89,11 @@ class Engine:
         self._check(self._lib.nagp_set_variant(self._ctx, variant))
 
     @property
+    def last_kernel(self) -> int:
+        """Factorisation kernel of the last fused launch: 1 column, 2 tile, 3 slot, 4 large."""
+        return int(self._lib.nagp_last_kernel(self._ctx))
+
+    @property
     def launch_count(self) -> int:
         return int(self._lib.nagp_launch_count(self._ctx))
 

@@ -6,8 +6,8 @@ one task per scenario on a private model copy (`/root/reference/src/forecasting.
 couplings are the per-scenario weight normalisation over that scenario's P particles and the final
 `hcat` (`forecasting.jl:166`). So: one process per GPU, all particles of a (series, scenario) pair on
 one GPU, pairs split contiguously across ranks — series first, so that in the scenario-shared fast
-path each particle is factored on exactly one GPU — and ONE collective at the end: an all-gather of
-the draws `[h, K·D]` and log-weights `[K, P]` (NCCL over NVLink on the GPU box, gloo in CPU tests).
+path each particle is factored on exactly one GPU — and ONE collective at the end: a single all-gather of a
+packed buffer holding the draws `[h, K·D]` and the log-weights `[K, P]` (NCCL over NVLink on the GPU box, gloo in CPU tests).
 No collective on the data path.
 """
 from __future__ import annotations
@@ -58,15 +58,34 @@ def partition(n_series: int, n_scenarios: Sequence[int] | int, world: int) -> Li
     return out
 
 
-def sharded_forecast(compute: Callable[[Slice], Tuple[np.ndarray, np.ndarray]], n_series: int,
-                     n_scenarios: Sequence[int] | int, h: int, D: int, P: int,
-                     group=None, device=None) -> Tuple[Dict[int, np.ndarray], Dict[int, np.ndarray]]:
-    """Run `compute(slice) -> (x [h, (k1-k0)·D], logw [(k1-k0), P])` on this rank's slices and gather.
+_PACKED: Dict[tuple, tuple] = {}     # (cap, D, h, P, world, device) -> (send, recv) packed buffers, reused across calls
 
-    Returns `(draws, logw)` dicts keyed by series on EVERY rank: `draws[s]` is the reference's
-    `(h, K_s·D)` matrix in scenario-major column order, `logw[s]` is `[K_s, P]`. Works without an
-    initialised process group (world = 1). The gather is a single padded `all_gather_into_tensor` per
-    output (ranks can own different numbers of pairs)."""
+
+def _packed_buffers(cap: int, D: int, h: int, P: int, world: int, dev):
+    import torch
+    key = (cap, D, h, P, world, str(dev))
+    if key not in _PACKED:
+        n = cap * (D * h + P)
+        _PACKED[key] = (torch.zeros(n, dtype=torch.float64, device=dev),
+                        torch.zeros((world, n), dtype=torch.float64, device=dev))
+    return _PACKED[key]
+
+
+def sharded_forecast(compute: Callable, n_series: int, n_scenarios: Sequence[int] | int, h: int, D: int, P: int,
+                     group=None, device=None, in_place: bool = False):
+    """Run `compute` on this rank's slices and gather with ONE collective.
+
+    Host form (default): `compute(slice) -> (x [h, (k1-k0)·D], logw [(k1-k0), P])` as NumPy arrays; returns
+    `(draws, logw)` dicts of NumPy arrays keyed by series on EVERY rank: `draws[s]` is the reference's `(h, K_s·D)`
+    matrix in scenario-major column order, `logw[s]` is `[K_s, P]`.
+    Device form (`in_place=True`): `compute(slice, x_out, lw_out)` fills `x_out [(k1-k0)·D, h]` (the column-major
+    `(h, (k1-k0)·D)` block, i.e. what `nagp_draw` writes) and `lw_out [(k1-k0), P]`, both views of the packed send
+    buffer on `device`; nothing bounces through the host and the dicts hold device tensors (`draws[s]` a
+    `(h, K_s·D)` transposed view).
+    Either way every rank's results travel in one packed buffer `[pairs·D·h draws | pairs·P log-weights]` and one
+    `all_gather_into_tensor` (NCCL over NVLink on the GPU box; the list form of `all_gather` under gloo). Works
+    without an initialised process group (world = 1). Ranks may own different numbers of pairs (padded to the
+    largest)."""
     import torch
     import torch.distributed as dist
 
@@ -76,46 +95,63 @@ def sharded_forecast(compute: Callable[[Slice], Tuple[np.ndarray, np.ndarray]], 
     ks = [int(n_scenarios)] * n_series if np.isscalar(n_scenarios) else [int(k) for k in n_scenarios]
     parts = partition(n_series, ks, world)
     mine = parts[rank]
-    # local results packed pair-major: draws [pairs, D, h] (column blocks of x transposed), logw [pairs, P]
     n_pairs = [sum(s.k1 - s.k0 for s in p) for p in parts]
     cap = max(max(n_pairs), 1)
-    xd = np.zeros((cap, D, h))
-    lw = np.zeros((cap, P))
+    dev = torch.device("cpu") if device is None else torch.device(device)
+    send, recv = _packed_buffers(cap, D, h, P, world, dev)
+    sx = send[:cap * D * h].view(cap, D, h)          # pair-major draws: the column blocks of x, transposed
+    sl_ = send[cap * D * h:].view(cap, P)
     off = 0
     for sl in mine:
-        x, logw = compute(sl)
         kk = sl.k1 - sl.k0
-        x = np.asarray(x, np.float64)
-        if x.shape != (h, kk * D):
-            raise ValueError(f"compute returned draws of shape {x.shape}, expected {(h, kk * D)}")
-        xd[off:off + kk] = x.T.reshape(kk, D, h)
-        lw[off:off + kk] = np.asarray(logw, np.float64).reshape(kk, P)
+        if in_place:
+            compute(sl, sx[off:off + kk].view(kk * D, h), sl_[off:off + kk])
+        else:
+            x, logw = compute(sl)
+            x = np.asarray(x, np.float64)
+            if x.shape != (h, kk * D):
+                raise ValueError(f"compute returned draws of shape {x.shape}, expected {(h, kk * D)}")
+            sx[off:off + kk] = torch.from_numpy(np.ascontiguousarray(x.T)).view(kk, D, h).to(dev)
+            sl_[off:off + kk] = torch.from_numpy(np.ascontiguousarray(np.asarray(logw, np.float64).reshape(kk, P))).to(dev)
         off += kk
     if use_dist:
-        dev = torch.device("cpu") if device is None else device
-        tx = torch.from_numpy(xd).to(dev)
-        tl = torch.from_numpy(lw).to(dev)
-        gx = torch.empty((world,) + tuple(tx.shape), dtype=tx.dtype, device=dev)
-        gl = torch.empty((world,) + tuple(tl.shape), dtype=tl.dtype, device=dev)
-        if dev.type == "cpu":     # gloo has no all_gather_into_tensor on older builds: use the list form
-            lx = list(gx.unbind(0)); ll = list(gl.unbind(0))
-            dist.all_gather(lx, tx, group=group)
-            dist.all_gather(ll, tl, group=group)
-            gx = torch.stack(lx); gl = torch.stack(ll)
+        if dev.type == "cpu":     # gloo: the list form is available on every build
+            dist.all_gather(list(recv.unbind(0)), send, group=group)
         else:
-            dist.all_gather_into_tensor(gx, tx, group=group)
-            dist.all_gather_into_tensor(gl, tl, group=group)
-        gx, gl = gx.cpu().numpy(), gl.cpu().numpy()
+            dist.all_gather_into_tensor(recv, send, group=group)
+        got = recv
     else:
-        gx, gl = xd[None], lw[None]
+        got = send[None]
+    gx = got[:, :cap * D * h].view(world, cap, D, h)
+    gl = got[:, cap * D * h:].view(world, cap, P)
+    if in_place:
+        draws, logws = {}, {}
+        whole = {sl.series for p in parts for sl in p if sl.k0 == 0 and sl.k1 == ks[sl.series]}
+        for s in range(n_series):
+            if s not in whole:
+                draws[s] = torch.empty((ks[s] * D, h), dtype=torch.float64, device=dev)
+                logws[s] = torch.empty((ks[s], P), dtype=torch.float64, device=dev)
+        for r in range(world):
+            off = 0
+            for sl in parts[r]:
+                kk = sl.k1 - sl.k0
+                if sl.series in whole:        # one rank owns the whole series: a view of the gathered buffer
+                    draws[sl.series] = gx[r, off:off + kk].view(kk * D, h)
+                    logws[sl.series] = gl[r, off:off + kk]
+                else:
+                    draws[sl.series][sl.k0 * D:sl.k1 * D] = gx[r, off:off + kk].view(kk * D, h)
+                    logws[sl.series][sl.k0:sl.k1] = gl[r, off:off + kk]
+                off += kk
+        return {s: x.t() for s, x in draws.items()}, logws
+    gxn, gln = gx.cpu().numpy(), gl.cpu().numpy()
     draws = {s: np.empty((h, ks[s] * D)) for s in range(n_series)}
     logws = {s: np.empty((ks[s], P)) for s in range(n_series)}
     for r in range(world):
         off = 0
         for sl in parts[r]:
             kk = sl.k1 - sl.k0
-            draws[sl.series][:, sl.k0 * D:sl.k1 * D] = gx[r, off:off + kk].reshape(kk * D, h).T
-            logws[sl.series][sl.k0:sl.k1] = gl[r, off:off + kk]
+            draws[sl.series][:, sl.k0 * D:sl.k1 * D] = gxn[r, off:off + kk].reshape(kk * D, h).T
+            logws[sl.series][sl.k0:sl.k1] = gln[r, off:off + kk]
             off += kk
     return draws, logws
 

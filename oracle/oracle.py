@@ -273,3 +273,95 @@ def logml_np(prog: bytes, theta, noise, t, y, jitter=1e-5, g=None, step=0.0) -> 
     L = cho_factor(K, lower=True)[0]
     z = solve_triangular(np.tril(L), y, lower=True)
     return float(-0.5 * (len(y) * np.log(2 * np.pi) + 2 * np.log(np.diag(L)).sum() + z @ z))
+
+
+# ------------------------------------------------------------------------------------------------
+# The TIMED CPU baseline (oracle/nagp_cpu_blocked.c): the reference schedule with blocked, AVX2/FMA-vectorised
+# Cholesky / LU at -O3. Checked against the Oracle above in tests/test_cpu_baseline.py; used by bench.py's
+# cpu_baseline and --impl reference legs only.
+# ------------------------------------------------------------------------------------------------
+class BlockedCpu:
+    def __init__(self):
+        self.lib = _load("libnagp_cpu_blocked.so")
+
+    def set_num_threads(self, n: int) -> None:
+        self.lib.nagp_b_set_num_threads(int(n))
+
+    def num_threads(self) -> int:
+        return int(self.lib.nagp_b_num_threads())
+
+    @staticmethod
+    def _p(a):
+        return a.ctypes.data_as(C.c_void_p)
+
+    def factor_rates(self, n: int, reps: int = 20):
+        """Single-thread GFLOP/s of the blocked Cholesky and LU alone at order n."""
+        c, l = C.c_double(), C.c_double()
+        self.lib.nagp_b_factor_rates(C.c_int64(n), C.c_int64(reps), C.byref(c), C.byref(l))
+        return c.value, l.value
+
+    def forecast_instances(self, ens, n, k, h, t, y1, y2, logw0, ya=1.0, yb=0.0, jitter=1e-5, noise_pred=-1.0,
+                           g=None, step=0.0, theta_per_scenario=None, noise_per_scenario=None):
+        """Reference schedule (three factorisations + LU solves + h x h Cholesky per instance), K x P instances."""
+        y2 = np.ascontiguousarray(y2, np.float64)
+        K, P = y2.shape[0], ens.size
+        t = np.ascontiguousarray(t, np.float64)
+        y1 = np.ascontiguousarray(y1, np.float64)
+        logw0 = np.ascontiguousarray(logw0, np.float64)
+        theta = ens.theta if theta_per_scenario is None else np.ascontiguousarray(theta_per_scenario, np.float64)
+        noise = ens.noise if noise_per_scenario is None else np.ascontiguousarray(noise_per_scenario, np.float64)
+        gp = _opt(g, np.int32)
+        logw, mu = np.empty((K, P)), np.full((K, P, h), np.nan)
+        Ls, info = np.full((K, P, h, h), np.nan), np.zeros((K, P), np.int32)
+        f = self.lib.nagp_b_forecast_instances
+        f.restype = C.c_int32
+        rc = f(C.c_int64(K), C.c_int64(P), self._p(ens.prog), self._p(ens.prog_off), self._p(theta), self._p(ens.theta_off),
+               C.c_int64(0 if theta_per_scenario is None else theta.shape[1]), self._p(noise),
+               C.c_int64(0 if noise_per_scenario is None else P), C.c_double(jitter), C.c_double(noise_pred),
+               C.c_int64(n), C.c_int64(k), C.c_int64(h), self._p(t), gp[0] if gp else None, C.c_double(step),
+               self._p(y1), self._p(y2), C.c_double(ya), C.c_double(yb), self._p(logw0), self._p(logw), self._p(mu),
+               self._p(Ls), self._p(info))
+        return dict(rc=rc, logw=logw, mu=mu, L=Ls, info=info)
+
+    def logml_batch(self, ens, t, y, jitter=1e-5, g=None, step=0.0):
+        t = np.ascontiguousarray(t, np.float64)
+        y = np.ascontiguousarray(y, np.float64)
+        gp = _opt(g, np.int32)
+        B = ens.size
+        out, info = np.empty(B), np.zeros(B, np.int32)
+        f = self.lib.nagp_b_logml_batch
+        f.restype = C.c_int32
+        f(C.c_int64(B), self._p(ens.prog), self._p(ens.prog_off), self._p(ens.theta), self._p(ens.theta_off),
+          self._p(ens.noise), C.c_double(jitter), C.c_int64(len(y)), self._p(t), gp[0] if gp else None,
+          C.c_double(step), self._p(y), self._p(out), self._p(info))
+        return out, info
+
+    def factor_store(self, ens, t, y, n_cap, jitter=1e-5, g=None, step=0.0):
+        """Factor every instance on the first len(y) points and keep L [B, n_cap, n_cap] and z [B, n_cap]."""
+        t = np.ascontiguousarray(t, np.float64)
+        y = np.ascontiguousarray(y, np.float64)
+        gp = _opt(g, np.int32)
+        B, n = ens.size, len(y)
+        L, z, lm = np.zeros((B, n_cap, n_cap)), np.zeros((B, n_cap)), np.empty(B)
+        f = self.lib.nagp_b_factor_store
+        f.restype = C.c_int32
+        rc = f(C.c_int64(B), self._p(ens.prog), self._p(ens.prog_off), self._p(ens.theta), self._p(ens.theta_off),
+               self._p(ens.noise), C.c_double(jitter), C.c_int64(n), C.c_int64(n_cap), self._p(t),
+               gp[0] if gp else None, C.c_double(step), self._p(y), self._p(L), self._p(z), self._p(lm))
+        return dict(rc=rc, L=L, z=z, logml=lm, n=n, n_cap=n_cap)
+
+    def append(self, ens, store, t, y, k, jitter=1e-5, g=None, step=0.0):
+        """Rank-append of k points to every stored factor in place; t/g/y cover all store['n'] + k points."""
+        t = np.ascontiguousarray(t, np.float64)
+        y = np.ascontiguousarray(y, np.float64)
+        gp = _opt(g, np.int32)
+        B = ens.size
+        dl = np.empty(B)
+        f = self.lib.nagp_b_append
+        f.restype = C.c_int32
+        rc = f(C.c_int64(B), self._p(ens.prog), self._p(ens.prog_off), self._p(ens.theta), self._p(ens.theta_off),
+               self._p(ens.noise), C.c_double(jitter), C.c_int64(store["n"]), C.c_int64(k), C.c_int64(store["n_cap"]),
+               self._p(t), gp[0] if gp else None, C.c_double(step), self._p(y), self._p(store["L"]), self._p(store["z"]),
+               self._p(dl))
+        store["n"] += k
+        return dict(rc=rc, dlogml=dl)

@@ -14,9 +14,10 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-9
 
 
-@pytest.fixture(params=[1, 2], ids=["column-kernel", "tile-kernel"])
+@pytest.fixture(params=[1, 2, 3], ids=["column-kernel", "tile-kernel", "slot-kernel"])
 def veng(engine, request):
-    """The engine pinned to one factorisation kernel (1 = shared-memory column, 2 = DMMA tile)."""
+    """The engine pinned to one factorisation kernel (1 = shared-memory column, 2 = DMMA tile, 3 = slot kernel
+    wherever it applies: lag-grid times and 17 <= q <= 168; the tile kernel elsewhere)."""
     engine.set_variant(request.param)
     yield engine
     engine.set_variant(0)

@@ -1,6 +1,4 @@
-set -x
-for e in 1 2 3 4; do NAGP_LIB=gpurun_exp/libnagp_exp$e.so python bench.py --only-value --skip-sanity --steps 5 --warmup 3 > gpurun_out/exp$e.log 2>&1; done
-python bench.py --only-value --steps 5 --warmup 3 > gpurun_out/exp0.log 2>&1
-NAGP_LIB=gpurun_exp/libnagp_exp9.so python tools/dbg_timeline.py 1000 > gpurun_out/timeline.log 2>&1
-tools/chol8_bench > gpurun_out/chol8.log 2>&1
-cat gpurun_out/exp*.log gpurun_out/timeline.log gpurun_out/chol8.log
+# runs bench --only-value against every experiment build in gpurun_exp/
+for so in gpurun_exp/libnagp_*.so; do
+  echo -n "$so "; NAGP_LIB=$PWD/$so timeout -k 10 60 python bench.py --steps 10 --warmup 3 --only-value 2>&1 | tail -1
+done
