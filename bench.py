@@ -10,9 +10,17 @@ its own hyperparameters (what `n_hmc > 0` rejuvenation produces, /root/reference
 then weights/ESS and the mixture draws. The default-API fast path (`n_hmc == 0`, one factorisation
 per particle) is timed as well and reported under "fast_path".
 
-`value`  : device-resident inputs, CUDA-event timed, max over ranks (weak scaling: one series/rank).
+`value`  : device-resident inputs, CUDA-event timed, max over ranks (weak scaling: one series/rank), through the
+           product multi-GPU function `sharding.sharded_forecast` at every N (one packed all-gather of draws and
+           log-weights over NCCL when N > 1).
 `e2e`    : same step through the C ABI with pinned HOST buffers, H2D/D2H inside the timed region.
-`--impl reference`: the CPU restatement of the reference schedule (oracle/), all host threads.
+`parity_max_rel`: after the timed region 64 random instances of the timed batch are recomputed by the CPU oracle
+           (checker only) and compared with what the device wrote; the run fails above 1e-9.
+`c4`     : (N = 8, or `--c4`) BASELINE configs[3]: 53 series x 64 particles x 1000 nowcasts through
+           `sharding.partition` / `sharded_forecast` (device-resident) and through the public
+           `forecast_with_nowcasts_sharded` API, both regimes.
+`--impl reference`: the reference schedule on the host cores (oracle/nagp_cpu_blocked.c: blocked AVX2 Cholesky/LU,
+           -O3, checked against the oracle), all host threads.
 """
 from __future__ import annotations
 
@@ -114,21 +122,29 @@ def clocks_sampler_stop(p, path, dev_index, skip_lines=0):
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_reference(w, theta_k, noise_k, zeta, u, steps, warmup, target_s=12.0):
-    """Reference schedule on the host cores (oracle port), bounded sample of the same workload."""
-    from oracle.oracle import Oracle
-    o = Oracle()
+def host_threads():
     try:     # all host cores this process may use, whatever OMP_NUM_THREADS the launcher exported (torchrun sets 1)
-        o.set_num_threads(len(os.sched_getaffinity(0)))
+        return len(os.sched_getaffinity(0))
     except (AttributeError, OSError):
-        o.set_num_threads(os.cpu_count() or 1)
-    c = CFG
+        return os.cpu_count() or 1
+
+
+def cpu_reference(w, theta_k, noise_k, zeta, u, steps, warmup, target_s=12.0, cfg=None):
+    """Reference schedule on the host cores, bounded sample of the same workload. The timed code is
+    oracle/nagp_cpu_blocked.c (blocked, AVX2/FMA Cholesky and LU, -O3; tests/test_cpu_baseline.py checks it against the
+    scalar oracle); the draws come from the oracle's bit-exact draw routine."""
+    from oracle.oracle import BlockedCpu, Oracle
+    o, f = Oracle(), BlockedCpu()
+    nth = host_threads()
+    o.set_num_threads(nth)
+    f.set_num_threads(nth)
+    c = CFG if cfg is None else cfg
 
     def run(Ks):
         t0 = time.perf_counter()
-        r = o.forecast_instances(w.ens, c["n"], c["k"], c["h"], w.t, w.y1, w.y2[:Ks], w.logw0, w.ya, w.yb,
-                                 g=w.g, step=w.step, use_joint=False,
-                                 theta_per_scenario=theta_k[:Ks], noise_per_scenario=noise_k[:Ks])
+        r = f.forecast_instances(w.ens, c["n"], c["k"], c["h"], w.t, w.y1, w.y2[:Ks], w.logw0, w.ya, w.yb,
+                                 g=w.g, step=w.step, theta_per_scenario=None if theta_k is None else theta_k[:Ks],
+                                 noise_per_scenario=None if noise_k is None else noise_k[:Ks])
         o.draws(r["logw"], r["mu"], r["L"], zeta[:Ks], u=u[:Ks])
         return time.perf_counter() - t0
 
@@ -139,9 +155,90 @@ def cpu_reference(w, theta_k, noise_k, zeta, u, steps, warmup, target_s=12.0):
         run(Ks)
     times = [run(Ks) for _ in range(steps)]
     t = float(np.mean(times))
-    return dict(value=Ks * c["D"] / t, unit=UNIT, cores=o.num_threads(), kind="port",
+    n, m, h = c["n"], c["n"] + c["k"], c["h"]
+    fl = Ks * c["P"] * (n ** 3 / 3 + m ** 3 / 3 + 2 * m ** 3 / 3 + 2 * h * m * m + 2 * n * n + 2 * m * m)
+    pc, pl = f.factor_rates(m, 30)
+    return dict(value=Ks * c["D"] / t, unit=UNIT, cores=f.num_threads(), kind="port",
                 sample=f"{Ks} of {c['K']} scenarios x {c['P']} particles per step, reference schedule "
-                       f"(rebuild+add_data!+predict_mvn LU+chol+draws), OpenMP over instances"), t * 1e3, Ks
+                       f"(rebuild+add_data!+predict_mvn LU+chol+draws), OpenMP over instances; blocked AVX2 build: "
+                       f"{fl / t / 1e9 / f.num_threads():.2f} GFLOP/s/core over the whole schedule (per-entry kernel "
+                       f"evaluation included, as in the reference), factorisations alone {pc:.1f} (Cholesky) / {pl:.1f} (LU) "
+                       f"GFLOP/s single-thread at order {m}"), t * 1e3, Ks
+
+
+def read_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel from the committed ncu summary
+    named in profiles/current.json (None when absent)."""
+    try:
+        cur = json.load(open(os.path.join(ROOT, "profiles", "current.json")))["fused_kernel"]
+        rd = wr = None
+        import csv
+        for row in csv.reader(open(os.path.join(ROOT, "profiles", cur["summary"]))):
+            if len(row) < 4:
+                continue
+            mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(row[2])
+            if mult is None:
+                continue
+            if row[1] == "dram__bytes_read.sum":
+                rd = float(row[3]) * mult
+            elif row[1] == "dram__bytes_write.sum":
+                wr = float(row[3]) * mult
+        if rd is None or wr is None:
+            return None, None
+        return int(rd + wr), f"profiles/{cur['summary']} ({cur.get('note', 'ncu --set full, one launch')})"
+    except (OSError, KeyError, ValueError):
+        return None, None
+
+
+def cpu_logml_baseline(rank=0):
+    """BASELINE configs[2] on the host cores: a bounded sample of the 1024 x (n = 512) batched logML (blocked AVX2
+    Cholesky, per-entry kernel evaluation), all host threads."""
+    from nowcastautogp_b200 import synthetic as syn
+    from nowcastautogp_b200 import kernels as kn_
+    from oracle.oracle import BlockedCpu
+    f = BlockedCpu()
+    nth = host_threads()
+    f.set_num_threads(nth)
+    nm = 512
+    Bs = max(2 * nth, 16)
+    wm = syn.make_workload(nm, 0, 0, 1, 1024, seed=20261018 + 3 + 1000 * rank, max_depth=4, period=365.0)
+    ens = kn_.pack_ensemble(wm.trees[:Bs], np.asarray(wm.noise)[:Bs])
+    f.logml_batch(ens, wm.t[:nm], wm.y1, g=wm.g[:nm], step=wm.step)
+    t0 = time.perf_counter()
+    _, info = f.logml_batch(ens, wm.t[:nm], wm.y1, g=wm.g[:nm], step=wm.step)
+    dt = time.perf_counter() - t0
+    return {"value": Bs / dt, "unit": "logML evals/s", "cores": f.num_threads(), "kind": "port",
+            "sample": f"first {Bs} of the 1024 instances (n = 512), Gram + blocked Cholesky + solve + logdet, OpenMP over instances",
+            "ok": bool((info == 0).all())}
+
+
+def cpu_append_baseline(rank=0):
+    """BASELINE configs[4] on the host cores: factor a sample of the 256 particles at n = 2048 (blocked AVX2 Cholesky) and
+    append k = 1 point to every stored factor (forward substitution of the new row: reads the factor once)."""
+    from nowcastautogp_b200 import synthetic as syn
+    from nowcastautogp_b200 import kernels as kn_
+    from oracle.oracle import BlockedCpu
+    f = BlockedCpu()
+    nth = host_threads()
+    f.set_num_threads(nth)
+    na, ka = 2048, 1
+    Bs = int(min(max(nth, 4), 32))                      # 34 MB of factor per instance
+    wa = syn.make_workload(na + 8 * ka, 0, 0, 1, 256, seed=20261018 + 5 + 1000 * rank, max_depth=4, period=365.0)
+    ens = kn_.pack_ensemble(wa.trees[:Bs], np.asarray(wa.noise)[:Bs])
+    t0 = time.perf_counter()
+    st = f.factor_store(ens, wa.t[:na], wa.y1[:na], n_cap=na + 8 * ka, g=wa.g[:na], step=wa.step)
+    t_factor = time.perf_counter() - t0
+    ts = []
+    for i in range(4):
+        m_ = na + (i + 1) * ka
+        t0 = time.perf_counter()
+        f.append(ens, st, wa.t[:m_], wa.y1[:m_], ka, g=wa.g[:m_], step=wa.step)
+        ts.append(time.perf_counter() - t0)
+    t_app = float(np.median(ts))
+    return {"factor_per_s": Bs / t_factor, "appends_per_s": Bs / t_app, "unit": "particles/s", "cores": f.num_threads(),
+            "kind": "port", "append_GBps": Bs * 4.0 * na * (na + 1) / t_app / 1e9,
+            "sample": f"first {Bs} of the 256 particles (n = 2048): from-scratch factorisation {t_factor * 1e3:.0f} ms, "
+                      f"k = 1 rank-append {t_app * 1e3:.1f} ms per {Bs} particles, OpenMP over particles"}
 
 
 def main():
@@ -155,6 +252,8 @@ def main():
     ap.add_argument("--only-value", action="store_true", help="time only the device-resident step")
     ap.add_argument("--no-micro", action="store_true", help="skip the configs[2]/configs[4] micro-benchmarks")
     ap.add_argument("--variant", type=int, default=0, help="factorisation kernel: 0 auto, 2 tile kernel, 3 slot kernel")
+    ap.add_argument("--c4", action="store_true", help="run the BASELINE configs[3] block at any N (default: only at N = 8)")
+    ap.add_argument("--no-c4", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -220,25 +319,27 @@ def main():
     d_theta, d_noise = to_dev(theta_k), to_dev(noise_k)
     d_y1, d_y2, d_logw0 = to_dev(w.y1), to_dev(w.y2), to_dev(w.logw0)
     d_zeta, d_u = to_dev(zeta), to_dev(u)
-    d_logw = torch.empty((K, P), dtype=torch.float64, device=dev)
+    d_logw = torch.empty((K, P), dtype=torch.float64, device=dev)     # kernel-only / fast-path runs
     d_mu = torch.empty((K, P, h), dtype=torch.float64, device=dev)
     d_L = torch.empty((K, P, h, h), dtype=torch.float64, device=dev)
     d_info = torch.zeros((K, P), dtype=torch.int32, device=dev)
     d_x = torch.empty((K * D, h), dtype=torch.float64, device=dev)
     d_ens_theta, d_ens_noise = to_dev(w.ens.theta), to_dev(w.ens.noise)
     ens_dev = FlatEnsemble(w.ens.prog, w.ens.prog_off, d_ens_theta, w.ens.theta_off, d_ens_noise)
-    gather_x = gather_lw = None
-    if world > 1:
-        gather_x = torch.empty((world,) + tuple(d_x.shape), dtype=torch.float64, device=dev)
-        gather_lw = torch.empty((world, K, P), dtype=torch.float64, device=dev)
+    from nowcastautogp_b200.sharding import sharded_forecast
+
+    def compute_series(sl, x_out, lw_out):
+        # this rank's series, all K scenarios: outputs straight into the packed send buffer of the gather
+        eng.forecast_instances(ens_dev, n, k, h, w.t, d_y1, d_y2, d_logw0, w.ya, w.yb, g=w.g, step=w.step,
+                               theta=d_theta, noise=d_noise, K=K, logw=lw_out, mu=d_mu, L=d_L, info=d_info)
+        eng.draw(lw_out, d_mu, d_L, d_zeta, u=d_u, x=x_out, want_aux=False)
+
+    res = {}
 
     def step_device():
-        eng.forecast_instances(ens_dev, n, k, h, w.t, d_y1, d_y2, d_logw0, w.ya, w.yb, g=w.g, step=w.step,
-                               theta=d_theta, noise=d_noise, K=K, logw=d_logw, mu=d_mu, L=d_L, info=d_info)
-        eng.draw(d_logw, d_mu, d_L, d_zeta, u=d_u, x=d_x, want_aux=False)
-        if world > 1:   # the only collective on the path: gather log-weights and draws (NCCL/NVLink)
-            dist.all_gather_into_tensor(gather_x, d_x)
-            dist.all_gather_into_tensor(gather_lw, d_logw)
+        # the product multi-GPU path: series-first partition (one series per rank here), per-rank compute, ONE packed
+        # all-gather of draws and log-weights (NCCL over NVLink when world > 1; no collective at world = 1)
+        res["x"], res["lw"] = sharded_forecast(compute_series, world, K, h, D, P, device=dev, in_place=True)
 
     def kernel_only():
         eng.forecast_instances(ens_dev, n, k, h, w.t, d_y1, d_y2, d_logw0, w.ya, w.yb, g=w.g, step=w.step,
@@ -303,6 +404,22 @@ def main():
             dist.all_reduce(t_, op=dist.ReduceOp.MAX)
             ms = float(t_.item())
         return ms
+
+    def timed_local(fn, steps, warmup):
+        """CUDA-event time of this rank alone (no barrier, no max over ranks)."""
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        total = 0.0
+        for _ in range(steps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            e1.synchronize()
+            total += e0.elapsed_time(e1)
+        return total / steps
 
     # clocks: nvidia-smi samples every 100 ms and needs a moment to start, the timed region is tens of ms. Wait for
     # its first line (idle), time the steps, then keep rank 0's GPU under the same kernel until a few samples have
@@ -457,20 +574,219 @@ def main():
         def run():
             eng._check(lib.nagp_forecast_summary(ctx, 1, 0.0, 0.0, 0.0, h, K * D, d_x.data_ptr(), d_x.data_ptr(), 3,
                                                  d_p.data_ptr(), d_q.data_ptr()))
-        step_device()
+        kernel_only()
+        eng.draw(d_logw, d_mu, d_L, d_zeta, u=d_u, x=d_x, want_aux=False)
         ms = timed(run, max(3, args.steps // 2), 3)
         return {"what": "inverse 'positive' transformation in place + 25/50/75 % row quantiles of the (9, 20000) draws",
                 "ms_per_step": ms, "bytes_per_launch": int(h * K * D * (8 + 16 + 2 * 3 * 8 * 8))}
 
+    # ---- BASELINE configs[3] (the north_star target): 53 series x 64 particles x 1000 nowcasts, sharded over the ranks --------
+    def run_c4():
+        from nowcastautogp_b200 import synthetic as syn
+        from nowcastautogp_b200.sharding import partition
+        S4, n4, k4, h4, P4, K4, D4 = 53, 150, 1, 4, 64, 1000, 20
+        parts = partition(S4, K4, world)
+        mine = [sl.series for sl in parts[rank]]
+        ser = {}
+        for s_ in mine:
+            ws = syn.make_workload(n4, k4, h4, K4, P4, seed=1000 + s_, max_depth=4)
+            th_, nz_ = syn.perturbed_theta(ws.ens, K4, seed=5000 + s_)
+            rg = np.random.default_rng(9000 + s_)
+            ser[s_] = dict(w=ws, th=to_dev(th_), nz=to_dev(nz_), y1=to_dev(ws.y1), y2=to_dev(ws.y2), lw0=to_dev(ws.logw0),
+                           zeta=to_dev(rg.standard_normal((K4, D4, h4))), u=to_dev(rg.uniform(size=(K4, D4))),
+                           ens=FlatEnsemble(ws.ens.prog, ws.ens.prog_off, to_dev(ws.ens.theta), ws.ens.theta_off,
+                                            to_dev(ws.ens.noise)), th_host=th_, nz_host=nz_)
+        mu4 = torch.empty((K4, P4, h4), dtype=torch.float64, device=dev)
+        L4 = torch.empty((K4, P4, h4, h4), dtype=torch.float64, device=dev)
+        inf4 = torch.zeros((K4, P4), dtype=torch.int32, device=dev)
+
+        def comp_per_scenario(sl, x_out, lw_out):
+            d_ = ser[sl.series]; ws = d_["w"]
+            eng.forecast_instances(d_["ens"], n4, k4, h4, ws.t, d_["y1"], d_["y2"], d_["lw0"], ws.ya, ws.yb, g=ws.g,
+                                   step=ws.step, theta=d_["th"], noise=d_["nz"], K=K4, logw=lw_out, mu=mu4, L=L4, info=inf4)
+            eng.draw(lw_out, mu4, L4, d_["zeta"], u=d_["u"], x=x_out, want_aux=False)
+
+        def comp_shared(sl, x_out, lw_out):
+            d_ = ser[sl.series]; ws = d_["w"]
+            eng.forecast_with_nowcasts(d_["ens"], n4, k4, h4, ws.t, d_["y1"], d_["y2"], d_["lw0"], d_["zeta"], ws.ya, ws.yb,
+                                       g=ws.g, step=ws.step, u=d_["u"], x=x_out, logw=lw_out, info=inf4[0], K=K4, D=D4)
+
+        def local_only(comp):
+            # this rank's compute without the gather: per-rank time, for the load-imbalance figure
+            xs = torch.empty((K4 * D4, h4), dtype=torch.float64, device=dev)
+            ls = torch.empty((K4, P4), dtype=torch.float64, device=dev)
+            def run():
+                for sl in parts[rank]:
+                    comp(sl, xs, ls)
+            return run
+
+        def per_rank(ms_local):
+            if world == 1:
+                return [ms_local]
+            t_ = torch.tensor([ms_local], dtype=torch.float64, device=dev)
+            out_ = torch.empty(world, dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(out_, t_)
+            return [float(v) for v in out_.cpu()]
+
+        out = {"what": "BASELINE configs[3]: 53 series x 64 particles x 1000 nowcast scenarios (n=150, k=1, h=4, D=20), series-first "
+                       "partition over the ranks (sharding.partition), one packed all-gather per step (sharding.sharded_forecast)",
+               "series_per_rank": [len(p_) for p_ in parts], "draws_per_step": S4 * K4 * D4}
+        steps4 = max(2, min(args.steps, 5))
+        fl_inst = flops_per_instance(n4, k4, h4)
+        for name, comp in (("per_scenario_theta", comp_per_scenario), ("scenario_shared", comp_shared)):
+            ms = timed(lambda: sharded_forecast(comp, S4, K4, h4, D4, P4, device=dev, in_place=True), steps4, 3)
+            ms_loc = per_rank(timed_local(local_only(comp), steps4, 2))
+            blk = {"ms_per_step": ms, "value": S4 * K4 * D4 / (ms * 1e-3), "unit": UNIT, "per_rank_compute_ms": ms_loc,
+                   "imbalance_max_over_mean": max(ms_loc) / (sum(ms_loc) / len(ms_loc)),
+                   "partition_efficiency_cap": (S4 / world) / max(len(p_) for p_ in parts)}
+            if name == "per_scenario_theta":
+                fl_busy = max(len(p_) for p_ in parts) * K4 * P4 * fl_inst
+                blk["roofline"] = {"bound": "tensor", "unit": "TFLOP/s", "peak": None,
+                                   "achieved_busiest_rank": fl_busy / (max(ms_loc) * 1e-3) / 1e12,
+                                   "achieved_aggregate": S4 * K4 * P4 * fl_inst / (ms * 1e-3) / 1e12 / world,
+                                   "flops_per_instance": fl_inst}
+            else:
+                m4, q4 = n4 + k4, n4 + k4 + h4
+                fl_s = P4 * (q4 ** 3 / 3.0 + h4 * m4 * m4 + h4 * h4 * m4) + K4 * P4 * (2 * k4 * m4 + 2 * h4 * k4) + K4 * D4 * h4 * h4
+                blk["roofline"] = {"bound": "launch latency", "unit": "GFLOP/s", "flops_per_series": fl_s,
+                                   "achieved_aggregate": S4 * fl_s / (ms * 1e-3) / 1e9,
+                                   "note": "SURVEY 8(d) algorithmic work of the n_hmc == 0 schedule: 64 factorisations and O(k m) per "
+                                           "scenario, three launches per series: bounded by launch latency, not by a pipe"}
+            inf_ok = int(inf4.abs().max().item()) == 0
+            blk["ok"] = inf_ok
+            out[name] = blk
+        # parity of the C4 batch: 16 instances of this rank's first series against the oracle
+        if mine:
+            from oracle.oracle import Oracle
+            o = Oracle()
+            s0 = mine[0]; d_ = ser[s0]; ws = d_["w"]
+            lw_t = torch.empty((K4, P4), dtype=torch.float64, device=dev)
+            eng.forecast_instances(d_["ens"], n4, k4, h4, ws.t, d_["y1"], d_["y2"], d_["lw0"], ws.ya, ws.yb, g=ws.g, step=ws.step,
+                                   theta=d_["th"], noise=d_["nz"], K=K4, logw=lw_t, mu=mu4, L=L4, info=inf4)
+            torch.cuda.synchronize()
+            lw_h, mu_h, L_h = lw_t.cpu().numpy(), mu4.cpu().numpy(), L4.cpu().numpy()
+            rg = np.random.default_rng(77 + rank)
+            off = ws.ens.theta_off
+            worst = 0.0
+            refs, gots = [], []
+            for _ in range(16):
+                a_, p_ = int(rg.integers(K4)), int(rg.integers(P4))
+                prog = bytes(ws.ens.prog[ws.ens.prog_off[p_]:ws.ens.prog_off[p_ + 1]])
+                r_ = o.instance_joint(prog, d_["th_host"][a_, off[p_]:off[p_ + 1]], d_["nz_host"][a_, p_], n4, k4, h4, ws.t,
+                                      np.concatenate([ws.y1, ws.y2[a_]]), ws.ya, ws.yb, g=ws.g, step=ws.step)
+                refs.append(np.concatenate([[ws.logw0[p_] + r_["logml_m"] - r_["logml_n"]], r_["mu"], r_["L"].ravel()]))
+                gots.append(np.concatenate([[lw_h[a_, p_]], mu_h[a_, p_], L_h[a_, p_].ravel()]))
+            refs, gots = np.asarray(refs), np.asarray(gots)
+            for lo, hi in ((0, 1), (1, 1 + h4), (1 + h4, refs.shape[1])):
+                worst = max(worst, float(np.abs(gots[:, lo:hi] - refs[:, lo:hi]).max() / np.abs(refs[:, lo:hi]).max()))
+            pr_ = worst
+        else:
+            pr_ = 0.0
+        if world > 1:
+            pt_ = torch.tensor([pr_], dtype=torch.float64, device=dev)
+            dist.all_reduce(pt_, op=dist.ReduceOp.MAX)
+            pr_ = float(pt_.item())
+        out["parity_max_rel"] = pr_
+        if not pr_ < 1e-9:
+            raise SystemExit(f"bench c4: device disagrees with the CPU oracle ({pr_:.3e})")
+        try:
+            out["api"] = run_c4_api(S4, n4, k4, h4, P4, K4, D4, parts)
+        except Exception as e:      # noqa: BLE001 - the device-level block above stands on its own
+            if world > 1:
+                raise               # a rank that drops out of the collectives would hang the others
+            out["api"] = {"error": f"{type(e).__name__}: {e}"}
+        return out
+
+    def run_c4_api(S4, n4, k4, h4, P4, K4, D4, parts):
+        """The same configuration through the PUBLIC API: GPModel objects (prior-sampled particle sets that absorbed their
+        series in one SMC step), TData scenarios, `forecast_with_nowcasts_sharded` with n_hmc = 0 and n_hmc = 1."""
+        import nowcastautogp_b200 as nag
+        from nowcastautogp_b200 import synthetic as syn
+        from nowcastautogp_b200.gpmodel import GPModel
+        t_build = time.perf_counter()
+        d0 = np.datetime64("2022-10-01")
+        dates = d0 + 7 * np.arange(n4 + k4 + h4)
+        models, nowcasts = [], []
+        for s_ in range(S4):
+            _, raw = syn.weekly_series(n4, 1000 + s_ + 1)
+            rg = np.random.default_rng([2026, s_])
+            m_ = GPModel(dates[:n4], np.log(raw), n_particles=P4, rng=rg, engine=eng)
+            m_.fit_smc(schedule=[n4], n_mcmc=0, n_hmc=0, shuffle=False)
+            models.append(m_)
+            scen = raw[-1] * np.exp(0.1 + 0.027 * rg.standard_normal((k4, K4)))
+            nowcasts.append(nag.create_nowcast_data(scen, dates[n4:n4 + k4], transformation=np.log)
+                            if s_ in {sl.series for sl in parts[rank]} else [None] * K4)
+        build_s = time.perf_counter() - t_build
+        fdates = dates[n4 + k4:]
+        out = {"what": "forecast_with_nowcasts_sharded (public API, host objects in, NumPy matrices out on every rank)",
+               "build_s": build_s}
+        for name, kw in (("n_hmc_0", dict(n_hmc=0)), ("n_hmc_1", dict(n_hmc=1))):
+            resd = {}
+            def call():
+                resd["d"], resd["lw"] = nag.forecast_with_nowcasts_sharded(models, nowcasts, fdates, D4, device=dev, **kw)
+            ms = timed(call, 2 if name == "n_hmc_1" else 3, 1, do_flush=False)
+            ok_ = all(np.isfinite(v).all() and v.shape == (h4, K4 * D4) for v in resd["d"].values()) and len(resd["d"]) == S4
+            out[name] = {"ms_per_step": ms, "value": S4 * K4 * D4 / (ms * 1e-3), "unit": UNIT, "ok": bool(ok_)}
+        return out
+
     micro = None if args.no_micro else {"logml": micro_logml(), "append": micro_append(), "grad": micro_grad(),
                                         "hmc": micro_hmc(), "summary": micro_summary()}
 
-    # sanity: the step produced finite draws and no factorisation failed
+    c4 = run_c4() if (args.c4 or (world == 8 and not args.no_c4)) else None
+    if c4 is not None and rank == 0:
+        pk = 37.1
+        try:
+            pk = float(json.load(open(os.path.join(ROOT, "profiles", "r01_fp64_peak.json"))).get("dmma_m8n8k4_tflops", 37.1))
+        except OSError:
+            pass
+        rl = c4["per_scenario_theta"]["roofline"]
+        rl["peak"] = pk
+        rl["frac_busiest_rank"] = rl["achieved_busiest_rank"] / pk
+        rl["frac_aggregate"] = rl["achieved_aggregate"] / pk
+
+    # sanity + parity of the timed batch: the step produced finite draws and no factorisation failed, and 64 random
+    # (scenario, particle) instances of THIS batch agree with the CPU oracle (checker only) within 1e-9 relative
     step_device()
     torch.cuda.synchronize()
-    ok = bool(torch.isfinite(d_x).all().item()) and int(d_info.abs().max().item()) == 0
+    x_mine = res["x"][rank]
+    ok = bool(torch.isfinite(x_mine).all().item()) and int(d_info.abs().max().item()) == 0
     if not ok and not args.skip_sanity:
         raise SystemExit("bench step produced non-finite draws or a failed factorisation")
+
+    def parity_spot_check(n_check=64):
+        from oracle.oracle import Oracle
+        from nowcastautogp_b200 import kernels as kn_
+        o = Oracle()
+        rng_ = np.random.default_rng(12345 + rank)
+        lw_dev = res["lw"][rank].cpu().numpy()
+        mu_dev, L_dev = d_mu.cpu().numpy(), d_L.cpu().numpy()
+        off = w.ens.theta_off
+        worst = 0.0
+        picks = [(int(rng_.integers(K)), int(rng_.integers(P))) for _ in range(n_check)]
+        ref = {"logw": [], "mu": [], "L": []}
+        got = {"logw": [], "mu": [], "L": []}
+        for s_, p_ in picks:
+            prog = bytes(w.ens.prog[w.ens.prog_off[p_]:w.ens.prog_off[p_ + 1]])
+            y = np.concatenate([w.y1, w.y2[s_]])
+            r_ = o.instance_joint(prog, theta_k[s_, off[p_]:off[p_ + 1]], noise_k[s_, p_], n, k, h, w.t, y, w.ya, w.yb,
+                                  g=w.g, step=w.step)
+            if r_["info"] != 0:
+                return float("inf")
+            ref["logw"].append(w.logw0[p_] + r_["logml_m"] - r_["logml_n"]); got["logw"].append(lw_dev[s_, p_])
+            ref["mu"].append(r_["mu"]); got["mu"].append(mu_dev[s_, p_])
+            ref["L"].append(r_["L"]); got["L"].append(L_dev[s_, p_])
+        for key in ref:
+            a_, b_ = np.asarray(got[key], float), np.asarray(ref[key], float)
+            worst = max(worst, float(np.abs(a_ - b_).max() / max(np.abs(b_).max(), 1e-300)))
+        return worst
+
+    parity = parity_spot_check() if not args.skip_sanity else None
+    if world > 1:
+        pt = torch.tensor([parity if parity is not None else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(pt, op=dist.ReduceOp.MAX)
+        parity = float(pt.item()) if parity is not None else None
+    if parity is not None and not parity < 1e-9:
+        raise SystemExit(f"bench: the timed batch disagrees with the CPU oracle (max relative error {parity:.3e} > 1e-9)")
 
     if rank == 0:
         draws = K * D * world
@@ -482,6 +798,7 @@ def main():
         peak_tf = float(peaks.get("dmma_m8n8k4_tflops", 37.1))
         fl = K * P * flops_per_instance(n, k, h)
         achieved = fl / (ms_kernel * 1e-3) / 1e12
+        traffic, traffic_src = read_traffic()
         line = {
             "metric": METRIC, "value": draws / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -492,14 +809,17 @@ def main():
             "e2e": {"value": draws / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches),
+            "parity_max_rel": parity,
+            "parity_check": "64 random (scenario, particle) instances per rank of the timed batch: log-weight, mu and L33 vs the "
+                            "CPU oracle's joint factorisation, max relative error (run fails above 1e-9)",
             "roofline": {"bound": "tensor", "pipe": "fp64 (DFMA/DMMA; tcgen05 has no f64 kind)",
                          "kernel": "fused Gram+Cholesky+solve (nagp_fused)", "achieved": achieved,
                          "peak": peak_tf, "peak_source": "profiles/r01_fp64_peak.json (DMMA m8n8k4 measured on this "
                          "pool's B200; MEASURED_PEAKS.json has no FP64 entry)", "unit": "TFLOP/s",
                          "frac": achieved / peak_tf,
-                         "traffic": 2722304, "traffic_source": "profiles/r01_v2i_final_summary.csv: dram__bytes_read.sum + "
-                         "dram__bytes_write.sum of one launch (bytes; the Gram and the factor never leave shared memory, and the 23 MB of "
-                         "outputs were still in L2 when the counter was read)",
+                         "traffic": traffic, "traffic_source": traffic_src,
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch; the Gram and the factor never "
+                                         "leave shared memory, and the 23 MB of outputs are still in L2 when the counter is read",
                          "kernel_ms": ms_kernel,
                          "flops_per_launch": fl},
             "fast_path": {"what": "default API path n_hmc==0: one factorisation per particle, O(k^2+hk) per scenario",
@@ -526,6 +846,20 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             cb, _, _ = cpu_reference(w, theta_k, noise_k, zeta, u, steps=1, warmup=0)
             line["cpu_baseline"] = cb
+            if micro is not None:
+                line["logml_microbench"]["cpu_baseline"] = cpu_logml_baseline(rank)
+                line["append_microbench"]["cpu_baseline"] = cpu_append_baseline(rank)
+        if c4 is not None:
+            if not args.no_cpu_baseline:
+                from nowcastautogp_b200 import synthetic as syn
+                c4cfg = dict(n=150, k=1, h=4, P=64, K=1000, D=20)
+                w4 = syn.make_workload(150, 1, 4, 1000, 64, seed=1000, max_depth=4)
+                th4, nz4 = syn.perturbed_theta(w4.ens, 1000, seed=5000)
+                rg4 = np.random.default_rng(9000)
+                cb4, _, _ = cpu_reference(w4, th4, nz4, rg4.standard_normal((1000, 20, 4)), rg4.uniform(size=(1000, 20)),
+                                          steps=1, warmup=0, target_s=8.0, cfg=c4cfg)
+                c4["cpu_baseline"] = cb4
+            line["c4"] = c4
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

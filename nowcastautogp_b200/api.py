@@ -230,22 +230,35 @@ def forecast_with_nowcasts_sharded(base_models: Sequence[GPModel], nowcasts: Seq
                                    forecast_dates, forecast_draws_per_nowcast: int, *,
                                    inv_transformation: Callable = _identity, n_mcmc: int = 0, n_hmc: int = 0,
                                    ess_threshold: float = 0.0, forecast_n_hmc: Optional[int] = None,
-                                   group=None, device=None):
+                                   group=None, device=None, seed: Optional[int] = None):
     """One `forecast_with_nowcasts` per series (the per-jurisdiction loop of
     `docs/vignettes/getting-started.jl:540-552`), with the (series, scenario) pairs partitioned over
     the ranks of the current `torch.distributed` group (one process per GPU) and one final all-gather.
     Returns `(draws, logw)`: per series the `(h, K_s·D)` matrix and the `[K_s, P]` log-weights, on
-    every rank. All models must have the same number of particles."""
+    every rank. All models must have the same number of particles. Every (series, first-scenario) slice draws from
+    its own generator, derived from `seed` (or from the series' model generator when `seed` is None) and the slice,
+    so the scenarios of one series computed on different ranks use independent normals and uniforms."""
     from .sharding import sharded_forecast
     D = int(forecast_draws_per_nowcast)
     P = base_models[0].num_particles()
     assert all(m.num_particles() == P for m in base_models), "all series must use the same n_particles"
     h = len(list(forecast_dates))
 
+    def slice_rng(sl):
+        # One generator per (series, first scenario) slice. Models rebuilt from the same dicts carry identically seeded
+        # generators on every rank, so drawing from `base_models[s].rng` would give every rank the same normals and
+        # uniforms: the column blocks of one series computed on different ranks would share their noise.
+        if seed is not None:
+            base = int(seed)
+        else:
+            st = base_models[sl.series].rng.bit_generator.state.get("state", {})
+            base = int(st.get("state", 0)) % (2 ** 63) if isinstance(st, dict) else 0
+        return np.random.default_rng([base, int(sl.series), int(sl.k0)])
+
     def compute(sl):
         return _forecast_with_nowcasts(base_models[sl.series], nowcasts[sl.series][sl.k0:sl.k1], forecast_dates, D,
                                        n_mcmc=n_mcmc, n_hmc=n_hmc, ess_threshold=ess_threshold,
-                                       forecast_n_hmc=forecast_n_hmc, rng=None)
+                                       forecast_n_hmc=forecast_n_hmc, rng=slice_rng(sl))
 
     draws, logw = sharded_forecast(compute, len(base_models), [len(nc) for nc in nowcasts], h, D, P,
                                    group=group, device=device)
@@ -268,21 +281,25 @@ def _forecast_with_nowcasts(base_model: GPModel, nowcasts: Sequence[TData], fore
     ds0 = np.asarray(nowcasts[0].ds)
     shared_ds = all(len(nc.ds) == len(ds0) and np.array_equal(np.asarray(nc.ds), ds0) for nc in nowcasts)
 
-    if n_mcmc > 0 or not shared_ds:
-        # structure moves make the programs diverge per scenario: the reference's schedule verbatim,
-        # one model copy per scenario (forecasting.jl:133-155); every likelihood is still a device call
+    def scenario_loop(ncs):
+        # the reference's schedule verbatim, one model copy per scenario (forecasting.jl:133-155); every likelihood is
+        # still a device call
         blocks, lws = [], []
-        for nc in nowcasts:
-            m = GPModel.from_dict(base_dict, engine=base_model.engine, rng=rng)
-            m.add_data(nc.ds, nc.y)
-            m.maybe_resample(ess_threshold * m.num_particles())
+        for nc in ncs:
+            m_ = GPModel.from_dict(base_dict, engine=base_model.engine, rng=rng)
+            m_.add_data(nc.ds, nc.y)
+            m_.maybe_resample(ess_threshold * m_.num_particles())
             if n_mcmc > 0 and n_hmc > 0:
-                m.mcmc_structure(n_mcmc, n_hmc)
+                m_.mcmc_structure(n_mcmc, n_hmc)
             elif n_hmc > 0:
-                m.mcmc_parameters(n_hmc)
-            blocks.append(forecast(m, dates, D, forecast_n_hmc=forecast_n_hmc))
-            lws.append(np.asarray(m.log_weights, np.float64).copy())
+                m_.mcmc_parameters(n_hmc)
+            blocks.append(forecast(m_, dates, D, forecast_n_hmc=forecast_n_hmc))
+            lws.append(np.asarray(m_.log_weights, np.float64).copy())
         return np.hstack(blocks), np.stack(lws)
+
+    if n_mcmc > 0 or not shared_ds:
+        # structure moves make the programs diverge per scenario
+        return scenario_loop(nowcasts)
 
     m = GPModel.from_dict(base_dict, engine=base_model.engine, rng=rng)
     eng = m._engine()
@@ -331,20 +348,37 @@ def _forecast_with_nowcasts(base_model: GPModel, nowcasts: Sequence[TData], fore
     if not np.all(np.isfinite(lm)):
         from .engine import PosDefError
         raise PosDefError(1)
-    # maybe_resample! per scenario (forecasting.jl:138-141)
+    # maybe_resample! per scenario (forecasting.jl:138-141). Resampling swaps whole particles — structure, z and noise
+    # together. The batch shares one program per particle index across scenarios, so it can express the swap only when
+    # every particle has the same program (then a parent's z is still read under its own structure). With
+    # heterogeneous programs the scenarios that resample go through the reference's one-model-per-scenario schedule
+    # instead (same semantics, one device call per likelihood), the others stay in the batch.
     ess, w = eng.ess(logw)
-    for s in np.nonzero(ess < ess_threshold * P)[0]:
+    need = np.nonzero(ess < ess_threshold * P)[0]
+    same_program = all(p_.prog == m.particles[0].prog for p_ in m.particles)
+    if len(need) and not same_program:
+        slow = set(int(i) for i in need)
+        fast = [i for i in range(K) if i not in slow]
+        x_out, lw_out = np.empty((h, K * D)), np.empty((K, P))
+        xs, ls = scenario_loop([nowcasts[i] for i in need])
+        for j, i in enumerate(need):
+            x_out[:, i * D:(i + 1) * D] = xs[:, j * D:(j + 1) * D]
+            lw_out[i] = ls[j]
+        if fast:
+            # the ESS depends on the data and the particles only: none of these triggers again
+            xf, lf = _forecast_with_nowcasts(base_model, [nowcasts[i] for i in fast], forecast_dates, D, n_mcmc=n_mcmc,
+                                             n_hmc=n_hmc, ess_threshold=ess_threshold, forecast_n_hmc=forecast_n_hmc, rng=rng)
+            for j, i in enumerate(fast):
+                x_out[:, i * D:(i + 1) * D] = xf[:, j * D:(j + 1) * D]
+                lw_out[i] = lf[j]
+        return x_out, lw_out
+    off = ens.theta_off
+    for s in need:
         parents = rng.choice(P, size=P, p=w[s])
-        off = ens.theta_off
-        sp.z[s] = np.concatenate([sp.z[s, off[a]:off[a + 1]] for a in parents]) \
-            if len({off[a + 1] - off[a] for a in range(P)}) == 1 else sp.z[s]
-        if len({off[a + 1] - off[a] for a in range(P)}) == 1:
-            sp.noise_z[s] = sp.noise_z[s, parents]
-            lm[s] = lm[s, parents]
-            logw[s] = 0.0
-    # NOTE: resampling swaps whole particles; with heterogeneous programs the parents' structures
-    # differ, which the shared-program batch cannot express — such scenarios keep their weights
-    # (weighted mixture, statistically equivalent for the forecast).
+        sp.z[s] = np.concatenate([sp.z[s, off[a]:off[a + 1]] for a in parents])
+        sp.noise_z[s] = sp.noise_z[s, parents]
+        lm[s] = lm[s, parents]
+        logw[s] = 0.0
 
     def metropolis(n_steps, step_size=0.15):
         nonlocal lm

@@ -210,3 +210,37 @@ def test_flat_and_constant_series_issue_51(engine):   # test_model_fitting.jl:97
         assert fc.shape == (8, 25) and np.isfinite(fc).all() and (fc >= 0).all()
         if band:
             assert 50_000 < fc.mean() < 100_000
+
+
+@pytest.mark.gpu
+def test_fwn_per_scenario_resampling_swaps_whole_particles(engine):
+    """forecasting.jl:138-141 with `ess_threshold = 1` and `n_hmc > 0`: every scenario resamples, and resampling swaps
+    whole particles. The particles here have three hyperparameter slots each but DIFFERENT structures (Linear /
+    GammaExponential / Periodic), so a parent's z must never be read under another particle's program: the call has
+    to agree with the reference's one-model-per-scenario schedule run by hand with the same generator."""
+    from nowcastautogp_b200.api import _forecast_with_nowcasts
+    from nowcastautogp_b200.gpmodel import GPModel, Particle
+    data = ng.create_transformed_data(drange("2024-01-01", "2024-01-10"), VALUES10, transformation=ident)
+    m = GPModel(data.ds, data.y, n_particles=3, rng=np.random.default_rng(8), engine=engine)
+    m.particles = [Particle(bytes([2]), np.array([0.3, -0.2, 0.1]), -0.5),       # Linear: intercept is an identity slot
+                   Particle(bytes([4]), np.array([0.4, 0.0, -0.3]), -0.4),       # GammaExponential
+                   Particle(bytes([5]), np.array([-0.1, 0.6, 0.2]), -0.6)]       # Periodic
+    m.fit_smc(schedule=[len(data.y)], n_mcmc=0, n_hmc=0, shuffle=False)
+    sc = ng.create_nowcast_data(np.array([[12.0, 11.8, 12.4], [13.0, 12.5, 13.3]]), NOWCAST_DATES)
+    fd = np.array([D("2024-01-13"), D("2024-01-14")])
+    x, lw = _forecast_with_nowcasts(m, sc, fd, 4, n_hmc=2, ess_threshold=1.0, rng=np.random.default_rng(31))
+    assert x.shape == (2, 12) and np.isfinite(x).all()
+    assert np.array_equal(lw, np.zeros((3, 3)))                                   # weights are reset after resampling
+    # by hand: one model copy per scenario, in scenario order, same generator
+    rng = np.random.default_rng(31)
+    blocks = []
+    for nc in sc:
+        c = GPModel.from_dict(m.to_dict(), engine=engine, rng=rng)
+        c.add_data(nc.ds, nc.y)
+        assert c.maybe_resample(1.0 * c.num_particles())
+        c.mcmc_parameters(2)
+        blocks.append(ng.forecast(c, fd, 4))
+    assert np.array_equal(x, np.hstack(blocks))
+    # scenarios that do not trigger stay in the batched path: shapes and finiteness with a threshold nobody reaches
+    x2, lw2 = _forecast_with_nowcasts(m, sc, fd, 4, n_hmc=2, ess_threshold=0.0, rng=np.random.default_rng(31))
+    assert x2.shape == (2, 12) and np.isfinite(x2).all() and np.isfinite(lw2).all()

@@ -151,3 +151,58 @@ def test_sharded_fit_single_process():
     assert [d["s"] for d in out] == [0, 1, 2, 3]
     with pytest.raises(ValueError):
         sharded_fit(lambda idx: [], 2)
+
+
+class _StubModel:
+    """Just enough of a GPModel for forecast_with_nowcasts_sharded: a generator, a particle count, an engine."""
+
+    def __init__(self, seed):
+        self.rng = np.random.default_rng(seed)
+
+    def num_particles(self):
+        return 2
+
+    def _engine(self):
+        return None
+
+
+def _rng_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from nowcastautogp_b200 import api
+
+        def fake(base_model, nowcasts, dates, D, *, n_mcmc=0, n_hmc=0, ess_threshold=0.0, forecast_n_hmc=None, rng=None):
+            kk, h = len(nowcasts), len(dates)
+            return rng.standard_normal((h, kk * D)), np.zeros((kk, 2))      # pure noise: what the generator supplies
+
+        api._forecast_with_nowcasts = fake
+        models = [_StubModel(7)]                 # the same seed on every rank, as models rebuilt from gathered dicts have
+        draws, _ = api.forecast_with_nowcasts_sharded(models, [[None] * 8], [0, 1, 2], 4)
+        q.put((rank, draws[0]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_forecast_slices_use_independent_generators():
+    """One series split over two ranks: the ranks' column blocks must not repeat each other's normals (identically
+    seeded model generators on every rank would make them identical), and every rank must hold the same full matrix."""
+    import torch.multiprocessing as mp
+    with socket.socket() as s_:
+        s_.bind(("127.0.0.1", 0))
+        port = s_.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_rng_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert np.array_equal(res[0], res[1]) and res[0].shape == (3, 32)
+    first, second = res[0][:, :16], res[0][:, 16:]          # scenarios 0-3 (rank 0) and 4-7 (rank 1), D = 4
+    assert not np.array_equal(first, second)
+    assert abs(np.corrcoef(first.ravel(), second.ravel())[0, 1]) < 0.5
