@@ -144,6 +144,8 @@ class CoalescingEngine:
 class _Client:
     """What a `GPModel` sees as its engine."""
 
+    is_coalescing = True      # lockstep fits keep every step a mergeable logML request (no per-series factor store)
+
     def __init__(self, hub: CoalescingEngine, cid: int):
         self._hub, self._cid = hub, cid
 

@@ -456,21 +456,60 @@ class GPModel:
             assert sorted(self.obs_order.tolist()) == list(range(n)), "obs_order must be a permutation of the observations"
         else:
             self.obs_order = self.rng.permutation(n) if shuffle else np.arange(n)
-        for step in schedule:
-            step = int(min(step, n))
-            idx = np.sort(self.obs_order[:step])
-            new = self.logml(self.particles, idx)
-            if not np.any(np.isfinite(new)):
-                raise PosDefError(1)
-            with np.errstate(invalid="ignore"):
-                self.log_weights = self.log_weights + np.where(np.isfinite(self._logml), new - self._logml, 0.0)
-            self._logml = new
-            self.n_obs = step
-            resampled = self.maybe_resample(ess_fraction * self.num_particles())
-            if not adaptive_rejuvenation or resampled:
-                self.mcmc_structure(n_mcmc, n_hmc)
-            if verbose:
-                print(f"fit_smc: {step}/{n} observations, ESS {self.effective_sample_size():.2f}")
+        # Steps after which no particle changed (no resampling, no rejuvenation: n_mcmc == 0, or adaptive rejuvenation
+        # that did not fire) extend the particles' Cholesky factors by the new observations instead of re-factoring:
+        # the factors stay on the device in an appendable store (`nagp_factor_store_large` / `nagp_factor_append`,
+        # rank-append of the new rows: the stored factor is read once). Observations are kept in arrival order
+        # (`obs_order`, never sorted: the row order of a Gram matrix is arbitrary), on the lag grid of the whole series.
+        use_store = (n_mcmc == 0 or adaptive_rejuvenation) and not getattr(self._engine(), "is_coalescing", False)
+        store = None                        # (Factor, failed-particle mask): valid while the particles are unchanged
+        t_all = g_all = None
+        step_all = 0.0
+        self.append_steps = 0               # schedule steps served by a rank-append (diagnostic, used by the tests)
+        try:
+            for step in schedule:
+                step = int(min(step, n))
+                if use_store and t_all is None:
+                    t_all, g_all, step_all = self._times(self.ds)
+                    y_all = self.y_transform.apply(self.y)
+                if use_store and store is not None and step > self.n_obs and store[0].n == self.n_obs:
+                    new_idx = self.obs_order[self.n_obs:step]
+                    dl, _, info = self._engine().factor_append(store[0], t_all[new_idx], y_all[new_idx],
+                                                               g_new=None if g_all is None else g_all[new_idx], check=False)
+                    bad = store[1] | (info != 0)
+                    store = (store[0], bad)
+                    with np.errstate(invalid="ignore"):
+                        new = np.where(bad, -np.inf, self._logml + dl)
+                    self.append_steps += 1
+                elif use_store:
+                    if store is not None:
+                        store[0].free()
+                    idx = self.obs_order[:step]
+                    f = self._engine().factor_store_large(pack_particles(self.particles, self.config), t_all[idx], y_all[idx],
+                                                          capacity=n, g=None if g_all is None else g_all[idx], step=step_all,
+                                                          check=False)
+                    store = (f, f.info != 0)
+                    new = np.where(f.info == 0, f.logml_n, -np.inf)
+                else:
+                    new = self.logml(self.particles, np.sort(self.obs_order[:step]))
+                if not np.any(np.isfinite(new)):
+                    raise PosDefError(1)
+                with np.errstate(invalid="ignore"):
+                    self.log_weights = self.log_weights + np.where(np.isfinite(self._logml), new - self._logml, 0.0)
+                self._logml = new
+                self.n_obs = step
+                resampled = self.maybe_resample(ess_fraction * self.num_particles())
+                rejuvenate = (not adaptive_rejuvenation or resampled) and n_mcmc > 0
+                if not adaptive_rejuvenation or resampled:
+                    self.mcmc_structure(n_mcmc, n_hmc)
+                if (resampled or rejuvenate) and store is not None:     # the particles changed: their factors are stale
+                    store[0].free()
+                    store = None
+                if verbose:
+                    print(f"fit_smc: {step}/{n} observations, ESS {self.effective_sample_size():.2f}")
+        finally:
+            if store is not None:
+                store[0].free()
 
     # ---- AutoGP.add_data!: src/forecasting.jl:135 -----------------------------------------------------
     def add_data(self, ds, y) -> None:

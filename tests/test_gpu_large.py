@@ -128,3 +128,40 @@ def test_large_not_positive_definite_reports_info(engine):
         assert info[0] > 0 and info[0] <= 8
     finally:
         engine.set_jitter(1e-5)
+
+
+def test_fit_smc_unrejuvenated_steps_use_rank_append(engine, oracle):
+    """`fit_smc!` with `n_mcmc = 0` (/root/reference/src/make_and_fit_model.jl:88-91: linear_schedule + fit_smc!): after the
+    first schedule step every step is a rank-append on the stored factors (observations in shuffled arrival order, lag
+    grid of the whole series). The log-weight trajectory must follow the oracle's from-scratch logML of the same
+    observations at every step."""
+    import nowcastautogp_b200 as ng
+    from nowcastautogp_b200.api import linear_schedule
+    from nowcastautogp_b200.gpmodel import GPModel, pack_particles
+    n, P = 96, 6
+    rng = np.random.default_rng(17)
+    ds = np.datetime64("2023-01-01") + 7 * np.arange(n)
+    y = np.log(50.0) + np.sin(2 * np.pi * np.arange(n) / 52.0) + 0.15 * rng.standard_normal(n)
+    m = GPModel(ds, y, n_particles=P, rng=np.random.default_rng(3), engine=engine)
+    sched = linear_schedule(n, 0.125)
+    traj = []
+    orig = m.maybe_resample
+
+    def spy(thr):                       # record the weights before any resampling resets them; never resample
+        traj.append((m.n_obs, m._logml.copy()))
+        return False
+    m.maybe_resample = spy
+    m.fit_smc(schedule=sched, n_mcmc=0, n_hmc=0)
+    m.maybe_resample = orig
+    assert m.append_steps == len(sched) - 1 and [s for s, _ in traj] == sched
+    ens = pack_particles(m.particles, m.config)
+    t_all, g_all, step_all = m._times(m.ds)
+    ys = m.y_transform.apply(m.y)
+    for step, lm in traj:
+        idx = m.obs_order[:step]
+        want, winfo = oracle.logml_batch(ens, t_all[idx], ys[idx], g=g_all[idx], step=step_all)
+        ok = winfo == 0
+        assert ok.any() and np.array_equal(np.isfinite(lm), ok)
+        assert rel(lm[ok], want[ok]) < 1e-9, step
+    # and the cumulative log-weights are the last logML (weights start at 0, nothing resampled)
+    assert rel(m.log_weights[ok], want[ok]) < 1e-9
