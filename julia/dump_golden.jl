@@ -3,7 +3,8 @@
 #
 # The build image has no Julia, so tests/golden/ currently holds mpmath / scikit-learn / closed-form
 # vectors only (DESIGN.md §3, "parity unpinned"). Once this script's output is committed,
-# tests/test_oracle_pinning.py picks it up (test_autogp_golden) and the oracle is pinned to AutoGP itself.
+# tests/test_autogp_golden.py picks it up (test_autogp_golden for the CPU oracle, test_autogp_golden_gpu for the CUDA path)
+# and both are pinned to AutoGP itself.
 using AutoGP, Dates, Random, JSON3, Distributions
 include(joinpath(@__DIR__, "NowcastAutoGPB200.jl"))
 using .NowcastAutoGPB200: flatten_model, time_arguments

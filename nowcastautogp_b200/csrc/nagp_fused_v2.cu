@@ -8,7 +8,6 @@
 // warp), factors every diagonal tile in registers with shuffles while building its inverse by the same row
 // operations; seven row-owning warps accumulate sum_P L_IP L_JP^T with one column of lookahead, solve their tiles of the column with one DMMA
 // pair against that inverse, and add the last term of the next column with the solved tiles still in registers.
-// (NAGP_V2_PANEL=0 builds the earlier schedule: eight row owners, the owner of a diagonal tile factors it.)
 //
 // One tile layout serves as A operand, B operand and accumulator: a sum over k may run in any order, so
 // the two k-chunks of a DMMA pair are taken as the even columns (k-slot t <-> column 2t) and the odd
@@ -27,29 +26,10 @@
 // Arithmetic contract: docs/KERNEL_SPEC.md §3-§6.
 #include <algorithm>
 
-#ifndef NAGP_QUIET_SIBLING
-#define NAGP_QUIET_SIBLING 0   // 1: the warp sharing the owner's scheduler skips the lookahead (measured neutral)
-#endif
-#ifndef NAGP_EXP
-#define NAGP_EXP 0   // timing-attribution experiments (tools/exp_build.sh); 0 in every product build
-#endif
 
 #include "nagp_kernels.cuh"
 #include "nagp_tree.cuh"
 #include "nagp_tile.cuh"
-
-#if NAGP_EXP == 9
-__device__ long long g_nagp_dbg[8192];
-extern "C" int nagp_debug_read(long long *out, int count)
-{
-    return (int)cudaMemcpyFromSymbol(out, g_nagp_dbg, sizeof(long long) * count);
-}
-#define DBG_T(J, ph) do { if (b == 0 && lane == 0) g_nagp_dbg[((J) * 8 + dbg_w) * 8 + (ph)] = clock64(); } while (0)
-#define DBG_G(ph) do { if (b == 0 && tid == 0) g_nagp_dbg[8000 + (ph)] = clock64(); } while (0)
-#else
-#define DBG_T(J, ph) do { } while (0)
-#define DBG_G(ph) do { } while (0)
-#endif
 
 namespace nagp {
 
@@ -58,12 +38,8 @@ namespace {
 #ifndef NAGP_V2_WARPS
 #define NAGP_V2_WARPS 8
 #endif
-#ifndef NAGP_V2_PANEL
-#define NAGP_V2_PANEL 1   // 1: the diagonal chain runs on its own warp scheduler (see "panel schedule" below); 0: rotating owner
-#endif
 constexpr int kW2 = NAGP_V2_WARPS;      // warps per CTA of the tile kernel
 constexpr int kT2 = kW2 * 32;
-#if NAGP_V2_PANEL
 // Panel schedule: a dependent FP64 chain shares its scheduler's issue slots and FP64 pipe with whatever else
 // runs there (tools/chol8_bench2.cu: the 8x8 factorisation takes 1.2 k cycles next to idle warps or to busy
 // warps on the OTHER three schedulers, 1.8 k next to one DMMA-issuing warp on its own scheduler, 4.4 k next to
@@ -77,9 +53,6 @@ static_assert(kW2 == 8, "the panel schedule assumes 8 warps: two per scheduler")
 #define NAGP_V2_PANEL_ROWS 7            // 6: the second warp of the chain's scheduler idles; 7: it owns rows too
 #endif
 constexpr int kNB = NAGP_V2_PANEL_ROWS; // row-owning warps
-#else
-constexpr int kNB = kW2;
-#endif
 constexpr int kTB = kNB * 32;
 constexpr int kMaxTilesPerWarp = (29 + kNB - 1) / kNB;   // ceil(nt / kNB), nt <= 29
 // The kernel is instantiated per KM = register slots (tile rows) per row-owning warp, 3, 4 and the full size: the
@@ -89,29 +62,9 @@ constexpr int kMaxTilesPerWarp = (29 + kNB - 1) / kNB;   // ceil(nt / kNB), nt <
 constexpr int kSlots3 = kMaxTilesPerWarp < 3 ? kMaxTilesPerWarp : 3;
 constexpr int kSlots4 = kMaxTilesPerWarp < 4 ? kMaxTilesPerWarp : 4;
 
-// DMMA inner loop of the left-looking update for NA tile rows of one warp: per P one 16-byte LDS for
-// the shared B fragment (tile (Jc, P)), and per row one 16-byte LDS + two DMMAs (one per k-chunk, on
-// separate accumulator chains).
-template <int KM, int NA>
-__device__ __forceinline__ void kloop(double (&acc)[KM][2][2], uint32_t bp,
-                                      const uint32_t (&rowa)[KM], int P0, int P1)
-{
-#pragma unroll 2
-    for (int P = P0; P < P1; ++P) {
-        const uint32_t off = (uint32_t)P * 512u;
-        const double2 bf = lds128(bp + off);
-#pragma unroll
-        for (int u = 0; u < NA; ++u) {
-            const double2 af = lds128(rowa[u] + off);
-            dmma(acc[u][0][0], acc[u][0][1], af.x, bf.x);
-            dmma(acc[u][1][0], acc[u][1][1], af.y, bf.y);
-        }
-    }
-}
-
-#if NAGP_V2_PANEL
-// Inner loop of the panel schedule: as kloop, and with WY the warp that carries the observation vector also
-// adds L_{Jc,P} z_P to its per-lane partial sums (two FMAs on the B fragment it has loaded anyway; the four
+// DMMA inner loop of the left-looking update for NA tile rows of one warp: per P one 16-byte LDS for the shared B
+// fragment (tile (Jc, P)), and per row one 16-byte LDS + two DMMAs (one per k-chunk, on separate accumulator chains).
+// With WY the warp that carries the observation vector also adds L_{Jc,P} z_P to its per-lane partial sums (two FMAs on the B fragment it has loaded anyway; the four
 // lanes of a row are summed once per column).
 template <int KM, int NA, bool WY>
 __device__ __forceinline__ void kloop_p(double (&acc)[KM][2][2], double &ys0, double &ys1, uint32_t bp,
@@ -152,7 +105,6 @@ __device__ __forceinline__ void hand_over(const double (&c)[KM][2], double (&acc
     sts128(rowa[U] + (uint32_t)(J + 1) * 512u, g2.x - (acc[U][0][0] + acc[U][1][0]), g2.y - (acc[U][0][1] + acc[U][1][1]));
     acc[U][0][0] = acc[U][0][1] = acc[U][1][0] = acc[U][1][1] = 0.0;
 }
-#endif
 
 struct V2Layout {
     int nt;            // tile rows/cols of the matrix (rows padded to Q = 8 nt)
@@ -194,19 +146,6 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
     double *sig = reinterpret_cast<double *>(aux(3));
     double *tab = reinterpret_cast<double *>(aux(4));
 
-#if NAGP_EXP == 9
-    if (lane == 0 && blockIdx.x < 600) {
-        unsigned smid, wid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
-        if (smid == 0) {   // who lives on SM 0, and in which hardware warp slot
-            int slot = atomicAdd((int *)&g_nagp_dbg[8100], 1);
-            if (slot < 40) g_nagp_dbg[8101 + slot] = ((long long)blockIdx.x << 32) | (warp << 8) | wid;
-            g_nagp_dbg[8150] = blockIdx.x;
-        }
-    }
-#endif
-#if NAGP_V2_PANEL
     // Roles by hardware scheduler, not by warp index: the hardware warp slot (%warpid; slot mod 4 = scheduler) is
     // some permutation of the CTA's warps that differs between co-resident CTAs, and the point of the panel
     // schedule is that the chain warps of BOTH resident CTAs share one scheduler with as little row work as possible.
@@ -234,14 +173,6 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
     }
     __syncthreads();
     const int role = s_role[warp];
-#endif
-#if NAGP_EXP == 9
-#if NAGP_V2_PANEL
-    const int dbg_w = role == -1 ? 0 : role == -2 ? 4 : role < 3 ? role + 1 : role + 2;   // timeline row of this warp
-#else
-    const int dbg_w = warp;
-#endif
-#endif
     for (int I = tid; I < nt; I += kT2)
         for (int J = 0; J <= I; ++J) s_ti[tri(I) + J] = (unsigned char)I;
     // times are common to every instance of the launch
@@ -263,7 +194,6 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
         const int64_t to = a.theta_off[p], ntheta = a.theta_off[p + 1] - to;
         const double *theta_g = a.theta + s * a.theta_stride_k + to;
 
-        DBG_G(0);
         if (tid == 0) s_info = 0;
         if (a.compiled) {
             // compiled once per particle on the host: every (scenario, particle) instance just copies it
@@ -287,7 +217,6 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
         }
         const int ntab = tp.ntab, ncp = tp.ncp;
 
-        DBG_G(1);
         // ---- lag tables and changepoint sigma tables ------------------------------------------------
         for (int e = tid; e < ntab * G; e += kT2) {
             int id = e / G, lg = e - id * G;
@@ -302,7 +231,6 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
         }
         __syncthreads();
 
-        DBG_G(2);
         // ---- Gram into row-major tiles: a warp writes two whole tiles per iteration; lane (r, c) owns
         //      the accumulator-layout pair (r, 2c), (r, 2c+1) of each, so stores are contiguous 16 B per lane
         const double nz = a.noise[s * a.noise_stride_k + p];
@@ -359,12 +287,6 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                     }
                 }
                 double out[GW];
-#if NAGP_EXP == 3
-                if (true) {
-#pragma unroll
-                    for (int x = 0; x < GW; ++x) out[x] = 0.0;
-                } else
-#endif
                 tree_evalw<GW>(tp, cx, ii, jj, lag, out);
                 if (!interior) {
 #pragma unroll
@@ -390,7 +312,6 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
         }
         __syncthreads();
 
-        DBG_G(3);
         // ---- left-looking tile-column Cholesky with one column of lookahead ---------------------------
         // A warp owns the tile rows I == warp (mod 8). Slot u counts them from the bottom (u = 0 is the
         // last row below nt), so the rows still active in column J are always the prefix u < NA and the
@@ -399,12 +320,8 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
         // warps already accumulate column J+1 over P < J (every term that does not need column J).
         const int lr = lane >> 2, lj = lane & 3;
         const int oi0 = op_idx(lr, 2 * lj), oi1 = op_idx(lr, 2 * lj + 1);
-#if NAGP_V2_PANEL
         const bool bulk = role >= 0;
         const int bi = bulk ? role : kNB;   // row-owner index 0..5
-#else
-        const int bi = warp;
-#endif
         const int nreg = bi < nt ? (nt - 1 - bi) / kNB + 1 : 0;   // regular rows of this warp
         const int Ilast = bi + (nreg - 1) * kNB;
         const bool has_y = (bi == nt % kNB);
@@ -416,137 +333,8 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
             rowa[u] = tiles_a + (uint32_t)(tri(I > 0 ? I : 0) * 512 + lane * 16);
         }
         double accn[KM][2][2];   // [slot][k-chunk chain][acc regs] partial sums of the current column
-        double yacc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
         for (int u = 0; u < KM; ++u) { accn[u][0][0] = accn[u][0][1] = accn[u][1][0] = accn[u][1][1] = 0.0; }
-        int pre_done = 0;                       // terms P < pre_done are already in accn / yacc
-
-        // accumulate sum_{P0 <= P < P1} L_IP L_{Jc,P}^T for the owned rows I >= Jc (and the observation row)
-        // skip_top: leave out the topmost active row (a diagonal tile that was brought up to date early)
-        auto accumulate = [&](int Jc, int P0, int P1, bool skip_top) {
-#if NAGP_EXP == 2 || defined(NAGP_EXP_NOACC)
-            return;
-#endif
-            if (P0 >= P1) return;
-            const int NA = (Ilast >= Jc ? (Ilast - Jc) / kNB + 1 : 0) - (skip_top ? 1 : 0);
-            const uint32_t bp = tiles_a + (uint32_t)(tri(Jc) * 512 + lane * 16);
-            switch (NA) {
-            case 1: kloop<KM, (KM >= 1 ? 1 : 1)>(accn, bp, rowa, P0, P1); break;
-            case 2: kloop<KM, (KM >= 2 ? 2 : 1)>(accn, bp, rowa, P0, P1); break;
-            case 3: kloop<KM, (KM >= 3 ? 3 : 1)>(accn, bp, rowa, P0, P1); break;
-            case 4: kloop<KM, (KM >= 4 ? 4 : 1)>(accn, bp, rowa, P0, P1); break;
-            case 5: kloop<KM, (KM >= 5 ? 5 : 1)>(accn, bp, rowa, P0, P1); break;
-            case 6: kloop<KM, (KM >= 6 ? 6 : 1)>(accn, bp, rowa, P0, P1); break;
-            case 7: kloop<KM, (KM >= 7 ? 7 : 1)>(accn, bp, rowa, P0, P1); break;
-            case 8: kloop<KM, (KM >= 8 ? 8 : 1)>(accn, bp, rowa, P0, P1); break;
-            default: break;
-            }
-            if (has_y) {
-                const uint32_t yp = yv_a + lj * 16;
-#pragma unroll 2
-                for (int P = P0; P < P1; ++P) {
-                    const double2 bf = lds128(bp + (uint32_t)P * 512u);
-                    double2 af = lds128(yp + P * 64);
-                    if (lr != 0) af.x = af.y = 0.0;
-                    dmma(yacc[0][0], yacc[0][1], af.x, bf.x);
-                    dmma(yacc[1][0], yacc[1][1], af.y, bf.y);
-                }
-            }
-        };
-
-#if !NAGP_V2_PANEL
-        for (int J = 0; J < nt; ++J) {
-            const bool owner = (warp == (J % kW2));
-            const int NA = Ilast >= J ? (Ilast - J) / kNB + 1 : 0;   // active regular rows (I >= J)
-            // (1) remaining terms of column J, (2) C = A_IJ - sum
-            DBG_T(J, 0);
-            accumulate(J, pre_done, J, false);
-            double c[KM][2], cy[2] = {0.0, 0.0}, d0 = 0.0, d1 = 0.0;
-            const uint32_t joff = (uint32_t)J * 512u;
-#pragma unroll
-            for (int u = 0; u < KM; ++u) {
-                c[u][0] = 0.0; c[u][1] = 0.0;
-                if (u < NA) {
-                    const double2 g2 = lds128(rowa[u] + joff);
-                    c[u][0] = g2.x - (accn[u][0][0] + accn[u][1][0]);
-                    c[u][1] = g2.y - (accn[u][0][1] + accn[u][1][1]);
-                    d0 = c[u][0]; d1 = c[u][1];   // ends up holding slot NA-1: the diagonal tile of its owner
-                }
-                accn[u][0][0] = accn[u][0][1] = accn[u][1][0] = accn[u][1][1] = 0.0;
-            }
-            if (has_y) {
-                double2 yj = lds128(yv_a + (J * 8 + 2 * lj) * 8);
-                if (lr != 0) yj.x = yj.y = 0.0;
-                cy[0] = yj.x - (yacc[0][0] + yacc[1][0]);
-                cy[1] = yj.y - (yacc[0][1] + yacc[1][1]);
-                yacc[0][0] = yacc[0][1] = yacc[1][0] = yacc[1][1] = 0.0;
-            }
-            DBG_T(J, 1);
-            if (owner) {
-                // (3) diagonal tile (slot NA-1): factor + invert in registers, publish, release the others
-                double w0, w1, piv[8];
-#if NAGP_EXP == 1
-                const int bad = 0; w0 = (lr == 2 * lj) ? 1.0 : 0.0; w1 = (lr == 2 * lj + 1) ? 1.0 : 0.0; (void)piv;
-#else
-                const int bad = chol8_inv(d0, d1, w0, w1, lane, q - J * 8, piv);
-#endif
-                const uint32_t dt = tiles_a + (uint32_t)((tri(J) + J) * 512);
-                sts128(dt + lane * 16, d0, d1);
-                sts128(invL_a + lane * 16, w0, w1);
-                if (KEEP && a.Wkeep) {
-                    double *wk = a.Wkeep + ((size_t)b * nt + J) * 64;
-                    wk[oi0] = w0; wk[oi1] = w1;
-                }
-                if (bad && lane == 0 && NAGP_EXP == 0) s_info = J * 8 + bad;
-                __syncwarp();
-                DBG_T(J, 2);
-                asm volatile("bar.arrive 1, %0;" ::"n"(kT2) : "memory");
-                pre_done = 0;   // its own lookahead is deferred to the next column (hidden behind that owner)
-            } else if (NAGP_QUIET_SIBLING && (warp & 3) == ((J % kW2) & 3)) {
-                // shares its scheduler (and FP64 pipe) with the owner: leave the pipe to the serial
-                // diagonal factorisation and catch up at the top of the next column
-                pre_done = 0;
-                DBG_T(J, 2);
-                asm volatile("bar.sync 1, %0;" ::"n"(kT2) : "memory");
-            } else {
-                // (4) lookahead: column J+1 over P < J
-                if (J + 1 < nt) accumulate(J + 1, 0, J, false);
-                pre_done = J;
-                DBG_T(J, 2);
-                asm volatile("bar.sync 1, %0;" ::"n"(kT2) : "memory");
-            }
-            // (5) triangular solve of the column: X = C * invL^T, stored in operand layout
-            DBG_T(J, 3);
-#if NAGP_EXP == 4
-            if (false) {
-#else
-            if (!s_info) {
-#endif
-                const double2 ib = lds128(invL_a + lane * 16);
-                const int nsolve = owner ? NA - 1 : NA;   // rows strictly below the diagonal
-#pragma unroll
-                for (int u = 0; u < KM; ++u) {
-                    if (u < nsolve) {
-                        // the accumulator pair (g, 2t), (g, 2t+1) is this lane's A fragment of both k-chunks
-                        double x0 = 0.0, x1 = 0.0;
-                        dmma(x0, x1, c[u][0], ib.x);
-                        dmma(x0, x1, c[u][1], ib.y);
-                        sts128(rowa[u] + joff, x0, x1);
-                    }
-                }
-                if (has_y) {
-                    double x0 = 0.0, x1 = 0.0;
-                    dmma(x0, x1, cy[0], ib.x);
-                    dmma(x0, x1, cy[1], ib.y);
-                    if (lr == 0) sts128(yv_a + (J * 8 + 2 * lj) * 8, x0, x1);
-                }
-            }
-            DBG_T(J, 4);
-            __syncthreads();
-            DBG_T(J, 5);
-            if (s_info) break;
-        }
-#else
         // ---- panel schedule -----------------------------------------------------------------------------
         // Named barriers: 1 = "inverse of diagonal tile J published" (chain warp arrives, row owners wait),
         // 2 = "C_JJ is in its tile" (the owner of row J arrives, the chain warp waits), 3 = "tile (J+1, J) is
@@ -559,23 +347,10 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
         if (role == -1) {
             for (int J = 0; J < nt; ++J) {
                 if (J > 0) asm volatile("bar.sync 2, 64;" ::: "memory");
-                DBG_T(J, 1);
                 const uint32_t dt = tiles_a + (uint32_t)((tri(J) + J) * 512 + lane * 16);
                 const double2 cj = lds128(dt);
                 double d0 = cj.x, d1 = cj.y, w0, w1, piv[8];
-#if NAGP_EXP == 9
-                if (d0 == 123.456) DBG_T(J, 5);   // forces the load to complete before the stamp
-                DBG_T(J, 4);
-#endif
-#ifdef NAGP_V2_ROLLED_CHOL8
-                const int bad = chol8_inv_rolled(d0, d1, w0, w1, lane, q - J * 8); (void)piv;
-#else
                 const int bad = chol8_inv(d0, d1, w0, w1, lane, q - J * 8, piv);
-#endif
-#if NAGP_EXP == 9
-                if (w0 == 123.456) DBG_T(J, 5);
-                DBG_T(J, 3);
-#endif
                 sts128(dt, d0, d1);
                 sts128(invL_a + (uint32_t)((J & 1) * 512 + lane * 16), w0, w1);
                 if (KEEP && a.Wkeep) {
@@ -584,7 +359,6 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                 }
                 if (bad && lane == 0) s_info = J * 8 + bad;
                 __syncwarp();
-                DBG_T(J, 2);
                 asm volatile("bar.arrive 1, %0;" ::"n"(kTB + 32) : "memory");
                 if (bad) break;
             }
@@ -607,9 +381,6 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                 if (has_y) cyv = lds64(yv_a + lr * 8);
             }
             auto lookahead = [&](int Jc, int P1, int NA) {     // NA: this warp's rows I >= Jc
-#if NAGP_EXP == 2 || defined(NAGP_EXP_NOACC)
-                return;
-#endif
                 if (P1 <= 0) return;
                 const uint32_t bp = tiles_a + (uint32_t)(tri(Jc) * 512 + lane * 16);
                 if (has_y) {
@@ -643,7 +414,6 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                 const bool more = J + 1 < nt;
                 const bool owns_next = more && ph == 1;
                 const int n2 = owns_next ? nsolve - 1 : nsolve;          // rows below diagonal J+1
-                DBG_T(J, 0);
                 asm volatile("bar.sync 1, %0;" ::"n"(kTB + 32) : "memory");
                 // The chain warp can already be factoring tile J+1 (it only needs the hand-over of one row owner): a
                 // failure it flags there must not make a late row owner leave one column before the others.
@@ -691,7 +461,6 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                     part += __shfl_xor_sync(kFull, part, 2);
                     if (lj == 0) sts64(yv_a + (J * 8 + lr) * 8, part);
                 }
-                DBG_T(J, 4);
                 if (!more) break;
                 if (!owns_next) asm volatile("bar.sync 3, %0;" ::"n"(kTB) : "memory");   // tile (J+1, J) is written (its owner only arrives)
                 else __syncwarp();
@@ -718,18 +487,14 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                     cyv = lds64(yv_a + ((J + 1) * 8 + lr) * 8) - sy;
                     ys0 = ys1 = 0.0;
                 }
-                DBG_T(J, 1);
                 // (3) lookahead: column J+2 over P <= J, in the shadow of the factorisation of diagonal tile J+1
                 if (J + 2 < nt) {
                     if (!owns_next2) asm volatile("bar.sync 4, %0;" ::"n"(kTB) : "memory");   // tile (J+2, J) is written
                     lookahead(J + 2, J + 1, n2);
                 }
-                DBG_T(J, 2);
             }
         }
         __syncthreads();
-#endif
-        DBG_G(4);
 
         if (KEEP && a.Lkeep && !s_info) {
             // keep the factor for the gradient kernel in its fragment-major tile layout (op_idx: columns c and
@@ -783,7 +548,6 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
             a.info[b] = 0;
         }
 
-        DBG_G(5);
         // ---- predictive moments / fast-path tail blocks ------------------------------------------------
         const int kh = k + h;
         if (a.mu && have_y2) {
@@ -876,9 +640,6 @@ int fused_v2_grid(const V2Plan &pl, int64_t B, int num_sms)
         cudaGetLastError();
         per_sm = 1;
     }
-#if NAGP_EXP == 9
-    if (getenv("NAGP_V2_ONE_CTA")) per_sm = 1;       // timeline experiment: one resident matrix per SM
-#endif
     int64_t g = (int64_t)per_sm * num_sms;
     return (int)std::min<int64_t>(g, B);
 }
