@@ -61,19 +61,23 @@ namespace {
 constexpr int kM3 = 3;                  // matrix slots per CTA
 constexpr int kRO = NAGP_V3_RO;         // row owners per slot: tile rows dealt mod kRO
 constexpr int kWS = 2 + kRO;            // warps per slot: chain, Gram producer, row owners
-constexpr int kW3 = kM3 * kWS;          // warps per CTA
+// With six row owners per slot the CTA carries three spare warps that exit at once: 27 warps fall on the four schedulers
+// as 7/7/7/6, the scheduler with six holds the three chain warps and the three spares (so the chains stay alone on it), the
+// others six row owners and one Gram producer each.
+constexpr int kSpare = kRO == 6 ? 3 : 0;
+constexpr int kW3 = kM3 * kWS + kSpare; // warps per CTA
 constexpr int kT3 = kW3 * 32;
 constexpr int kST = kWS * 32;           // threads per slot
 constexpr int kMaxNt3 = 21;             // the slot map has one byte per tile of a 21 x 21 triangle
-constexpr int kInvBufs = kRO <= 3 ? 4 : 8;   // inverse-tile buffers (power of two > kRO; the chain also checks the row owners' progress)
+constexpr int kInvBufs = 4;             // inverse-tile buffers (power of two; the chain checks the row owners' progress before reuse)
 constexpr int kBig = 1 << 20;           // counter value that releases every waiter (abort)
-static_assert(kRO <= 6 && kInvBufs > kRO, "control block layout / inverse buffers");
+static_assert(kRO == 3 || kRO == 6, "row owners per slot");
 
 // per-slot control block (ints)
 enum : int { C_INV = 0, C_DIAG = 1, C_GRAM = 2, C_INFO = 3, C_TOP = 4, C_DONE = 4 + kRO, C_NEXT = 4 + 2 * kRO /* 2 ints, 8-byte aligned */,
              C_RED = 6 + 2 * kRO };
-static_assert((C_NEXT % 2) == 0 && C_RED * 4 + 4 * kWS * 8 <= (kRO <= 3 ? 256 : 512), "control block layout");
-constexpr int kCtrlBytes = kRO <= 3 ? 256 : 512;
+static_assert((C_NEXT % 2) == 0 && C_RED * 4 + 4 * kWS * 8 <= (kRO <= 3 ? 256 : 384), "control block layout");
+constexpr int kCtrlBytes = kRO <= 3 ? 256 : 384;
 
 // Counters in shared memory couple the roles of a slot. The writer's lanes store their data, __syncwarp(), then
 // lane 0 stores the counter; the reader polls the counter and then loads the data. NAGP_V3_FENCE=1 makes the
@@ -324,15 +328,17 @@ __global__ void __launch_bounds__(kT3, 1) fused_v3_kernel(const FusedArgs a, con
         };
 #pragma unroll 1
         for (int w = 0; w < kW3; ++w) s_role[w] = -1;
-        // chains (and, when there is room beside them, the Gram producers) on the least populated scheduler; row owner r
-        // of every slot on scheduler 1 + r mod 3 of the remaining three
+        // chains on the least populated scheduler (with the spare warps, if any); row owner r of every slot on scheduler
+        // 1 + r mod 3 of the remaining three, one Gram producer on each of those
         for (int mm = 0; mm < kM3; ++mm) { int w = pick(so[0]); s_slot[w] = (signed char)mm; s_role[w] = 0; }
+        for (int i = 0; i < kSpare; ++i) { int w = pick(so[0]); s_slot[w] = 0; s_role[w] = 127; }      // spare: exits below
         for (int mm = 0; mm < kM3; ++mm)
             for (int r = 0; r < kRO; ++r) { int w = pick(so[1 + r % 3]); s_slot[w] = (signed char)mm; s_role[w] = (signed char)(2 + r); }
-        for (int mm = 0; mm < kM3; ++mm) { int w = pick(kRO == 3 ? so[1 + mm % 3] : so[0]); s_slot[w] = (signed char)mm; s_role[w] = 1; }
+        for (int mm = 0; mm < kM3; ++mm) { int w = pick(so[1 + mm % 3]); s_slot[w] = (signed char)mm; s_role[w] = 1; }
     }
     __syncthreads();
     const int slot = s_slot[warp], role = s_role[warp];
+    if (role == 127) return;                  // spare warp (keeps the chains' scheduler free of row work)
     const int stid = role * 32 + lane;        // thread index inside the slot
 
     unsigned char *sb = smem3 + lay.off_slots + (size_t)slot * lay.slot_stride;
@@ -426,8 +432,7 @@ __global__ void __launch_bounds__(kT3, 1) fused_v3_kernel(const FusedArgs a, con
                 if (J == 0) WAIT_GE(seen, ctrl_a + C_GRAM * 4, 1);
                 else WAIT_GE(seen, ctrl_a + C_DIAG * 4, J + 1);
                 if (J >= kInvBufs) {
-                    // the inverse buffer of step J was last read in step J - kInvBufs (a row owner without rows left
-                    // hands nothing over, so nothing else bounds how far it may lag)
+                    // the inverse buffer of step J was last read in step J - kInvBufs: wait until every row owner is past it
                     for (int r = 0; r < kRO; ++r) WAIT_GE(seen, ctrl_a + (C_DONE + r) * 4, J - kInvBufs + 1);
                 }
                 TR(J, 0);
