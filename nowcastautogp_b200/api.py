@@ -70,7 +70,7 @@ def make_and_fit_model(data: TData, *, n_particles: int = 1, smc_data_proportion
 
 def make_and_fit_models(datas: Sequence[TData], *, n_particles: int = 1, smc_data_proportion: float = 0.1,
                         flat_threshold: float = 1e-3, config: Optional[GPConfig] = None, rng=None, engine=None,
-                        share_order: bool = True, **kwargs) -> List[GPModel]:
+                        share_order: bool = True, rngs: Optional[Sequence] = None, **kwargs) -> List[GPModel]:
     """`make_and_fit_model` for S independent series at once (the per-jurisdiction loop of
     `docs/vignettes/getting-started.jl:540-552`): one host thread per series runs the unchanged SMC logic, and a
     `CoalescingEngine` merges the S concurrent likelihood / gradient requests of every step into one device
@@ -87,7 +87,11 @@ def make_and_fit_models(datas: Sequence[TData], *, n_particles: int = 1, smc_dat
         return []
     eng = default_engine() if engine is None else engine
     seq = np.random.SeedSequence(rng.integers(2 ** 63) if rng is not None else None)
-    rngs = [np.random.default_rng(ss) for ss in seq.spawn(S + 1)]
+    spawned = [np.random.default_rng(ss) for ss in seq.spawn(S + 1)]
+    if rngs is not None:        # explicit per-series generators (the sharded fit: results independent of the rank count)
+        assert len(rngs) == S, "rngs must hold one generator per series"
+        spawned[:S] = list(rngs)
+    rngs = spawned
     same_dates = all(len(d.ds) == len(datas[0].ds) and np.array_equal(np.asarray(d.ds), np.asarray(datas[0].ds))
                      for d in datas)
     order = rngs[S].permutation(len(datas[0].y)) if (share_order and same_dates and kwargs.get("shuffle", True)) else None
@@ -134,8 +138,9 @@ def make_and_fit_models_sharded(datas: Sequence[TData], *, seed: int = 0, engine
     eng = default_engine() if engine is None else engine
 
     def fit_local(idx: List[int]) -> List[dict]:
-        rng = np.random.default_rng([int(seed), int(idx[0])])
-        models = make_and_fit_models([datas[s] for s in idx], rng=rng, engine=eng, **kwargs)
+        # one generator per SERIES, derived from (seed, series index): independent of how the series fall on the ranks
+        models = make_and_fit_models([datas[s] for s in idx], rngs=[np.random.default_rng([int(seed), int(s)]) for s in idx],
+                                     rng=np.random.default_rng([int(seed), 10 ** 9 + int(idx[0])]), engine=eng, **kwargs)
         return [m.to_dict() for m in models]
 
     dicts = sharded_fit(fit_local, len(datas), group=group)

@@ -521,9 +521,13 @@ class GPModel:
         self.y = np.concatenate([self.y, y])
         self.obs_order = np.concatenate([self.obs_order, np.arange(self.n_obs, len(self.y))])
         new = self.logml(self.particles, np.arange(len(self.y)))
-        if not np.all(np.isfinite(new)):
+        # a particle that left the fit with weight -inf (its Gram was not positive definite) carries no mass: only
+        # the particles that still count must factor
+        alive = np.isfinite(self.log_weights)
+        if not np.all(np.isfinite(new[alive])) or not alive.any():
             raise PosDefError(1)
-        self.log_weights = self.log_weights + (new - old)     # log w += logML(m) - logML(n) [R]
+        with np.errstate(invalid="ignore"):
+            self.log_weights = np.where(alive, self.log_weights + (new - old), -np.inf)     # log w += logML(m) - logML(n) [R]
         self._logml = new
         self.n_obs = len(self.y)
 
@@ -739,7 +743,16 @@ class GPModel:
         eng = self._engine()
         f = eng.factor_store(ens, len(idx), 0, len(fd), t, self.y_transform.apply(self.y[idx]), self.log_weights,
                              self.y_transform.slope, self.y_transform.intercept, g=g, step=step,
-                             noise_pred=-1.0 if noise_pred is None else float(noise_pred))
+                             noise_pred=-1.0 if noise_pred is None else float(noise_pred), check=False)
+        # PosDefException only for particles that carry weight (MvNormal's constructor would never see the others)
+        alive = np.isfinite(self.log_weights)
+        bad = np.asarray(f.info) != 0
+        if (bad & alive).any() or not alive.any():
+            f.free()
+            raise PosDefError(int(np.asarray(f.info)[bad & alive][0]) if (bad & alive).any() else 1)
         mu, L = eng.predict(f)
         f.free()
+        if bad.any():       # zero-weight particles: finite placeholders, never drawn from
+            mu = np.where(bad[:, None], 0.0, mu)
+            L = np.where(bad[:, None, None], np.eye(L.shape[-1])[None], L)
         return MixtureMVN(eng, self.log_weights.copy(), mu, L)

@@ -77,8 +77,12 @@ def fit_boxcox_lambda(x: np.ndarray) -> float:
             break
         lo, hi = lo * 2.0, hi * 2.0
     res = optimize.minimize_scalar(neg, bracket=(lo, 0.0, hi), method="brent", options={"xtol": 1e-10})
-    if not np.isfinite(res.fun):
-        res = optimize.minimize_scalar(neg, bounds=(-5.0, 5.0), method="bounded", options={"xatol": 1e-10})
+    # On near-constant data the profile likelihood is flat and the maximiser is arbitrary: the reference's unbounded
+    # optimiser then returns a pathological λ and `get_transformations` falls back to the log transformation (issue
+    # #51, `src/transformations.jl:164-168`). Signal the same case instead of returning whatever Brent stopped at:
+    # no measurable likelihood gain over λ = 0, or a non-finite optimum.
+    if not np.isfinite(res.fun) or not np.isfinite(res.x) or (f0 - res.fun) < 1e-8 * max(1.0, abs(f0)):
+        return float("nan")
     return float(res.x)
 
 

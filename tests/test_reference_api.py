@@ -244,3 +244,24 @@ def test_fwn_per_scenario_resampling_swaps_whole_particles(engine):
     # scenarios that do not trigger stay in the batched path: shapes and finiteness with a threshold nobody reaches
     x2, lw2 = _forecast_with_nowcasts(m, sc, fd, 4, n_hmc=2, ess_threshold=0.0, rng=np.random.default_rng(31))
     assert x2.shape == (2, 12) and np.isfinite(x2).all() and np.isfinite(lw2).all()
+
+
+@pytest.mark.gpu
+def test_zero_weight_particle_does_not_break_forecasts(engine):
+    """A particle whose Gram is not positive definite leaves `fit_smc` with weight -inf (it carries no mass). Forecasts,
+    `add_data` and `forecast_with_nowcasts` must keep working on the particles that count (the MvNormal constructor of the
+    reference never sees a zero-weight component's factorisation fail the mixture)."""
+    from nowcastautogp_b200.gpmodel import GPModel, Particle
+    data = ng.create_transformed_data(drange("2024-01-01", "2024-01-10"), VALUES10, transformation=ident)
+    m = GPModel(data.ds, data.y, n_particles=2, rng=np.random.default_rng(5), engine=engine)
+    m.particles = [Particle(bytes([4]), np.array([0.2, 0.0, -0.3]), -0.4),
+                   Particle(bytes([1]), np.array([-200.0]), -200.0)]          # Constant ~ 0 with noise ~ 0: jitter only
+    m.config.noise = None
+    m.fit_smc(schedule=[len(data.y)], n_mcmc=0, n_hmc=0, shuffle=False, ess_fraction=0.0)
+    m.log_weights = np.array([0.0, -np.inf])                                   # as after a failed factorisation
+    fd = drange("2024-01-11", "2024-01-13")
+    x = ng.forecast(m, fd, 6)
+    assert x.shape == (3, 6) and np.isfinite(x).all()
+    sc = [ng.TData(SINGLE_DATES, [12.0], transformation=ident)]
+    r = ng.forecast_with_nowcasts(m, sc, [D("2024-01-12")], 4)
+    assert r.shape == (1, 4) and np.isfinite(r).all()
