@@ -307,6 +307,21 @@ def _forecast_with_nowcasts(base_model: GPModel, nowcasts: Sequence[TData], fore
         return scenario_loop(nowcasts)
 
     m = GPModel.from_dict(base_dict, engine=base_model.engine, rng=rng)
+    alive = np.isfinite(m.log_weights)
+    if not alive.all() and alive.any():
+        # particles that left the fit with weight -inf (Gram not positive definite) carry no mass: the batched paths run
+        # on the others and report -inf for these
+        pruned = base_model.to_dict()
+        keep = np.nonzero(alive)[0]
+        pruned["particles"] = [pruned["particles"][i] for i in keep]
+        pruned["log_weights"] = [pruned["log_weights"][i] for i in keep]
+        pruned["logml"] = [pruned["logml"][i] for i in keep]
+        x_, lw_ = _forecast_with_nowcasts(GPModel.from_dict(pruned, engine=base_model.engine, rng=rng), nowcasts, forecast_dates,
+                                          forecast_draws_per_nowcast, n_mcmc=n_mcmc, n_hmc=n_hmc, ess_threshold=ess_threshold,
+                                          forecast_n_hmc=forecast_n_hmc, rng=rng)
+        lw_full = np.full((len(nowcasts), len(alive)), -np.inf)
+        lw_full[:, keep] = lw_
+        return x_, lw_full
     eng = m._engine()
     K, P, n, k, h = len(nowcasts), m.num_particles(), len(m.y), len(ds0), len(dates)
     idx = m._obs_idx()

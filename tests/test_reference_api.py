@@ -255,10 +255,10 @@ def test_zero_weight_particle_does_not_break_forecasts(engine):
     data = ng.create_transformed_data(drange("2024-01-01", "2024-01-10"), VALUES10, transformation=ident)
     m = GPModel(data.ds, data.y, n_particles=2, rng=np.random.default_rng(5), engine=engine)
     m.particles = [Particle(bytes([4]), np.array([0.2, 0.0, -0.3]), -0.4),
-                   Particle(bytes([1]), np.array([-200.0]), -200.0)]          # Constant ~ 0 with noise ~ 0: jitter only
+                   Particle(bytes([2]), np.array([0.3, 40.0, 40.0]), -200.0)]  # Linear, amplitude 1e16: rank 2 + jitter, not PD in FP64
     m.config.noise = None
     m.fit_smc(schedule=[len(data.y)], n_mcmc=0, n_hmc=0, shuffle=False, ess_fraction=0.0)
-    m.log_weights = np.array([0.0, -np.inf])                                   # as after a failed factorisation
+    assert np.isneginf(m.log_weights[1]) and np.isfinite(m.log_weights[0])     # the fit flags it, keeps it, gives it no mass
     fd = drange("2024-01-11", "2024-01-13")
     x = ng.forecast(m, fd, 6)
     assert x.shape == (3, 6) and np.isfinite(x).all()
