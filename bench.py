@@ -359,14 +359,13 @@ def main():
     h_ens = FlatEnsemble(w.ens.prog, w.ens.prog_off, w.ens.theta, w.ens.theta_off, w.ens.noise)
     h2d = sum(t_.numel() * t_.element_size() for t_ in (h_theta, h_noise, h_y1, h_y2, h_logw0, h_zeta, h_u))
     h2d += w.ens.prog.nbytes + w.ens.prog_off.nbytes + w.ens.theta_off.nbytes + w.t.nbytes + w.g.nbytes
-    h2d += h_logw.numel() * 8    # log-weights go back in for the draw call
     d2h = sum(t_.numel() * t_.element_size() for t_ in (h_x, h_logw, h_info))
 
     def step_e2e():
-        # C ABI with host buffers: H2D of every input, D2H of draws, log-weights and info
-        eng.forecast_instances(h_ens, n, k, h, w.t, h_y1, h_y2, h_logw0, w.ya, w.yb, g=w.g, step=w.step,
-                               theta=h_theta, noise=h_noise, K=K, logw=h_logw, mu=d_mu, L=d_L, info=h_info)
-        eng.draw(h_logw, d_mu, d_L, h_zeta, u=h_u, x=h_x, want_aux=False)
+        # ONE C-ABI call with host buffers (nagp_forecast_with_nowcasts_theta): H2D of every input, fused instances, ESS +
+        # draws, D2H of draws, log-weights and info
+        eng.forecast_with_nowcasts_theta(h_ens, n, k, h, w.t, h_y1, h_y2, h_logw0, h_zeta, h_theta, h_noise, w.ya, w.yb,
+                                         g=w.g, step=w.step, u=h_u, x=h_x, logw=h_logw, info=h_info, K=K, D=D)
 
     h2d_fast = sum(t_.numel() * t_.element_size() for t_ in (h_y1, h_y2, h_logw0, h_zeta, h_u)) + \
         w.ens.prog.nbytes + w.ens.theta.nbytes + w.ens.noise.nbytes + w.t.nbytes + w.g.nbytes

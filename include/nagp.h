@@ -224,6 +224,22 @@ int32_t nagp_forecast_with_nowcasts(nagp_ctx *ctx, int64_t K, int64_t P, int64_t
                                     double ess_thr, const double *zeta,
                                     double *x, double *logw_out, double *ess_out, int32_t *info);
 
+/* The same body for PER-SCENARIO hyperparameters — what the particles look like after `mcmc_parameters!` has run on every
+ * scenario's model copy (/root/reference/src/forecasting.jl:145-149 with n_hmc > 0, then :152-155): one fused Gram +
+ * factorisation per (scenario, particle), log-weights, ESS/resample, draws, in ONE call (nagp_forecast_instances +
+ * nagp_draw without the round trip of the moments). theta/noise strides as in nagp_forecast_instances; info[K*P]. */
+int32_t nagp_forecast_with_nowcasts_theta(nagp_ctx *ctx, int64_t K, int64_t P, int64_t D,
+                                          const uint8_t *prog, const int64_t *prog_off,
+                                          const double *theta, const int64_t *theta_off, int64_t theta_stride_k,
+                                          const double *noise, int64_t noise_stride_k, double noise_pred,
+                                          int64_t n, int64_t k, int64_t h,
+                                          const double *t, const int32_t *g, double step,
+                                          const double *y1, const double *y2, double ya, double yb,
+                                          const double *logw0,
+                                          const int32_t *comp, const double *u, const double *u_res,
+                                          double ess_thr, const double *zeta,
+                                          double *x, double *logw_out, double *ess_out, int32_t *info);
+
 /* ---- (f4) inverse transformation + per-date quantiles of a forecast matrix --------------------------------
  * /root/reference/src/forecasting.jl:50,73,166 apply `inv_transformation.(x)` to the (h, K*D) draws on the host,
  * and every vignette then takes row quantiles (/root/reference/docs/vignettes/getting-started.jl:432-435).

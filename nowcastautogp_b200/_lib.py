@@ -46,6 +46,9 @@ SIGNATURES = {
     "nagp_forecast_with_nowcasts": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _f64,
                                            _i64, _i64, _i64, _vp, _vp, _f64, _vp, _vp, _f64, _f64, _vp,
                                            _vp, _vp, _vp, _f64, _vp, _vp, _vp, _vp, _vp]),
+    "nagp_forecast_with_nowcasts_theta": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _f64,
+                                                 _i64, _i64, _i64, _vp, _vp, _f64, _vp, _vp, _f64, _f64, _vp,
+                                                 _vp, _vp, _vp, _f64, _vp, _vp, _vp, _vp, _vp]),
     "nagp_forecast_summary": (_i32, [_vp, _i32, _f64, _f64, _f64, _i64, _i64, _vp, _vp, _i64, _vp, _vp]),
 }
 

@@ -489,6 +489,9 @@ def _forecast_with_nowcasts(base_model: GPModel, nowcasts: Sequence[TData], fore
         hmc(n_hmc)                                              # mcmc_parameters!: forecasting.jl:148
 
     def draw_block(Dn):
+        # predict_mvn + rand for every scenario's rejuvenated particles (forecasting.jl:152-155, :66-67). The mixture
+        # weights are the log-weights fixed at add_data! (rejuvenation leaves them untouched [R]); moments and draws stay on
+        # the device: nagp_forecast_with_nowcasts_theta would also recompute the weights, so the two-call form is kept here.
         th_, nz_ = sp.theta(sp.z, sp.noise_z)
         r_, _ = score(th_, nz_, True)
         zeta = rng.standard_normal((K, Dn, h))

@@ -1112,6 +1112,74 @@ int32_t nagp_draw(nagp_ctx *ctx, int64_t K, int64_t P, int64_t h, int64_t D, con
     return finish(ctx);
 }
 
+int32_t nagp_forecast_with_nowcasts_theta(nagp_ctx *ctx, int64_t K, int64_t P, int64_t D, const uint8_t *prog,
+                                          const int64_t *prog_off, const double *theta, const int64_t *theta_off,
+                                          int64_t theta_stride_k, const double *noise, int64_t noise_stride_k,
+                                          double noise_pred, int64_t n, int64_t k, int64_t h, const double *t,
+                                          const int32_t *g, double step, const double *y1, const double *y2, double ya,
+                                          double yb, const double *logw0, const int32_t *comp, const double *u,
+                                          const double *u_res, double ess_thr, const double *zeta, double *x,
+                                          double *logw_out, double *ess_out, int32_t *info)
+{
+    NAGP_RANGE("nagp_forecast_with_nowcasts_theta");
+    if (!ctx) return NAGP_E_ARG;
+    if (K <= 0 || P <= 0 || D <= 0 || h <= 0 || !prog || !prog_off || !theta || !theta_off || !noise || !t || !y1 ||
+        (k > 0 && !y2) || !zeta || !x || !info || (!comp && !u) || ya == 0.0)
+        return fail(ctx, NAGP_E_ARG, "nagp_forecast_with_nowcasts_theta: null or empty argument");
+    if (u_res && !u) return fail(ctx, NAGP_E_ARG, "nagp_forecast_with_nowcasts_theta: resampling needs u");
+    NAGP_TRY(check_dims(ctx, n, k, h));
+    if (on_device(prog_off) || on_device(theta_off))
+        return fail(ctx, NAGP_E_ARG, "prog_off/theta_off must be host arrays");
+    NAGP_CUDA(ctx, cudaSetDevice(ctx->device));
+    NAGP_TRY(arena_reset(ctx));
+    const int64_t q = n + k + h, B = K * P;
+
+    // (1) one fused Gram + factorisation per (scenario, particle): log-weights, mu*, L33 stay on the device
+    FusedArgs a{};
+    NAGP_TRY(grid_extent(ctx, g, q, &a.G));
+    NAGP_TRY(plan_tables(ctx, P, prog, prog_off, theta_off, (int)q, a.G, &a.ntab_cap, &a.ncp_cap));
+    const int64_t nprog = prog_off[P], ntheta = theta_off[P];
+    a.B = B; a.P = P;
+    NAGP_TRY(stage_in(ctx, prog, (size_t)nprog, &a.prog));
+    NAGP_TRY(stage_in(ctx, prog_off, (size_t)P + 1, &a.prog_off));
+    NAGP_TRY(stage_in(ctx, theta, (size_t)(theta_stride_k ? (K - 1) * theta_stride_k + ntheta : ntheta), &a.theta));
+    NAGP_TRY(stage_in(ctx, theta_off, (size_t)P + 1, &a.theta_off));
+    a.theta_stride_k = theta_stride_k;
+    NAGP_TRY(stage_in(ctx, noise, (size_t)(noise_stride_k ? (K - 1) * noise_stride_k + P : P), &a.noise));
+    a.noise_stride_k = noise_stride_k;
+    a.jitter = ctx->jitter; a.noise_pred = noise_pred;
+    a.n = (int)n; a.k = (int)k; a.h = (int)h;
+    NAGP_TRY(stage_in(ctx, t, (size_t)q, &a.t));
+    NAGP_TRY(stage_in(ctx, g, (size_t)q, &a.g));
+    a.step = step;
+    NAGP_TRY(stage_in(ctx, y1, (size_t)n, &a.y1));
+    NAGP_TRY(stage_in(ctx, y2, (size_t)(K * k), &a.y2));
+    a.ya = ya; a.yb = yb;
+    NAGP_TRY(stage_in(ctx, logw0, (size_t)P, &a.logw0));
+    if (logw_out) NAGP_TRY(stage_out(ctx, logw_out, (size_t)B, &a.logw));
+    else NAGP_TRY(scratch(ctx, (size_t)B, &a.logw));
+    NAGP_TRY(scratch(ctx, (size_t)(B * h), &a.mu));
+    NAGP_TRY(scratch(ctx, (size_t)(B * h * h), &a.L33));
+    NAGP_TRY(stage_out(ctx, info, (size_t)B, &a.info));
+    NAGP_TRY(run_fused(ctx, a, theta_off));
+
+    // (2) maybe_resample! + rand(MixtureModel, D) per scenario
+    DrawArgs d{};
+    d.K = K; d.P = P; d.h = (int)h; d.D = D;
+    d.logw = a.logw; d.mu = a.mu; d.mu_stride_k = P * h; d.L = a.L33; d.l_stride_k = P * h * h;
+    NAGP_TRY(stage_in(ctx, comp, (size_t)(K * D), &d.comp));
+    NAGP_TRY(stage_in(ctx, u, (size_t)(K * D), &d.u));
+    NAGP_TRY(stage_in(ctx, u_res, (size_t)(K * P), &d.u_res));
+    d.ess_thr = ess_thr;
+    NAGP_TRY(stage_in(ctx, zeta, (size_t)(K * D * h), &d.zeta));
+    NAGP_TRY(stage_out(ctx, x, (size_t)(K * D * h), &d.x));
+    NAGP_TRY(stage_out(ctx, ess_out, (size_t)K, &d.ess_out));
+    NAGP_CUDA(ctx, launch_draw(d, ctx->stream));
+    ctx->launches += 1;
+    NAGP_TRY(finish(ctx));
+    return on_device(info) ? NAGP_OK : worst_info(info, B);
+}
+
 int32_t nagp_forecast_with_nowcasts(nagp_ctx *ctx, int64_t K, int64_t P, int64_t D, const uint8_t *prog,
                                     const int64_t *prog_off, const double *theta, const int64_t *theta_off,
                                     const double *noise, double noise_pred, int64_t n, int64_t k, int64_t h,

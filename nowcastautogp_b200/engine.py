@@ -315,6 +315,28 @@ class Engine:
         return xbuf.T if x is None else xbuf
 
 
+    def forecast_with_nowcasts_theta(self, ens: FlatEnsemble, n, k, h, t, y1, y2, logw0, zeta, theta, noise, ya=1.0, yb=0.0,
+                                     g=None, step=0.0, noise_pred=-1.0, comp=None, u=None, u_res=None, ess_thr=0.0,
+                                     x=None, logw=None, ess=None, info=None, check: bool = False, K=None, D=None):
+        """Per-scenario hyperparameters (`theta` [K,total], `noise` [K,P]): instances + ESS/resample + draws in one call."""
+        P = ens.size
+        if K is None:
+            K = zeta.shape[0]
+        if D is None:
+            D = zeta.shape[1]
+        xbuf = np.empty((K * D, h)) if x is None else x
+        info = np.zeros((K, P), np.int32) if info is None else info
+        keep = [_ptr(ens.prog), _ptr(ens.prog_off), _ptr(theta), _ptr(ens.theta_off), _ptr(noise),
+                _ptr(t, np.float64), _ptr(g, np.int32), _ptr(y1, np.float64), _ptr(y2, np.float64),
+                _ptr(logw0, np.float64), _ptr(comp, np.int32), _ptr(u, np.float64), _ptr(u_res, np.float64),
+                _ptr(zeta, np.float64), _ptr(xbuf), _ptr(logw), _ptr(ess), _ptr(info)]
+        p = [k_[0] for k_ in keep]
+        rc = self._lib.nagp_forecast_with_nowcasts_theta(
+            self._ctx, K, P, D, p[0], p[1], p[2], p[3], int(ens.theta_off[-1]), p[4], P, noise_pred, n, k, h, p[5], p[6],
+            step, p[7], p[8], ya, yb, p[9], p[10], p[11], p[12], ess_thr, p[13], p[14], p[15], p[16], p[17])
+        self._check(rc, raise_posdef=check)
+        return xbuf.T if x is None else xbuf
+
     # ---- (f4) inverse transformation + per-date quantiles ---------------------------------------------
     def forecast_summary(self, x, spec=(0, 0.0, 0.0, 0.0), probs=None, want_x: bool = True):
         """x [h, N] transformed-space draws (numpy) → (inverse-transformed x [h, N] or None, quantiles [h, nq] or

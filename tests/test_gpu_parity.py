@@ -226,3 +226,24 @@ def test_failures_in_later_tile_columns_mixed_batch(veng, oracle):
             assert r["info"] == info[s, p], (s, p)
             if r["info"] == 0:
                 assert rel(logw[s, p], w.logw0[p] + r["logml_m"] - r["logml_n"]) < RTOL
+
+
+def test_forecast_with_nowcasts_theta_one_call(veng, oracle):
+    """nagp_forecast_with_nowcasts_theta = nagp_forecast_instances + nagp_draw without the round trip: draws bit-identical
+    to the oracle's draw routine fed the oracle's own moments only up to the moments' 1e-9, so compare against the
+    two-call device path bit for bit and against the oracle at the moment tolerance."""
+    n, k, h, P, K, D = 60, 1, 4, 5, 6, 7
+    w = syn.make_workload(n, k, h, K, P, seed=91)
+    th, nz = syn.perturbed_theta(w.ens, K, seed=92)
+    rng = np.random.default_rng(93)
+    zeta, u = rng.standard_normal((K, D, h)), rng.uniform(size=(K, D))
+    logw = np.empty((K, P))
+    x1 = veng.forecast_with_nowcasts_theta(w.ens, n, k, h, w.t, w.y1, w.y2, w.logw0, zeta, th, nz, w.ya, w.yb, g=w.g,
+                                           step=w.step, u=u, logw=logw)
+    r = veng.forecast_instances(w.ens, n, k, h, w.t, w.y1, w.y2, w.logw0, w.ya, w.yb, g=w.g, step=w.step, theta=th, noise=nz)
+    x2, _, _ = veng.draw(r["logw"], r["mu"], r["L"], zeta, u=u)
+    assert np.array_equal(np.asarray(x1), np.asarray(x2)) and np.array_equal(logw, r["logw"])
+    want = oracle.forecast_instances(w.ens, n, k, h, w.t, w.y1, w.y2, w.logw0, w.ya, w.yb, g=w.g, step=w.step,
+                                     use_joint=True, theta_per_scenario=th, noise_per_scenario=nz)
+    xo, _, _ = oracle.draws(want["logw"], want["mu"], want["L"], zeta, u=u)
+    assert rel(logw, want["logw"]) < RTOL and rel(x1, xo) < 1e-8
