@@ -39,6 +39,8 @@ std::string g_init_error;
 struct nagp_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t copy_stream = nullptr;     // host->device copies that can run under a kernel of `stream`
+    cudaEvent_t copy_done = nullptr, fork = nullptr;
     double jitter = 1e-5;
     int variant = 0;
     int last_kernel = 0;
@@ -127,13 +129,13 @@ void *arena_alloc(nagp_ctx *ctx, size_t bytes)
 }
 
 template <class T>
-int32_t stage_in(nagp_ctx *ctx, const T *p, size_t count, const T **dev)
+int32_t stage_in(nagp_ctx *ctx, const T *p, size_t count, const T **dev, cudaStream_t on = nullptr)
 {
     if (!p || count == 0) { *dev = nullptr; return NAGP_OK; }
     if (on_device(p)) { *dev = p; return NAGP_OK; }
     T *d = static_cast<T *>(arena_alloc(ctx, count * sizeof(T)));
     if (!d) return fail(ctx, NAGP_E_CUDA, "device workspace allocation failed");
-    NAGP_CUDA(ctx, cudaMemcpyAsync(d, p, count * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    NAGP_CUDA(ctx, cudaMemcpyAsync(d, p, count * sizeof(T), cudaMemcpyHostToDevice, on ? on : ctx->stream));
     *dev = d;
     return NAGP_OK;
 }
@@ -372,6 +374,9 @@ int32_t nagp_init(int32_t device, nagp_ctx **out)
     ctx->device = device;
     if ((e = cudaSetDevice(device)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->fork, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device)) != cudaSuccess ||
         (e = cudaDeviceGetAttribute(&ctx->smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device)) != cudaSuccess ||
         (e = cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) {
@@ -389,6 +394,9 @@ void nagp_destroy(nagp_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto &c : ctx->chunks) cudaFree(c.base);
+    if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
+    if (ctx->fork) cudaEventDestroy(ctx->fork);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -1161,17 +1169,23 @@ int32_t nagp_forecast_with_nowcasts_theta(nagp_ctx *ctx, int64_t K, int64_t P, i
     NAGP_TRY(scratch(ctx, (size_t)(B * h), &a.mu));
     NAGP_TRY(scratch(ctx, (size_t)(B * h * h), &a.L33));
     NAGP_TRY(stage_out(ctx, info, (size_t)B, &a.info));
-    NAGP_TRY(run_fused(ctx, a, theta_off));
+    // the inputs of the draw kernel travel on the copy stream, under the fused kernel (ordered after whatever the
+    // caller's stream has already queued; the arena memory they land in is not touched by the fused kernel)
+    DrawArgs d{};
+    NAGP_CUDA(ctx, cudaEventRecord(ctx->fork, ctx->stream));
+    NAGP_TRY(run_fused(ctx, a, theta_off));          // its own inputs go first through the copy engine
+    NAGP_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->fork, 0));
+    NAGP_TRY(stage_in(ctx, comp, (size_t)(K * D), &d.comp, ctx->copy_stream));
+    NAGP_TRY(stage_in(ctx, u, (size_t)(K * D), &d.u, ctx->copy_stream));
+    NAGP_TRY(stage_in(ctx, u_res, (size_t)(K * P), &d.u_res, ctx->copy_stream));
+    NAGP_TRY(stage_in(ctx, zeta, (size_t)(K * D * h), &d.zeta, ctx->copy_stream));
+    NAGP_CUDA(ctx, cudaEventRecord(ctx->copy_done, ctx->copy_stream));
 
     // (2) maybe_resample! + rand(MixtureModel, D) per scenario
-    DrawArgs d{};
     d.K = K; d.P = P; d.h = (int)h; d.D = D;
     d.logw = a.logw; d.mu = a.mu; d.mu_stride_k = P * h; d.L = a.L33; d.l_stride_k = P * h * h;
-    NAGP_TRY(stage_in(ctx, comp, (size_t)(K * D), &d.comp));
-    NAGP_TRY(stage_in(ctx, u, (size_t)(K * D), &d.u));
-    NAGP_TRY(stage_in(ctx, u_res, (size_t)(K * P), &d.u_res));
     d.ess_thr = ess_thr;
-    NAGP_TRY(stage_in(ctx, zeta, (size_t)(K * D * h), &d.zeta));
+    NAGP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->copy_done, 0));
     NAGP_TRY(stage_out(ctx, x, (size_t)(K * D * h), &d.x));
     NAGP_TRY(stage_out(ctx, ess_out, (size_t)K, &d.ess_out));
     NAGP_CUDA(ctx, launch_draw(d, ctx->stream));
