@@ -15,17 +15,23 @@
 //   S_II = (L_II^-T - sum_{K>I} S_KI^T L_KI) L_II^-1
 //   alpha_I^T = (z_I^T - sum_{K>I} alpha_K^T L_KI) L_II^-1      (alpha rides along as one more row)
 //
-// Column I of L is dead once column I of S exists, so no second matrix is needed; a transposed copy of the
-// column (operand layout of L_KI^T) is staged per step so every DMMA operand but the mirrored S_JK is one
-// 16-byte LDS. 2 q^3/3 FLOP, all on the FP64 tensor pipe (mma.sync m8n8k4 f64: there is no tcgen05 kind for f64).
+// Column I of L is dead once column I of S exists, so no second matrix is needed. The factor is transposed tile by
+// tile while it is loaded (tile (K, I) holds L_KI^T in operand layout), so every DMMA operand but the mirrored S_JK
+// is one 16-byte LDS and no column has to be staged; two barriers per tile column (all reads of column I of L done /
+// column I of S in place), the diagonal tile finished by the warp that needs it next. 2 q^3/3 FLOP, all on the FP64
+// tensor pipe (mma.sync m8n8k4 f64: there is no tcgen05 kind for f64).
 //
 // The tree is then differentiated in reverse mode per matrix entry over the COMPILED program (stationary
 // sub-trees folded into lag tables, ChangePoint sigmoids tabulated per point, as in the Gram pass of the tile
 // kernel). A lane owns one lag d of a group of 32 and walks rows a with b = ginv[g_a - d]; the rows are dealt
 // round-robin to the 8 warps. The adjoint that reaches a lag table is summed per (table, lag, warp) in a register
 // — no atomics, fixed order, bit-reproducible — and only afterwards pushed through the stationary sub-tree once
-// per (table, lag): G transcendental evaluations per table instead of n^2/2. A fully stationary tree needs no
-// per-entry interpretation at all (the entry's weight is the table's adjoint).
+// per (table, lag): G transcendental evaluations per table instead of n^2/2. Leaves that hang off the root through
+// Plus nodes only (a sum of components is the typical AutoGP posterior structure) never reach the interpreter: their
+// adjoint is the entry's weight w itself, so a lag table just receives the lag sums of w and a Linear / Constant leaf
+// is differentiated from three weighted moments (sum w, sum w (ti + tj), sum w ti tj about the middle of the series).
+// What is left after that, if at most nine compiled ops, is swept with every value and adjoint in a register
+// (rev_entry_reg); longer programs go through the local-memory interpreter (rev_entry).
 // Formulas: docs/KERNEL_SPEC.md §3, §8.
 #include <algorithm>
 
@@ -44,7 +50,131 @@ constexpr int kMaxRows = (29 + kGW - 1) / kGW;
 struct RevProgram {
     int8_t cleft[MAX_PROG];    // compiled program: root index of the left child of a binary node
     int8_t sleft[MAX_PROG];    // source program: same
+    int8_t slot[MAX_PROG];     // register-resident sweep: accumulator slot of a Linear / Constant leaf or a ChangePoint
+    int reg_ok;                // the compiled program qualifies for the register-resident sweep
+    // leaves that hang off the root through Plus nodes only (their adjoint is the entry's weight itself) are taken out
+    // of the per-entry program: lag tables get the lag sums of the weights, Linear / Constant the weighted moments
+    uint32_t peel_tab;                  // bit id: lag table id is such a leaf
+    int npeel_lin, npeel_con;
+    int16_t peel_lin[MAX_PROG / 2 + 1], peel_con[MAX_PROG / 2 + 1];   // theta offsets
 };
+
+#ifndef NAGP_GRAD_REG
+#define NAGP_GRAD_REG 1
+#endif
+constexpr int kRegOps = 9;     // compiled ops the register-resident sweep holds (values and adjoints in registers)
+constexpr int kRegLeaf = 4;    // Linear / Constant leaves with named accumulators
+constexpr int kRegCp = 2;      // tabulated ChangePoints with named accumulators
+constexpr int kRegTab = 5;     // lag tables (at most five leaves among nine ops)
+
+// Thread-0 only: accumulator slots of the register-resident sweep, or reg_ok = 0 when the program does not fit it.
+__device__ void reg_slots(const TreeProgram &tp, RevProgram &rp)
+{
+    int nl = 0, nc = 0;
+    bool ok = tp.clen <= kRegOps && tp.ntab <= kRegTab;
+    for (int i = 0; ok && i < tp.clen; ++i) {
+        const int o = tp.cop[i];
+        rp.slot[i] = 0;
+        if (o == OP_LINEAR || o == OP_CONSTANT) { if (nl < kRegLeaf) rp.slot[i] = (int8_t)nl++; else ok = false; }
+        else if (o == OP_CHANGEPOINT_TAB) { if (nc < kRegCp) rp.slot[i] = (int8_t)nc++; else ok = false; }
+        else if (o != OP_TABLE && o != OP_PLUS && o != OP_TIMES) ok = false;
+    }
+    rp.reg_ok = ok && NAGP_GRAD_REG;
+}
+
+// Reverse-mode sweep of a short compiled program for one pair with every value and adjoint in a register: the ops
+// loop is unrolled so positions are compile-time, and the only run-time indices (left child, accumulator slot, table
+// id) are warp-uniform and resolved by select chains. Same arithmetic and order as rev_entry.
+struct RegAcc {
+    double la[kRegLeaf][3];
+    double cp[kRegCp][2];
+};
+__device__ __forceinline__ void rev_entry_reg(const TreeProgram &tp, const RevProgram &rp, const double *th, double ti,
+                                              double tj, int lag, int pi, int pj, const double *tab, int G,
+                                              const double *sig, int Q, double w, RegAcc &acc, double (&hacc)[kRegTab])
+{
+    const int clen = tp.clen;
+    double val[kRegOps], adj[kRegOps];
+#pragma unroll
+    for (int i = 0; i < kRegOps; ++i) {
+        double v = 0.0;
+        if (i < clen) {
+            const uint32_t cw = tp.cword[i];
+            const int o = cw & 0xff, arg = (cw >> 8) & 0xffff;
+            if (o == OP_TABLE) v = tab[arg * G + lag];
+            else if (o == OP_LINEAR) v = fma(th[arg + 2], (ti - th[arg]) * (tj - th[arg]), th[arg + 1]);
+            else if (o == OP_CONSTANT) v = th[arg];
+            else if (i >= 2) {
+                const int l = rp.cleft[i];
+                double vl = val[0];
+#pragma unroll
+                for (int j = 1; j < i - 1; ++j) vl = (l == j) ? val[j] : vl;
+                const double vr = val[i - 1];
+                if (o == OP_PLUS) v = vl + vr;
+                else if (o == OP_TIMES) v = vl * vr;
+                else {
+                    const int ax = cw >> 24;
+                    const double si = sig[ax * Q + pi], sj = sig[ax * Q + pj];
+                    v = ((1.0 - si) * (1.0 - sj)) * vl + (si * sj) * vr;
+                }
+            }
+        }
+        val[i] = v;
+        adj[i] = (i == clen - 1) ? w : 0.0;
+    }
+#pragma unroll
+    for (int i = kRegOps - 1; i >= 0; --i) {
+        if (i < clen) {
+            const uint32_t cw = tp.cword[i];
+            const int o = cw & 0xff, arg = (cw >> 8) & 0xffff;
+            const double ad = adj[i];
+            if (o == OP_TABLE) {
+#pragma unroll
+                for (int j = 0; j < kRegTab; ++j) hacc[j] += (arg == j) ? ad : 0.0;
+            } else if (o == OP_LINEAR || o == OP_CONSTANT) {
+                double g0, g1 = 0.0, g2 = 0.0;
+                if (o == OP_LINEAR) {
+                    const double u = ti - th[arg], v2 = tj - th[arg];
+                    g0 = ad * (-th[arg + 2] * (u + v2));
+                    g1 = ad;
+                    g2 = ad * (u * v2);
+                } else g0 = ad;
+                const int sl = rp.slot[i];
+#pragma unroll
+                for (int q = 0; q < kRegLeaf; ++q)
+                    if (sl == q) { acc.la[q][0] += g0; acc.la[q][1] += g1; acc.la[q][2] += g2; }
+            } else if (i >= 2) {
+                const int l = rp.cleft[i];
+                double kl = val[0];
+#pragma unroll
+                for (int j = 1; j < i - 1; ++j) kl = (l == j) ? val[j] : kl;
+                const double kr = val[i - 1];
+                double al, ar;
+                if (o == OP_PLUS) { al = ad; ar = ad; }
+                else if (o == OP_TIMES) { al = ad * kr; ar = ad * kl; }
+                else {
+                    const int ax = cw >> 24;
+                    const double si = sig[ax * Q + pi], sj = sig[ax * Q + pj];
+                    const double xi = (ti - th[arg]) / th[arg + 1], xj = (tj - th[arg]) / th[arg + 1];
+                    al = ad * ((1.0 - si) * (1.0 - sj));
+                    ar = ad * (si * sj);
+                    const double dsi = 2.0 * si * (1.0 - si), dsj = 2.0 * sj * (1.0 - sj);
+                    const double dk_dsi = -(1.0 - sj) * kl + sj * kr;
+                    const double dk_dsj = -(1.0 - si) * kl + si * kr;
+                    const double c0 = ad * (dk_dsi * dsi + dk_dsj * dsj) * (-1.0 / th[arg + 1]);
+                    const double c1 = ad * (dk_dsi * dsi * (-xi / th[arg + 1]) + dk_dsj * dsj * (-xj / th[arg + 1]));
+                    const int sl = rp.slot[i];
+#pragma unroll
+                    for (int q = 0; q < kRegCp; ++q)
+                        if (sl == q) { acc.cp[q][0] += c0; acc.cp[q][1] += c1; }
+                }
+                adj[i - 1] += ar;
+#pragma unroll
+                for (int j = 0; j < i - 1; ++j) adj[j] += (l == j) ? al : 0.0;
+            }
+        }
+    }
+}
 
 // left-child roots of a post-order program (leaf: opcode <= OP_PERIODIC or OP_TABLE)
 __device__ void left_roots(const uint8_t *op, int len, int8_t *left)
@@ -57,6 +187,47 @@ __device__ void left_roots(const uint8_t *op, int len, int8_t *left)
         if (o <= OP_PERIODIC || o == OP_TABLE) { if (sp < MAX_STACK) stack[sp++] = (int8_t)i; }
         else if (sp >= 2) { left[i] = stack[sp - 2]; sp -= 2; stack[sp++] = (int8_t)i; }
     }
+}
+
+// Thread-0 only. Splits the compiled program at its root: the program is a sum of terms (the operands of the Plus
+// nodes reachable from the root through Plus nodes); a term that is a single lag table, Linear or Constant leaf is
+// recorded in rp.peel_* and removed, the other terms are re-joined by Plus nodes into the program the per-entry
+// sweep interprets (tp.clen == 0 when nothing is left). Then left-child roots and register slots of what is left.
+__device__ void peel_root(TreeProgram &tp, RevProgram &rp)
+{
+    const int len = tp.clen;
+    uint8_t op[MAX_PROG]; int16_t arg[MAX_PROG]; int8_t aux[MAX_PROG], size[MAX_PROG], st[MAX_PROG];
+    left_roots(tp.cop, len, rp.cleft);
+    for (int i = 0; i < len; ++i) {
+        op[i] = tp.cop[i]; arg[i] = tp.carg[i]; aux[i] = tp.caux[i];
+        size[i] = rp.cleft[i] < 0 ? 1 : (int8_t)(1 + size[i - 1] + size[rp.cleft[i]]);
+    }
+    rp.peel_tab = 0; rp.npeel_lin = 0; rp.npeel_con = 0;
+    unsigned long long roots = 0;
+    int sp = 0;
+    if (len > 0) st[sp++] = (int8_t)(len - 1);
+    while (sp > 0) {
+        const int i = st[--sp], o = op[i];
+        if (o == OP_PLUS) { st[sp++] = rp.cleft[i]; st[sp++] = (int8_t)(i - 1); }
+        else if (o == OP_TABLE) rp.peel_tab |= 1u << arg[i];
+        else if (o == OP_LINEAR) rp.peel_lin[rp.npeel_lin++] = arg[i];
+        else if (o == OP_CONSTANT) rp.peel_con[rp.npeel_con++] = arg[i];
+        else roots |= 1ull << i;
+    }
+    int nout = 0, nterms = 0;
+    auto emit = [&](int o, int ar, int ax) {
+        tp.cop[nout] = (uint8_t)o; tp.carg[nout] = (int16_t)ar; tp.caux[nout] = (int8_t)ax;
+        tp.cword[nout] = (uint32_t)o | ((uint32_t)(uint16_t)ar << 8) | ((uint32_t)(uint8_t)ax << 24);
+        ++nout;
+    };
+    for (int i = 0; i < len; ++i) {
+        if (!((roots >> i) & 1ull)) continue;
+        for (int j = i - size[i] + 1; j <= i; ++j) emit(op[j], arg[j], aux[j]);
+        if (++nterms > 1) emit(OP_PLUS, 0, 0);
+    }
+    tp.clen = nout;
+    left_roots(tp.cop, nout, rp.cleft);
+    reg_slots(tp, rp);
 }
 
 // Reverse-mode sweep of ops [i0, i1) for one pair: forward values, then the adjoint `w` of the root pushed to
@@ -162,7 +333,7 @@ __device__ __forceinline__ void rev_entry(const uint8_t *op, const int16_t *arg,
 
 struct GradTileLayout {
     int nt;
-    int region_bytes;         // union region: {lcolT, part} during the sweep, {tt, theta, gg, ginv} afterwards
+    int region_bytes;         // union region: {part} during the sweep, {tt, theta, gg, ginv} afterwards
     int Gd;                   // lags handled (lag-grid extent, or n when times are pairwise)
     int scratch_stride;       // bytes of global scratch per CTA (lag tables, sigma tables, per-warp table adjoints)
     char *scratch;
@@ -175,7 +346,6 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
     __shared__ TreeProgram tp;
     __shared__ RevProgram rp;
     __shared__ long long s_next;
-    __shared__ double s_red[kGW];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = a.n, nt = lay.nt, Q = nt * 8, ntiles = tri(nt);
@@ -183,11 +353,10 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
 
     double *tiles = smem;
     double *alpha = tiles + ntiles * 64;        // [Q]
-    double *invs = alpha + Q;                   // [64] inverse of the current diagonal tile of L
-    double *region = invs + 64;
+    double *invs = alpha + Q;                   // [2][64] inverses of the diagonal tiles of L, current and next column
+    double *region = invs + 128;
     // sweep view of the region
-    double *lcolT = region;                     // [nt][64] operand layout of L_KI^T
-    double *part = lcolT + nt * 64;             // [kGW][64] partial sums of the diagonal tile, accumulator layout
+    double *part = region;                      // [kGW][64] partial sums of the diagonal tile, accumulator layout
     // differentiation view of the region
     double *tt = region;                        // [Q]
     double *th = tt + Q;                        // [MAX_THETA]
@@ -201,15 +370,16 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
     const int oi0 = op_idx(lr, 2 * lj), oi1 = op_idx(lr, 2 * lj + 1);
     const int tr0 = op_idx(lj, lr);                       // transposed fragment: element (lj, lr); chunk 1 is +32
     const int cv0 = (lane & ~3) + (lj >> 1), cv1 = cv0 + 2;
+    const int ts0 = lj * 4 + (lr >> 1);                   // accumulator layout -> A operand of the transposed tile
     const bool odd = lane & 1;
-    const uint32_t tiles_a = smem_addr(tiles), lcol_a = smem_addr(lcolT), invs_a = smem_addr(invs);
+    const uint32_t tiles_a = smem_addr(tiles), invs_a = smem_addr(invs);
     const int nreg = warp < nt ? (nt - 1 - warp) / kGW + 1 : 0;
     const int Ilast = warp + (nreg - 1) * kGW;
     const bool has_alpha = (warp == nt % kGW);
 
     // C (accumulator layout) times invL, result in accumulator layout: X * invL = X * (invL^T)^T
-    auto times_inv = [&](double c0, double c1, double &x0, double &x1) {
-        const double ibx = lds64(invs_a + tr0 * 8), iby = lds64(invs_a + tr0 * 8 + 256);
+    auto times_inv = [&](uint32_t inv_a, double c0, double c1, double &x0, double &x1) {
+        const double ibx = lds64(inv_a + tr0 * 8), iby = lds64(inv_a + tr0 * 8 + 256);
         const double v00 = shfl(c0, cv0), v01 = shfl(c1, cv0);
         const double v10 = shfl(c0, cv1), v11 = shfl(c1, cv1);
         x0 = 0.0; x1 = 0.0;
@@ -244,10 +414,16 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
             if (ntheta > MAX_THETA) tp.error = -3;
             else tree_compile(tp, a.prog + po, (int)plen, (int)ntheta, G > 0 ? a.ntab_cap : 0, a.ncp_cap);
         }
-        {
+        {   // factor into shared memory, every tile transposed: tile (K, I) then holds L_KI^T in operand layout, which is
+            // the B operand of every product of the sweep (one 16-byte LDS), and no column has to be staged
             const double2 *Lg = reinterpret_cast<const double2 *>(a.L + (size_t)b * ((size_t)ntiles * 64));
-            double2 *Ls = reinterpret_cast<double2 *>(tiles);
-            for (int i = tid; i < ntiles * 32; i += kGT2) Ls[i] = Lg[i];
+            for (int i = tid; i < ntiles * 32; i += kGT2) {
+                const double2 v = Lg[i];
+                const int ln = i & 31, r = ln >> 2, c = ln & 3;
+                double *dst = tiles + (i >> 5) * 64 + op_idx(c, r);
+                dst[0] = v.x;            // element (r, c) -> (c, r)
+                dst[32] = v.y;           // element (r, c + 4) -> (c + 4, r)
+            }
         }
         __syncthreads();
         if (tp.error) {
@@ -255,52 +431,78 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
             if (tid == 0) a.grad_noise[b] = nan("");
             continue;
         }
-        if (tid == 0) left_roots(tp.cop, tp.clen, rp.cleft);
+        if (tid == 0) peel_root(tp, rp);
         if (tid == 32) left_roots(tp.sop, tp.slen, rp.sleft);
         const double *zb = a.z + (size_t)b * Q;
         const double *Wb = a.Winv + (size_t)b * ((size_t)nt * 64);
 
         // ---- 1. S = K^-1 in place, alpha = K^-1 y ------------------------------------------------------------
-        for (int I = nt - 1; I >= 0; --I) {
-            __syncthreads();                                   // column I+1 of S complete (incl. its diagonal tile)
-            for (int e = tid; e < (nt - 1 - I) * 64; e += kGT2) {
-                const int K = I + 1 + (e >> 6), el = e & 63, r = el >> 3, c = el & 7;
-                lcolT[K * 64 + op_idx(c, r)] = tiles[(tri(K) + I) * 64 + op_idx(r, c)];
+        // Two barriers per tile column. A: every product that reads column I of L is done (results wait in registers),
+        // so the column may be overwritten by S. B: column I of S and the partial sums of its diagonal tile are in place.
+        // The diagonal tile S_II is finished after B by the warp that owns row I, which needs it only for that row (its
+        // last of the next column); the other warps go straight on with rows that do not touch it.
+        if (tid < 64) invs[((nt - 1) & 1) * 64 + tid] = Wb[(nt - 1) * 64 + tid];
+        auto finish_diag = [&](int D) {
+            double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+            for (int w = 0; w < kGW; ++w) {
+                const double2 v = *reinterpret_cast<const double2 *>(part + w * 64 + lane * 2);
+                t0 += v.x; t1 += v.y;
             }
-            if (tid < 64) invs[tid] = Wb[I * 64 + tid];
-            __syncthreads();
+            // invL^T in accumulator layout: element (lr, c) = invL[c][lr]
+            const double *iv = invs + (D & 1) * 64;
+            const double r0 = iv[op_idx(2 * lj, lr)] - t0, r1 = iv[op_idx(2 * lj + 1, lr)] - t1;
+            double x0, x1;
+            times_inv(invs_a + (uint32_t)((D & 1) * 512), r0, r1, x0, x1);
+            const uint32_t dt = tiles_a + (uint32_t)((tri(D) + D) * 512);
+            sts64(dt + oi0 * 8, x0);
+            sts64(dt + oi1 * 8, x1);
+            __syncwarp();
+        };
+        for (int I = nt - 1; I >= 0; --I) {
+            __syncthreads();                                   // B of column I+1 (first pass: the factor is loaded)
+            const uint32_t inv_cur = invs_a + (uint32_t)((I & 1) * 512);
+            double wnext = 0.0;
+            if (tid < 64 && I > 0) wnext = Wb[(I - 1) * 64 + tid];
+            if (I + 1 < nt && warp == (I + 1) % kGW) finish_diag(I + 1);
             const int NA = Ilast > I ? (Ilast - I - 1) / kGW + 1 : 0;      // owned rows J > I (slots from the bottom)
             double pd[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+            double xs[kMaxRows][2];
 #pragma unroll
             for (int u = 0; u < kMaxRows; ++u) {
                 if (u < NA) {
                     const int J = Ilast - u * kGW;
                     double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
                     const uint32_t rowa = tiles_a + (uint32_t)(tri(J) * 512 + lane * 16);
+                    const uint32_t cola = tiles_a + (uint32_t)(I * 512 + lane * 16);      // + tri(K) * 512: tile (K, I)
                     for (int K = I + 1; K <= J; ++K) {
                         const double2 af = lds128(rowa + (uint32_t)K * 512u);
-                        const double2 bf = lds128(lcol_a + (uint32_t)(K * 512 + lane * 16));
+                        const double2 bf = lds128(cola + (uint32_t)tri(K) * 512u);
                         dmma(acc[0][0], acc[0][1], af.x, bf.x);
                         dmma(acc[1][0], acc[1][1], af.y, bf.y);
                     }
                     for (int K = J + 1; K < nt; ++K) {
                         const uint32_t ta = tiles_a + (uint32_t)((tri(K) + J) * 512 + tr0 * 8);
                         const double ax = lds64(ta), ay = lds64(ta + 256);
-                        const double2 bf = lds128(lcol_a + (uint32_t)(K * 512 + lane * 16));
+                        const double2 bf = lds128(cola + (uint32_t)tri(K) * 512u);
                         dmma(acc[0][0], acc[0][1], ax, bf.x);
                         dmma(acc[1][0], acc[1][1], ay, bf.y);
                     }
                     double x0, x1;
-                    times_inv(-(acc[0][0] + acc[1][0]), -(acc[0][1] + acc[1][1]), x0, x1);
-                    const uint32_t dt = tiles_a + (uint32_t)((tri(J) + I) * 512);
-                    sts64(dt + oi0 * 8, x0);
-                    sts64(dt + oi1 * 8, x1);
+                    times_inv(inv_cur, -(acc[0][0] + acc[1][0]), -(acc[0][1] + acc[1][1]), x0, x1);
+                    xs[u][0] = x0; xs[u][1] = x1;
+                    // partial sum of the diagonal tile, S_JI^T L_JI: S_JI^T as an A operand straight from the registers
+                    const double s00 = shfl(x0, ts0), s01 = shfl(x1, ts0);
+                    const double s10 = shfl(x0, ts0 + 16), s11 = shfl(x1, ts0 + 16);
+                    const double2 bf = lds128(cola + (uint32_t)tri(J) * 512u);
+                    dmma(pd[0][0], pd[0][1], (lr & 1) ? s01 : s00, bf.x);
+                    dmma(pd[1][0], pd[1][1], (lr & 1) ? s11 : s10, bf.y);
                 }
             }
             if (has_alpha) {
                 double ya[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
                 for (int K = I + 1; K < nt; ++K) {
-                    const double2 bf = lds128(lcol_a + (uint32_t)(K * 512 + lane * 16));
+                    const double2 bf = lds128(tiles_a + (uint32_t)((tri(K) + I) * 512 + lane * 16));
                     const double a0 = lr == 0 ? alpha[K * 8 + lj] : 0.0;
                     const double a1 = lr == 0 ? alpha[K * 8 + 4 + lj] : 0.0;
                     dmma(ya[0][0], ya[0][1], a0, bf.x);
@@ -309,40 +511,24 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
                 const double z0 = lr == 0 ? zb[I * 8 + 2 * lj] : 0.0;
                 const double z1 = lr == 0 ? zb[I * 8 + 2 * lj + 1] : 0.0;
                 double x0, x1;
-                times_inv(z0 - (ya[0][0] + ya[1][0]), z1 - (ya[0][1] + ya[1][1]), x0, x1);
+                times_inv(inv_cur, z0 - (ya[0][0] + ya[1][0]), z1 - (ya[0][1] + ya[1][1]), x0, x1);
                 if (lr == 0) { alpha[I * 8 + 2 * lj] = x0; alpha[I * 8 + 2 * lj + 1] = x1; }
+                __syncwarp();
             }
-            __syncwarp();
-            // partial sum of the diagonal tile over the owned rows: sum_J S_JI^T L_JI (new S_JI, staged L_JI)
+            __syncthreads();                                   // A: column I of L is dead
 #pragma unroll
             for (int u = 0; u < kMaxRows; ++u) {
                 if (u < NA) {
-                    const int J = Ilast - u * kGW;
-                    const uint32_t ta = tiles_a + (uint32_t)((tri(J) + I) * 512 + tr0 * 8);
-                    const double ax = lds64(ta), ay = lds64(ta + 256);
-                    const double2 bf = lds128(lcol_a + (uint32_t)(J * 512 + lane * 16));
-                    dmma(pd[0][0], pd[0][1], ax, bf.x);
-                    dmma(pd[1][0], pd[1][1], ay, bf.y);
+                    const uint32_t dt = tiles_a + (uint32_t)((tri(Ilast - u * kGW) + I) * 512);
+                    sts64(dt + oi0 * 8, xs[u][0]);
+                    sts64(dt + oi1 * 8, xs[u][1]);
                 }
             }
             *reinterpret_cast<double2 *>(part + warp * 64 + lane * 2) = make_double2(pd[0][0] + pd[1][0], pd[0][1] + pd[1][1]);
-            __syncthreads();
-            if (warp == I % kGW) {
-                double t0 = 0.0, t1 = 0.0;
-#pragma unroll
-                for (int w = 0; w < kGW; ++w) {
-                    const double2 v = *reinterpret_cast<const double2 *>(part + w * 64 + lane * 2);
-                    t0 += v.x; t1 += v.y;
-                }
-                // invL^T in accumulator layout: element (lr, c) = invL[c][lr]
-                const double r0 = invs[op_idx(2 * lj, lr)] - t0, r1 = invs[op_idx(2 * lj + 1, lr)] - t1;
-                double x0, x1;
-                times_inv(r0, r1, x0, x1);
-                const uint32_t dt = tiles_a + (uint32_t)((tri(I) + I) * 512);
-                sts64(dt + oi0 * 8, x0);
-                sts64(dt + oi1 * 8, x1);
-            }
+            if (tid < 64 && I > 0) invs[((I - 1) & 1) * 64 + tid] = wnext;
         }
+        __syncthreads();
+        if (warp == 0) finish_diag(0);
         __syncthreads();
 
         // ---- 2. tables for the forward values of the compiled program ------------------------------------------
@@ -377,25 +563,39 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
         for (int j = 0; j < (int)ntheta; ++j) gl[j] = 0.0;
         double gnoise = 0.0;
         const bool grid = a.g != nullptr;
-        const bool single_table = (tp.clen == 1 && tp.cop[0] == OP_TABLE);
+        // what peel_root took out of the program: per entry these leaves cost one add (lag tables) or five FLOP (moments)
+        const bool resid = tp.clen > 0;
+        const uint32_t peel_tab = rp.peel_tab;
+        const bool peel_mom = (rp.npeel_lin | rp.npeel_con) != 0, peel_any = peel_mom || peel_tab != 0;
+        const double tc = 0.5 * (tt[0] + tt[n - 1]);            // moments are taken about the middle of the series
+        double m0 = 0.0, m1 = 0.0, m2 = 0.0;
         // Short compiled programs — one leaf, or two leaves under one Plus / Times / tabulated ChangePoint, leaves being
         // lag tables, Linear or Constant (most prior-sampled trees once the stationary sub-trees are folded) — are
         // differentiated in registers without the interpreter: adjoints and parameter sums live in named registers.
         auto short_leaf = [](int o) { return o == OP_TABLE || o == OP_LINEAR || o == OP_CONSTANT; };
         const int k0 = tp.cop[0], k1 = tp.clen == 3 ? tp.cop[1] : 0, kb = tp.clen == 3 ? tp.cop[2] : 0;
-        const bool short_prog = !single_table && short_leaf(k0) &&
+        const bool short_prog = resid && short_leaf(k0) &&
                                 (tp.clen == 1 || (tp.clen == 3 && short_leaf(k1) &&
                                                   (kb == OP_PLUS || kb == OP_TIMES || kb == OP_CHANGEPOINT_TAB)));
         const int a0 = tp.carg[0], a1 = tp.clen == 3 ? tp.carg[1] : 0, ab = tp.clen == 3 ? tp.carg[2] : 0;
         const double *sgb = sig + (tp.clen == 3 ? tp.caux[2] : 0) * Q;
         double la0[3] = {0.0, 0.0, 0.0}, la1[3] = {0.0, 0.0, 0.0}, cpa[2] = {0.0, 0.0};
+        const bool reg_prog = resid && !short_prog && rp.reg_ok;
+        RegAcc racc;
+#pragma unroll
+        for (int q = 0; q < kRegLeaf; ++q) { racc.la[q][0] = 0.0; racc.la[q][1] = 0.0; racc.la[q][2] = 0.0; }
+#pragma unroll
+        for (int q = 0; q < kRegCp; ++q) { racc.cp[q][0] = 0.0; racc.cp[q][1] = 0.0; }
         const int ngroups = (Gd + 31) >> 5, Gp = ngroups * 32;
         for (int lg = 0; lg < ngroups; ++lg) {
             const int d = lg * 32 + lane;
             double hacc[MAX_TABLES];
 #pragma unroll
             for (int j = 0; j < MAX_TABLES; ++j) hacc[j] = 0.0;
-            double ha0 = 0.0, ha1 = 0.0;
+            double ha0 = 0.0, ha1 = 0.0, hp = 0.0;
+            double rh[kRegTab];
+#pragma unroll
+            for (int j = 0; j < kRegTab; ++j) rh[j] = 0.0;
             for (int ia = warp; ia < n; ia += kGW) {
                 const int ga = gg[ia] - g0;
                 if (ga < lg * 32) continue;                    // no lag of this group reaches back from row ia
@@ -406,8 +606,14 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
                 const double Wab = 0.5 * (alpha[ia] * alpha[ib] - Sab);
                 const double w = d == 0 ? Wab : 2.0 * Wab;
                 if (d == 0) gnoise += Wab;
-                if (single_table) { ha0 += w; continue; }       // fully stationary tree: the entry's weight IS the adjoint
+                if (peel_any) hp += w;                          // a lag table under the root: the entry's weight IS the adjoint
+                if (!peel_mom && !resid) continue;
                 const double ti = tt[ia], tj = tt[ib];
+                if (peel_mom) {
+                    const double ui = ti - tc, uj = tj - tc;
+                    m0 += w; m1 += w * (ui + uj); m2 += w * (ui * uj);
+                }
+                if (!resid) continue;
                 if (short_prog) {
                     auto leaf_val = [&](int o, int arg) {
                         if (o == OP_TABLE) return tab[arg * G + d];
@@ -446,11 +652,22 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
                     }
                     continue;
                 }
+                if (reg_prog) {
+                    rev_entry_reg(tp, rp, th, ti, tj, d, ia, ib, tab, G, sig, Q, w, racc, rh);
+                    continue;
+                }
                 const double delta = grid ? (double)d * a.step : fabs(ti - tj);
                 rev_entry(tp.cop, tp.carg, tp.caux, rp.cleft, 0, tp.clen, th, ti, tj, delta, d, ia, ib, tab, G, sig, Q,
                           w, gl, hacc);
             }
-            if (single_table || short_prog) {
+            if (reg_prog) {
+#pragma unroll
+                for (int j = 0; j < kRegTab; ++j) hacc[j] += rh[j];
+            }
+#pragma unroll
+            for (int j = 0; j < MAX_TABLES; ++j)
+                if ((peel_tab >> j) & 1u) hacc[j] += hp;
+            if (short_prog) {
                 // named accumulators back to their tables (two leaves may share nothing: table ids are distinct)
                 if (k0 == OP_TABLE) hacc[a0] += ha0;
                 if (k1 == OP_TABLE) hacc[a1] += ha1;
@@ -459,12 +676,40 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
             for (int j = 0; j < MAX_TABLES; ++j)
                 if (j < ntab) hpart[(warp * a.ntab_cap + j) * Gp + d] = hacc[j];
         }
+        for (int q = 0; q < rp.npeel_lin; ++q) {
+            // sum w (ti - p0)(tj - p0) and its derivatives from the moments about tc: ti - p0 = (ti - tc) + dl
+            const int arg = rp.peel_lin[q];
+            const double dl = tc - th[arg];
+            gl[arg] += -th[arg + 2] * (m1 + 2.0 * dl * m0);
+            gl[arg + 1] += m0;
+            gl[arg + 2] += m2 + dl * m1 + (dl * dl) * m0;
+        }
+        for (int q = 0; q < rp.npeel_con; ++q) gl[rp.peel_con[q]] += m0;
         if (short_prog) {
             if (k0 == OP_LINEAR) { gl[a0] += la0[0]; gl[a0 + 1] += la0[1]; gl[a0 + 2] += la0[2]; }
             else if (k0 == OP_CONSTANT) gl[a0] += la0[0];
             if (k1 == OP_LINEAR) { gl[a1] += la1[0]; gl[a1 + 1] += la1[1]; gl[a1 + 2] += la1[2]; }
             else if (k1 == OP_CONSTANT) gl[a1] += la1[0];
             if (kb == OP_CHANGEPOINT_TAB) { gl[ab] += cpa[0]; gl[ab + 1] += cpa[1]; }
+        }
+        if (reg_prog) {
+            for (int i = 0; i < tp.clen; ++i) {
+                const int o = tp.cop[i], arg = tp.carg[i], sl = rp.slot[i];
+                if (o == OP_LINEAR || o == OP_CONSTANT) {
+                    double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+#pragma unroll
+                    for (int q = 0; q < kRegLeaf; ++q)
+                        if (sl == q) { g0 = racc.la[q][0]; g1 = racc.la[q][1]; g2 = racc.la[q][2]; }
+                    gl[arg] += g0;
+                    if (o == OP_LINEAR) { gl[arg + 1] += g1; gl[arg + 2] += g2; }
+                } else if (o == OP_CHANGEPOINT_TAB) {
+                    double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                    for (int q = 0; q < kRegCp; ++q)
+                        if (sl == q) { c0 = racc.cp[q][0]; c1 = racc.cp[q][1]; }
+                    gl[arg] += c0; gl[arg + 1] += c1;
+                }
+            }
         }
         __syncthreads();
         // ---- 4. table adjoints through the stationary sub-trees, once per (table, lag) -------------------------
@@ -480,17 +725,24 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
                 }
             }
         }
-        // ---- 5. block reduction --------------------------------------------------------------------------------
-        for (int j = 0; j <= (int)ntheta; ++j) {
-            const double v = warp_sum(j < (int)ntheta ? gl[j] : gnoise);
+        // ---- 5. block reduction: warp sums side by side in the (now free) region, one barrier pair per 64 slots ----
+        __syncthreads();
+        double *red = region;                       // [kGW][64]
+        for (int j0 = 0; j0 <= (int)ntheta; j0 += 64) {
+            const int cnt = min(64, (int)ntheta + 1 - j0);
+            for (int jj = 0; jj < cnt; ++jj) {
+                const int j = j0 + jj;
+                const double v = warp_sum(j < (int)ntheta ? gl[j] : gnoise);
+                if (lane == 0) red[warp * 64 + jj] = v;
+            }
             __syncthreads();
-            if (lane == 0) s_red[warp] = v;
-            __syncthreads();
-            if (tid == 0) {
+            if (tid < cnt) {
                 double r = 0.0;
-                for (int w = 0; w < kGW; ++w) r += s_red[w];
+                for (int w = 0; w < kGW; ++w) r += red[w * 64 + tid];
+                const int j = j0 + tid;
                 if (j < (int)ntheta) gout[j] = r; else a.grad_noise[b] = r;
             }
+            __syncthreads();
         }
     }
 }
@@ -498,7 +750,7 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
 size_t region_bytes_for(int nt, int Gd)
 {
     const int Q = nt * 8;
-    const size_t sweep = ((size_t)nt * 64 + (size_t)kGW * 64) * 8;
+    const size_t sweep = (size_t)kGW * 64 * 8;
     size_t diff = ((size_t)Q + MAX_THETA) * 8 + (size_t)Q * 4 + (size_t)Gd * 2;
     diff = (diff + 15) & ~size_t(15);
     return std::max(sweep, diff);
@@ -517,7 +769,7 @@ GradTilePlan plan_grad_tile(int n, int G, int ntab_cap, int ncp_cap, int smem_op
     size_t static_smem = 4096;
     if (cudaFuncGetAttributes(&fa, grad_tile_kernel) == cudaSuccess) static_smem = fa.sharedSizeBytes + 1024;
     else cudaGetLastError();
-    const size_t base = ((size_t)(nt * (nt + 1) / 2) * 64 + Q + 64) * 8;
+    const size_t base = ((size_t)(nt * (nt + 1) / 2) * 64 + Q + 128) * 8;
     pl.nsec = 0;
     pl.region_bytes = (int)region_bytes_for(nt, pl.Gd);
     pl.smem_bytes = base + pl.region_bytes;

@@ -76,6 +76,38 @@ def test_grad_every_node_type(engine, oracle_q, n, use_grid):
         assert abs(gnz[0, p] - wnz) < 2e-6 * scale
 
 
+# One tree per route through the tile kernel's differentiation pass (csrc/nagp_grad_tile.cu): leaves under the root's
+# Plus nodes are summarised by lag sums / weighted moments, what is left is swept in registers (<= 9 compiled ops) or
+# by the local-memory interpreter.
+L1, L2, L3 = kn.Linear(0.3, 0.2, 0.7), kn.Linear(-0.2, 0.1, 0.4), kn.Linear(0.6, 0.3, 0.2)
+SE, PER, GE = kn.SquaredExponential(0.3, 0.9), kn.Periodic(0.9, 0.25, 0.8), kn.GammaExponential(0.4, 1.3, 0.6)
+ROUTES = [
+    kn.Plus(SE, kn.Plus(L1, kn.Plus(kn.Constant(0.4), PER))),                              # nothing left to interpret
+    kn.Plus(L1, kn.Times(L2, SE)),                                                         # moments + a three-op rest
+    kn.Plus(kn.Times(L1, SE), kn.Plus(kn.Constant(0.3), kn.ChangePoint(GE, L2, 0.45, 0.05))),   # two terms re-joined
+    kn.Times(L1, kn.Times(SE, kn.Times(L2, PER))),                                         # seven ops in registers
+    kn.Plus(PER, kn.Times(L1, kn.Times(L2, kn.Times(L3, kn.Times(L1, kn.Times(L2, SE)))))),     # too many leaves: interpreter
+]
+
+
+@pytest.mark.parametrize("use_grid", [False, True])
+def test_grad_every_route_of_the_differentiation_pass(engine, oracle_q, use_grid):
+    n = 37
+    w = syn.make_workload(n, 0, 0, 1, 2, seed=5)
+    noise = np.array([0.05, 0.2, 0.1, 0.02, 0.08])
+    ens = kn.pack_ensemble(ROUTES, noise)
+    g = w.g[:n] if use_grid else None
+    lm, gth, gnz, info = engine.logml_grad(ens, w.t[:n], w.y1, g=g, step=w.step)
+    assert (info == 0).all()
+    for p, tr in enumerate(ROUTES):
+        prog, th = kn.flatten(tr)
+        wth, wnz = fd_grad(oracle_q, prog, th, noise[p], w.t[:n], w.y1, g, w.step)
+        got = gth[0, ens.theta_off[p]:ens.theta_off[p + 1]]
+        scale = max(np.abs(wth).max(), abs(wnz), 1.0)
+        assert np.abs(got - wth).max() < 2e-6 * scale, (p, got, wth)
+        assert abs(gnz[0, p] - wnz) < 2e-6 * scale
+
+
 def test_grad_prior_sampled_trees_per_scenario(engine, oracle_q):
     """K scenarios with their own hyperparameters and nowcast values: the per-scenario HMC batch."""
     n, k, P, K = 40, 2, 5, 3
