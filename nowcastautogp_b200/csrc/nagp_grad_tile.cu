@@ -39,13 +39,36 @@
 #include "nagp_tree.cuh"
 #include "nagp_tile.cuh"
 
+#ifndef NAGP_GRAD_LOAD
+#define NAGP_GRAD_LOAD 1        // 16-byte loads batched per thread while the factor streams in (measured: 1 17.3 ms, 2-4 18.0, 8 18.5
+                                // per 32 000 chains - the other CTA of the SM hides this phase, and larger batches cost registers)
+#endif
+#ifndef NAGP_GRAD_LD
+#define NAGP_GRAD_LD(p) (*(p))
+#endif
+#ifndef NAGP_GRAD_TRACE
+#define NAGP_GRAD_TRACE 0   // n: clock64 stamps of the n-th instance of block 0 for tools/grad_timeline.py; 0 in product builds
+#endif
+#if NAGP_GRAD_TRACE
+__device__ long long g_grad_trace[32 * 8 * 8 + 16];      // [tile column][warp][stamp], then per-phase stamps
+extern "C" int nagp_debug_read_grad(long long *out, int count)
+{
+    return (int)cudaMemcpyFromSymbol(out, g_grad_trace, sizeof(long long) * count);
+}
+#define GTR(I, ph) do { if (tracing && lane == 0) g_grad_trace[((I) * 8 + warp) * 8 + (ph)] = clock64(); } while (0)
+#define GTP(i) do { if (tracing && tid == 0) g_grad_trace[32 * 8 * 8 + (i)] = clock64(); } while (0)
+#else
+#define GTR(I, ph) do { } while (0)
+#define GTP(i) do { } while (0)
+#endif
+
 namespace nagp {
 
 namespace {
 
 constexpr int kGW = 8;              // warps per CTA
 constexpr int kGT2 = kGW * 32;
-constexpr int kMaxRows = (29 + kGW - 1) / kGW;
+constexpr int kMaxRows = 4;         // work slots per warp and tile column (covers 32 tile rows; shared memory stops at 28)
 
 struct RevProgram {
     int8_t cleft[MAX_PROG];    // compiled program: root index of the left child of a binary node
@@ -352,7 +375,7 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
     const int G = a.G, Gd = lay.Gd;
 
     double *tiles = smem;
-    double *alpha = tiles + ntiles * 64;        // [Q]
+    double *alpha = tiles + (ntiles + nt) * 64; // [Q] z during the sweep (tile row nt of `tiles` is alpha's row), alpha after it
     double *invs = alpha + Q;                   // [2][64] inverses of the diagonal tiles of L, current and next column
     double *region = invs + 128;
     // sweep view of the region
@@ -373,9 +396,6 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
     const int ts0 = lj * 4 + (lr >> 1);                   // accumulator layout -> A operand of the transposed tile
     const bool odd = lane & 1;
     const uint32_t tiles_a = smem_addr(tiles), invs_a = smem_addr(invs);
-    const int nreg = warp < nt ? (nt - 1 - warp) / kGW + 1 : 0;
-    const int Ilast = warp + (nreg - 1) * kGW;
-    const bool has_alpha = (warp == nt % kGW);
 
     // C (accumulator layout) times invL, result in accumulator layout: X * invL = X * (invL^T)^T
     auto times_inv = [&](uint32_t inv_a, double c0, double c1, double &x0, double &x1) {
@@ -387,12 +407,20 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
         dmma(x0, x1, odd ? v11 : v10, iby);
     };
 
+#if NAGP_GRAD_TRACE
+    int n_inst = 0;
+#endif
     for (;;) {
         __syncthreads();
         if (tid == 0) s_next = (long long)atomicAdd(lay.work_counter, 1ull);
         __syncthreads();
         const int64_t b = s_next;
         if (b >= a.B) break;
+#if NAGP_GRAD_TRACE
+        const bool tracing = (blockIdx.x == 0 && ++n_inst == NAGP_GRAD_TRACE);
+        if (tracing && tid == 0) g_grad_trace[32 * 8 * 8 + 15] = b % a.P;
+#endif
+        GTP(0);
         const int64_t s = b / a.P;
         const int p = (int)(b % a.P);
         const int64_t po = a.prog_off[p], plen = a.prog_off[p + 1] - po;
@@ -417,13 +445,28 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
         {   // factor into shared memory, every tile transposed: tile (K, I) then holds L_KI^T in operand layout, which is
             // the B operand of every product of the sweep (one 16-byte LDS), and no column has to be staged
             const double2 *Lg = reinterpret_cast<const double2 *>(a.L + (size_t)b * ((size_t)ntiles * 64));
-            for (int i = tid; i < ntiles * 32; i += kGT2) {
-                const double2 v = Lg[i];
-                const int ln = i & 31, r = ln >> 2, c = ln & 3;
-                double *dst = tiles + (i >> 5) * 64 + op_idx(c, r);
-                dst[0] = v.x;            // element (r, c) -> (c, r)
-                dst[32] = v.y;           // element (r, c + 4) -> (c + 4, r)
+            // several 16-byte loads in flight per thread: the factor is ~100 KB straight from HBM
+            const int nld = ntiles * 32;
+            for (int i0 = tid; i0 < nld; i0 += kGT2 * NAGP_GRAD_LOAD) {
+                double2 v[NAGP_GRAD_LOAD];
+#pragma unroll
+                for (int q = 0; q < NAGP_GRAD_LOAD; ++q)
+                    if (i0 + q * kGT2 < nld) v[q] = NAGP_GRAD_LD(Lg + i0 + q * kGT2);
+#pragma unroll
+                for (int q = 0; q < NAGP_GRAD_LOAD; ++q) {
+                    const int i = i0 + q * kGT2;
+                    if (i < nld) {
+                        const int ln = i & 31, r = ln >> 2, c = ln & 3;
+                        double *dst = tiles + (i >> 5) * 64 + op_idx(c, r);
+                        dst[0] = v[q].x;         // element (r, c) -> (c, r)
+                        dst[32] = v[q].y;        // element (r, c + 4) -> (c + 4, r)
+                    }
+                }
             }
+            // alpha rides along as tile row nt (its first row; the other seven stay zero), z waits in shared memory
+            for (int i = tid; i < nt * 64; i += kGT2) tiles[ntiles * 64 + i] = 0.0;
+            const double *zg = a.z + (size_t)b * Q;
+            for (int i = tid; i < Q; i += kGT2) alpha[i] = zg[i];
         }
         __syncthreads();
         if (tp.error) {
@@ -433,7 +476,6 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
         }
         if (tid == 0) peel_root(tp, rp);
         if (tid == 32) left_roots(tp.sop, tp.slen, rp.sleft);
-        const double *zb = a.z + (size_t)b * Q;
         const double *Wb = a.Winv + (size_t)b * ((size_t)nt * 64);
 
         // ---- 1. S = K^-1 in place, alpha = K^-1 y ------------------------------------------------------------
@@ -441,6 +483,7 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
         // so the column may be overwritten by S. B: column I of S and the partial sums of its diagonal tile are in place.
         // The diagonal tile S_II is finished after B by the warp that owns row I, which needs it only for that row (its
         // last of the next column); the other warps go straight on with rows that do not touch it.
+        GTP(1);
         if (tid < 64) invs[((nt - 1) & 1) * 64 + tid] = Wb[(nt - 1) * 64 + tid];
         auto finish_diag = [&](int D) {
             double t0 = 0.0, t1 = 0.0;
@@ -460,66 +503,102 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
             __syncwarp();
         };
         for (int I = nt - 1; I >= 0; --I) {
+            GTR(I, 0);
             __syncthreads();                                   // B of column I+1 (first pass: the factor is loaded)
+            GTR(I, 1);
             const uint32_t inv_cur = invs_a + (uint32_t)((I & 1) * 512);
             double wnext = 0.0;
             if (tid < 64 && I > 0) wnext = Wb[(I - 1) * 64 + tid];
-            if (I + 1 < nt && warp == (I + 1) % kGW) finish_diag(I + 1);
-            const int NA = Ilast > I ? (Ilast - I - 1) / kGW + 1 : 0;      // owned rows J > I (slots from the bottom)
+            // Work of column I, dealt afresh: the warp that finishes the diagonal tile of column I+1 takes row I+1 (the
+            // only row that needs that tile) as its last slot; alpha and the rows below are dealt round-robin to the
+            // other seven warps first, so the serial piece sits on the least loaded warp.
+            const int r = nt - 1 - I, w0 = (I + 1) % kGW, pos = (warp - w0 - 1) & (kGW - 1);
+            auto row_of = [&](int u) -> int {
+                if (u == kMaxRows - 1 && warp == w0) return r >= 1 ? I + 1 : -1;
+                const int e = pos + kGW * u;                    // e = 0 is alpha's row nt, e >= 1 is row nt - e
+                return (e == 0 || e <= r - 1) ? nt - e : -1;
+            };
+            if (I + 1 < nt && warp == w0) finish_diag(I + 1);
+            GTR(I, 2);
             double pd[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
             double xs[kMaxRows][2];
 #pragma unroll
             for (int u = 0; u < kMaxRows; ++u) {
-                if (u < NA) {
-                    const int J = Ilast - u * kGW;
-                    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+                const int J = row_of(u);
+                if (J >= 0) {
+                    // four independent accumulator pairs (two tile products in flight): the dependent DMMA chain of a
+                    // row is what a warp waits on, and the FP64 tensor pipe is rarely full
+                    double acc[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+                    const bool is_alpha = (J == nt);              // alpha_I^T = -(sum_K alpha_K^T L_KI - z_I^T) L_II^-1
+                    const int Jd = is_alpha ? nt - 1 : J;         // last directly stored tile of the row
+                    if (is_alpha && lr == 0) { acc[0][0] = -alpha[I * 8 + 2 * lj]; acc[0][1] = -alpha[I * 8 + 2 * lj + 1]; }
                     const uint32_t rowa = tiles_a + (uint32_t)(tri(J) * 512 + lane * 16);
-                    const uint32_t cola = tiles_a + (uint32_t)(I * 512 + lane * 16);      // + tri(K) * 512: tile (K, I)
-                    for (int K = I + 1; K <= J; ++K) {
+                    uint32_t cb = tiles_a + (uint32_t)((tri(I + 1) + I) * 512 + lane * 16);   // tile (K, I), K = I + 1
+                    int K = I + 1;
+                    for (; K + 1 <= Jd; K += 2) {
+                        const double2 af0 = lds128(rowa + (uint32_t)K * 512u);
+                        const double2 bf0 = lds128(cb);
+                        const double2 af1 = lds128(rowa + (uint32_t)K * 512u + 512u);
+                        const double2 bf1 = lds128(cb + (uint32_t)(K + 1) * 512u);
+                        cb += (uint32_t)(2 * K + 3) * 512u;
+                        dmma(acc[0][0], acc[0][1], af0.x, bf0.x);
+                        dmma(acc[1][0], acc[1][1], af0.y, bf0.y);
+                        dmma(acc[2][0], acc[2][1], af1.x, bf1.x);
+                        dmma(acc[3][0], acc[3][1], af1.y, bf1.y);
+                    }
+                    if (K <= Jd) {
                         const double2 af = lds128(rowa + (uint32_t)K * 512u);
-                        const double2 bf = lds128(cola + (uint32_t)tri(K) * 512u);
+                        const double2 bf = lds128(cb);
+                        cb += (uint32_t)(K + 1) * 512u;
                         dmma(acc[0][0], acc[0][1], af.x, bf.x);
                         dmma(acc[1][0], acc[1][1], af.y, bf.y);
+                        ++K;
                     }
-                    for (int K = J + 1; K < nt; ++K) {
-                        const uint32_t ta = tiles_a + (uint32_t)((tri(K) + J) * 512 + tr0 * 8);
+                    // K = J + 1: mirrored tiles S_JK = S_KJ^T, read transposed
+                    uint32_t ta = tiles_a + (uint32_t)((tri(K) + J) * 512 + tr0 * 8);
+                    for (; K + 1 < nt; K += 2) {
+                        const double ax0 = lds64(ta), ay0 = lds64(ta + 256);
+                        const double2 bf0 = lds128(cb);
+                        const uint32_t ta1 = ta + (uint32_t)(K + 1) * 512u;
+                        const double ax1 = lds64(ta1), ay1 = lds64(ta1 + 256);
+                        const double2 bf1 = lds128(cb + (uint32_t)(K + 1) * 512u);
+                        ta += (uint32_t)(2 * K + 3) * 512u;
+                        cb += (uint32_t)(2 * K + 3) * 512u;
+                        dmma(acc[0][0], acc[0][1], ax0, bf0.x);
+                        dmma(acc[1][0], acc[1][1], ay0, bf0.y);
+                        dmma(acc[2][0], acc[2][1], ax1, bf1.x);
+                        dmma(acc[3][0], acc[3][1], ay1, bf1.y);
+                    }
+                    if (K < nt) {
                         const double ax = lds64(ta), ay = lds64(ta + 256);
-                        const double2 bf = lds128(cola + (uint32_t)tri(K) * 512u);
+                        const double2 bf = lds128(cb);
                         dmma(acc[0][0], acc[0][1], ax, bf.x);
                         dmma(acc[1][0], acc[1][1], ay, bf.y);
                     }
+                    acc[0][0] = (acc[0][0] + acc[2][0]) + (acc[1][0] + acc[3][0]);
+                    acc[0][1] = (acc[0][1] + acc[2][1]) + (acc[1][1] + acc[3][1]);
+                    const uint32_t cola = tiles_a + (uint32_t)(I * 512 + lane * 16);      // + tri(K) * 512: tile (K, I)
                     double x0, x1;
-                    times_inv(inv_cur, -(acc[0][0] + acc[1][0]), -(acc[0][1] + acc[1][1]), x0, x1);
+                    times_inv(inv_cur, -acc[0][0], -acc[0][1], x0, x1);
                     xs[u][0] = x0; xs[u][1] = x1;
-                    // partial sum of the diagonal tile, S_JI^T L_JI: S_JI^T as an A operand straight from the registers
-                    const double s00 = shfl(x0, ts0), s01 = shfl(x1, ts0);
-                    const double s10 = shfl(x0, ts0 + 16), s11 = shfl(x1, ts0 + 16);
-                    const double2 bf = lds128(cola + (uint32_t)tri(J) * 512u);
-                    dmma(pd[0][0], pd[0][1], (lr & 1) ? s01 : s00, bf.x);
-                    dmma(pd[1][0], pd[1][1], (lr & 1) ? s11 : s10, bf.y);
+                    if (!is_alpha) {
+                        // partial sum of the diagonal tile, S_JI^T L_JI: S_JI^T as an A operand straight from the registers
+                        const double s00 = shfl(x0, ts0), s01 = shfl(x1, ts0);
+                        const double s10 = shfl(x0, ts0 + 16), s11 = shfl(x1, ts0 + 16);
+                        const double2 bf = lds128(cola + (uint32_t)tri(J) * 512u);
+                        dmma(pd[0][0], pd[0][1], (lr & 1) ? s01 : s00, bf.x);
+                        dmma(pd[1][0], pd[1][1], (lr & 1) ? s11 : s10, bf.y);
+                    }
                 }
             }
-            if (has_alpha) {
-                double ya[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-                for (int K = I + 1; K < nt; ++K) {
-                    const double2 bf = lds128(tiles_a + (uint32_t)((tri(K) + I) * 512 + lane * 16));
-                    const double a0 = lr == 0 ? alpha[K * 8 + lj] : 0.0;
-                    const double a1 = lr == 0 ? alpha[K * 8 + 4 + lj] : 0.0;
-                    dmma(ya[0][0], ya[0][1], a0, bf.x);
-                    dmma(ya[1][0], ya[1][1], a1, bf.y);
-                }
-                const double z0 = lr == 0 ? zb[I * 8 + 2 * lj] : 0.0;
-                const double z1 = lr == 0 ? zb[I * 8 + 2 * lj + 1] : 0.0;
-                double x0, x1;
-                times_inv(inv_cur, z0 - (ya[0][0] + ya[1][0]), z1 - (ya[0][1] + ya[1][1]), x0, x1);
-                if (lr == 0) { alpha[I * 8 + 2 * lj] = x0; alpha[I * 8 + 2 * lj + 1] = x1; }
-                __syncwarp();
-            }
+            GTR(I, 3);
             __syncthreads();                                   // A: column I of L is dead
+            GTR(I, 4);
 #pragma unroll
             for (int u = 0; u < kMaxRows; ++u) {
-                if (u < NA) {
-                    const uint32_t dt = tiles_a + (uint32_t)((tri(Ilast - u * kGW) + I) * 512);
+                const int J = row_of(u);
+                if (J >= 0) {
+                    const uint32_t dt = tiles_a + (uint32_t)((tri(J) + I) * 512);
                     sts64(dt + oi0 * 8, xs[u][0]);
                     sts64(dt + oi1 * 8, xs[u][1]);
                 }
@@ -529,7 +608,9 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
         }
         __syncthreads();
         if (warp == 0) finish_diag(0);
+        for (int i = tid; i < Q; i += kGT2) alpha[i] = tiles[(ntiles + (i >> 3)) * 64 + op_idx(0, i & 7)];
         __syncthreads();
+        GTP(2);
 
         // ---- 2. tables for the forward values of the compiled program ------------------------------------------
         for (int i = tid; i < Q; i += kGT2) {
@@ -555,6 +636,8 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
         }
         __syncthreads();
 
+        GTP(3);
+        GTR(31, 0);
         // ---- 3. reverse mode per entry: lane <-> lag within a group of 32 lags, rows dealt round-robin to the warps --
         // Every warp walks every lag group over its own rows (a = warp, warp + 8, ...), so the triangle's uneven
         // diagonals cost all warps the same; a lag's adjoint sum is then split over the 8 warps and recombined in a
@@ -711,7 +794,9 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
                 }
             }
         }
+        GTR(31, 1);
         __syncthreads();
+        GTP(4);
         // ---- 4. table adjoints through the stationary sub-trees, once per (table, lag) -------------------------
         for (int d = tid; d < G; d += kGT2) {
             for (int j = 0; j < ntab; ++j) {
@@ -726,6 +811,7 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
             }
         }
         // ---- 5. block reduction: warp sums side by side in the (now free) region, one barrier pair per 64 slots ----
+        GTR(31, 2);
         __syncthreads();
         double *red = region;                       // [kGW][64]
         for (int j0 = 0; j0 <= (int)ntheta; j0 += 64) {
@@ -744,6 +830,8 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
             }
             __syncthreads();
         }
+        GTR(31, 3);
+        GTP(5);
     }
 }
 
@@ -764,12 +852,12 @@ GradTilePlan plan_grad_tile(int n, int G, int ntab_cap, int ncp_cap, int smem_op
     const int nt = (n + 7) / 8, Q = nt * 8;
     pl.nt = nt;
     pl.Gd = G > 0 ? G : n;
-    if (pl.Gd > 16384) { pl.ok = 0; return pl; }                 // ginv holds 16-bit row indices
+    if (pl.Gd > 16384 || nt > 8 * kMaxRows) { pl.ok = 0; return pl; }   // ginv holds 16-bit row indices; row slots per warp
     cudaFuncAttributes fa{};
     size_t static_smem = 4096;
     if (cudaFuncGetAttributes(&fa, grad_tile_kernel) == cudaSuccess) static_smem = fa.sharedSizeBytes + 1024;
     else cudaGetLastError();
-    const size_t base = ((size_t)(nt * (nt + 1) / 2) * 64 + Q + 128) * 8;
+    const size_t base = ((size_t)(nt * (nt + 1) / 2 + nt) * 64 + Q + 128) * 8;
     pl.nsec = 0;
     pl.region_bytes = (int)region_bytes_for(nt, pl.Gd);
     pl.smem_bytes = base + pl.region_bytes;
