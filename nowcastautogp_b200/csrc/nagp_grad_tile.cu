@@ -642,14 +642,15 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
         // Every warp walks every lag group over its own rows (a = warp, warp + 8, ...), so the triangle's uneven
         // diagonals cost all warps the same; a lag's adjoint sum is then split over the 8 warps and recombined in a
         // fixed order below (bit-reproducible, no atomics).
+        const bool grid = a.g != nullptr;
         double gl[MAX_THETA];
         for (int j = 0; j < (int)ntheta; ++j) gl[j] = 0.0;
         double gnoise = 0.0;
-        const bool grid = a.g != nullptr;
         // what peel_root took out of the program: per entry these leaves cost one add (lag tables) or five FLOP (moments)
         const bool resid = tp.clen > 0;
         const uint32_t peel_tab = rp.peel_tab;
-        const bool peel_mom = (rp.npeel_lin | rp.npeel_con) != 0, peel_any = peel_mom || peel_tab != 0;
+        const bool peel_mom = (rp.npeel_lin | rp.npeel_con) != 0;
+        const bool regular = grid && gg[n - 1] - g0 == n - 1;  // no gaps in the time grid
         const double tc = 0.5 * (tt[0] + tt[n - 1]);            // moments are taken about the middle of the series
         double m0 = 0.0, m1 = 0.0, m2 = 0.0;
         // Short compiled programs — one leaf, or two leaves under one Plus / Times / tabulated ChangePoint, leaves being
@@ -675,26 +676,39 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
             double hacc[MAX_TABLES];
 #pragma unroll
             for (int j = 0; j < MAX_TABLES; ++j) hacc[j] = 0.0;
-            double ha0 = 0.0, ha1 = 0.0, hp = 0.0;
+            double ha0 = 0.0, ha1 = 0.0;
+            double wsum = 0.0, q1 = 0.0, q2 = 0.0;             // this lag's sums of w, w u_a, w u_a^2 (u = t - tc)
+            const double fw = d == 0 ? 0.5 : 1.0;              // the entry's weight: W_ab on the diagonal, 2 W_ab below it
             double rh[kRegTab];
 #pragma unroll
             for (int j = 0; j < kRegTab; ++j) rh[j] = 0.0;
             for (int ia = warp; ia < n; ia += kGW) {
-                const int ga = gg[ia] - g0;
-                if (ga < lg * 32) continue;                    // no lag of this group reaches back from row ia
-                const int gb = ga - d;
-                const int ib = (gb >= 0 && d < Gd) ? ginv[gb] : -1;
-                if (ib < 0) continue;
+                int ib;
+                if (regular) {                                 // complete grid: the partner of row ia at lag d is row ia - d
+                    if (ia < lg * 32) continue;
+                    ib = ia - d;
+                    if (ib < 0) continue;
+                } else {
+                    const int ga = gg[ia] - g0;
+                    if (ga < lg * 32) continue;                // no lag of this group reaches back from row ia
+                    const int gb = ga - d;
+                    ib = (gb >= 0 && d < Gd) ? ginv[gb] : -1;
+                    if (ib < 0) continue;
+                }
                 const double Sab = tiles[(tri(ia >> 3) + (ib >> 3)) * 64 + op_idx(ia & 7, ib & 7)];
-                const double Wab = 0.5 * (alpha[ia] * alpha[ib] - Sab);
-                const double w = d == 0 ? Wab : 2.0 * Wab;
-                if (d == 0) gnoise += Wab;
-                if (peel_any) hp += w;                          // a lag table under the root: the entry's weight IS the adjoint
+                const double w = fw * (alpha[ia] * alpha[ib] - Sab);
+                wsum += w;            // lag 0: d logML / d noise; a lag table under the root: the weight IS the adjoint
                 if (!peel_mom && !resid) continue;
-                const double ti = tt[ia], tj = tt[ib];
-                if (peel_mom) {
+                const double ti = tt[ia];
+                if (peel_mom && grid) {                        // t_b = t_a - d step: moments of the row time only
+                    const double wu = w * (ti - tc);
+                    q1 += wu; q2 += wu * (ti - tc);
+                    if (!resid) continue;
+                }
+                const double tj = tt[ib];
+                if (peel_mom && !grid) {
                     const double ui = ti - tc, uj = tj - tc;
-                    m0 += w; m1 += w * (ui + uj); m2 += w * (ui * uj);
+                    m1 += w * (ui + uj); m2 += w * (ui * uj);
                 }
                 if (!resid) continue;
                 if (short_prog) {
@@ -743,13 +757,22 @@ __global__ void __launch_bounds__(kGT2, 2) grad_tile_kernel(const GradArgs a, co
                 rev_entry(tp.cop, tp.carg, tp.caux, rp.cleft, 0, tp.clen, th, ti, tj, delta, d, ia, ib, tab, G, sig, Q,
                           w, gl, hacc);
             }
+            if (d == 0) gnoise += wsum;
+            if (peel_mom) {
+                m0 += wsum;
+                if (grid) {               // sum w (ua + ub) and sum w ua ub with ub = ua - d step
+                    const double dd = (double)d * a.step;
+                    m1 += 2.0 * q1 - dd * wsum;
+                    m2 += q2 - dd * q1;
+                }
+            }
             if (reg_prog) {
 #pragma unroll
                 for (int j = 0; j < kRegTab; ++j) hacc[j] += rh[j];
             }
 #pragma unroll
             for (int j = 0; j < MAX_TABLES; ++j)
-                if ((peel_tab >> j) & 1u) hacc[j] += hp;
+                if ((peel_tab >> j) & 1u) hacc[j] += wsum;
             if (short_prog) {
                 // named accumulators back to their tables (two leaves may share nothing: table ids are distinct)
                 if (k0 == OP_TABLE) hacc[a0] += ha0;
