@@ -608,8 +608,9 @@ def main():
         from nowcastautogp_b200 import synthetic as syn
         from nowcastautogp_b200.sharding import partition
         S4, n4, k4, h4, P4, K4, D4 = 53, 150, 1, 4, 64, 1000, 20
-        parts = partition(S4, K4, world)
-        mine = [sl.series for sl in parts[rank]]
+        parts = partition(S4, K4, world)                           # scenario-shared regime: whole series per rank
+        parts_split = partition(S4, K4, world, split_series=True)  # per-scenario regime: the pair list cut evenly
+        mine = sorted({sl.series for sl in parts[rank]} | {sl.series for sl in parts_split[rank]})
         ser = {}
         for s_ in mine:
             ws = syn.make_workload(n4, k4, h4, K4, P4, seed=1000 + s_, max_depth=4)
@@ -625,22 +626,25 @@ def main():
 
         def comp_per_scenario(sl, x_out, lw_out):
             d_ = ser[sl.series]; ws = d_["w"]
-            eng.forecast_instances(d_["ens"], n4, k4, h4, ws.t, d_["y1"], d_["y2"], d_["lw0"], ws.ya, ws.yb, g=ws.g,
-                                   step=ws.step, theta=d_["th"], noise=d_["nz"], K=K4, logw=lw_out, mu=mu4, L=L4, info=inf4)
-            eng.draw(lw_out, mu4, L4, d_["zeta"], u=d_["u"], x=x_out, want_aux=False)
+            a_, b_ = sl.k0, sl.k1
+            eng.forecast_instances(d_["ens"], n4, k4, h4, ws.t, d_["y1"], d_["y2"][a_:b_], d_["lw0"], ws.ya, ws.yb, g=ws.g,
+                                   step=ws.step, theta=d_["th"][a_:b_], noise=d_["nz"][a_:b_], K=b_ - a_, logw=lw_out,
+                                   mu=mu4[:b_ - a_], L=L4[:b_ - a_], info=inf4[:b_ - a_])
+            eng.draw(lw_out, mu4[:b_ - a_], L4[:b_ - a_], d_["zeta"][a_:b_], u=d_["u"][a_:b_], x=x_out, want_aux=False)
 
         def comp_shared(sl, x_out, lw_out):
             d_ = ser[sl.series]; ws = d_["w"]
             eng.forecast_with_nowcasts(d_["ens"], n4, k4, h4, ws.t, d_["y1"], d_["y2"], d_["lw0"], d_["zeta"], ws.ya, ws.yb,
                                        g=ws.g, step=ws.step, u=d_["u"], x=x_out, logw=lw_out, info=inf4[0], K=K4, D=D4)
 
-        def local_only(comp):
+        def local_only(comp, parts_):
             # this rank's compute without the gather: per-rank time, for the load-imbalance figure
             xs = torch.empty((K4 * D4, h4), dtype=torch.float64, device=dev)
             ls = torch.empty((K4, P4), dtype=torch.float64, device=dev)
             def run():
-                for sl in parts[rank]:
-                    comp(sl, xs, ls)
+                for sl in parts_[rank]:
+                    kk = sl.k1 - sl.k0
+                    comp(sl, xs[:kk * D4], ls[:kk])
             return run
 
         def per_rank(ms_local):
@@ -653,17 +657,22 @@ def main():
 
         out = {"what": "BASELINE configs[3]: 53 series x 64 particles x 1000 nowcast scenarios (n=150, k=1, h=4, D=20), series-first "
                        "partition over the ranks (sharding.partition), one packed all-gather per step (sharding.sharded_forecast)",
-               "series_per_rank": [len(p_) for p_ in parts], "draws_per_step": S4 * K4 * D4}
+               "series_per_rank": [len(p_) for p_ in parts],
+               "pairs_per_rank_split": [sum(sl.k1 - sl.k0 for sl in p_) for p_ in parts_split], "draws_per_step": S4 * K4 * D4}
         steps4 = max(2, min(args.steps, 5))
         fl_inst = flops_per_instance(n4, k4, h4)
-        for name, comp in (("per_scenario_theta", comp_per_scenario), ("scenario_shared", comp_shared)):
-            ms = timed(lambda: sharded_forecast(comp, S4, K4, h4, D4, P4, device=dev, in_place=True), steps4, 3)
-            ms_loc = per_rank(timed_local(local_only(comp), steps4, 2))
+        for name, comp, split in (("per_scenario_theta", comp_per_scenario, True), ("scenario_shared", comp_shared, False)):
+            parts_ = parts_split if split else parts
+            ms = timed(lambda: sharded_forecast(comp, S4, K4, h4, D4, P4, device=dev, in_place=True, split_series=split),
+                       steps4, 3)
+            ms_loc = per_rank(timed_local(local_only(comp, parts_), steps4, 2))
+            pairs_ = [sum(sl.k1 - sl.k0 for sl in p_) for p_ in parts_]
             blk = {"ms_per_step": ms, "value": S4 * K4 * D4 / (ms * 1e-3), "unit": UNIT, "per_rank_compute_ms": ms_loc,
                    "imbalance_max_over_mean": max(ms_loc) / (sum(ms_loc) / len(ms_loc)),
-                   "partition_efficiency_cap": (S4 / world) / max(len(p_) for p_ in parts)}
+                   "partition": "pairs cut evenly (split_series)" if split else "whole series per rank",
+                   "partition_efficiency_cap": (S4 * K4 / world) / max(pairs_)}
             if name == "per_scenario_theta":
-                fl_busy = max(len(p_) for p_ in parts) * K4 * P4 * fl_inst
+                fl_busy = max(pairs_) * P4 * fl_inst
                 blk["roofline"] = {"bound": "tensor", "unit": "TFLOP/s", "peak": None,
                                    "achieved_busiest_rank": fl_busy / (max(ms_loc) * 1e-3) / 1e12,
                                    "achieved_aggregate": S4 * K4 * P4 * fl_inst / (ms * 1e-3) / 1e12 / world,
@@ -713,14 +722,14 @@ def main():
         if not pr_ < 1e-9:
             raise SystemExit(f"bench c4: device disagrees with the CPU oracle ({pr_:.3e})")
         try:
-            out["api"] = run_c4_api(S4, n4, k4, h4, P4, K4, D4, parts)
+            out["api"] = run_c4_api(S4, n4, k4, h4, P4, K4, D4, set(mine))
         except Exception as e:      # noqa: BLE001 - the device-level block above stands on its own
             if world > 1:
                 raise               # a rank that drops out of the collectives would hang the others
             out["api"] = {"error": f"{type(e).__name__}: {e}"}
         return out
 
-    def run_c4_api(S4, n4, k4, h4, P4, K4, D4, parts):
+    def run_c4_api(S4, n4, k4, h4, P4, K4, D4, mine_set):
         """The same configuration through the PUBLIC API: GPModel objects (prior-sampled particle sets that absorbed their
         series in one SMC step), TData scenarios, `forecast_with_nowcasts_sharded` with n_hmc = 0 and n_hmc = 1."""
         import nowcastautogp_b200 as nag
@@ -738,7 +747,7 @@ def main():
             models.append(m_)
             scen = raw[-1] * np.exp(0.1 + 0.027 * rg.standard_normal((k4, K4)))
             nowcasts.append(nag.create_nowcast_data(scen, dates[n4:n4 + k4], transformation=np.log)
-                            if s_ in {sl.series for sl in parts[rank]} else [None] * K4)
+                            if s_ in mine_set else [None] * K4)
         build_s = time.perf_counter() - t_build
         fdates = dates[n4 + k4:]
         out = {"what": "forecast_with_nowcasts_sharded (public API, host objects in, NumPy matrices out on every rank)",

@@ -265,8 +265,10 @@ def forecast_with_nowcasts_sharded(base_models: Sequence[GPModel], nowcasts: Seq
                                        n_mcmc=n_mcmc, n_hmc=n_hmc, ess_threshold=ess_threshold,
                                        forecast_n_hmc=forecast_n_hmc, rng=slice_rng(sl))
 
+    # per-scenario refinement makes every (series, scenario) pair its own piece of work: cut the pair list evenly;
+    # without it the particles of a series are factored once for all its scenarios, so series stay whole
     draws, logw = sharded_forecast(compute, len(base_models), [len(nc) for nc in nowcasts], h, D, P,
-                                   group=group, device=device)
+                                   group=group, device=device, split_series=(n_hmc > 0 or n_mcmc > 0))
     return {s: _apply(inv_transformation, np.ascontiguousarray(x), base_models[s]._engine())
             for s, x in draws.items()}, logw
 

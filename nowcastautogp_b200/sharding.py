@@ -25,12 +25,15 @@ class Slice:
     k1: int     # last scenario (exclusive)
 
 
-def partition(n_series: int, n_scenarios: Sequence[int] | int, world: int) -> List[List[Slice]]:
+def partition(n_series: int, n_scenarios: Sequence[int] | int, world: int, split_series: bool = False) -> List[List[Slice]]:
     """Contiguous split of the flattened (series, scenario) pairs over `world` ranks.
 
     Whole series are kept together whenever there are at least as many series as ranks (C4: 53 series
-    on 8 GPUs → 7/7/7/7/7/6/6/6); otherwise the pair list is cut into `world` near-equal contiguous
-    runs, which splits a series' scenarios across ranks (C2: one series, K scenarios → K/world each).
+    on 8 GPUs → 7/7/7/7/7/6/6/6); otherwise — or always with `split_series=True` — the pair list is cut into
+    `world` near-equal contiguous runs, which splits a series' scenarios across ranks (C2: one series, K scenarios
+    → K/world each; C4 with `split_series`: 6625 pairs per rank instead of 7000/6000). Splitting costs nothing when
+    every scenario is its own piece of work (per-scenario hyperparameters: `n_hmc > 0`); in the scenario-shared
+    regime it would factor the particles of a boundary series on two GPUs, hence the default.
     Every pair is owned by exactly one rank; a rank's slices are in global order."""
     if world < 1:
         raise ValueError("world must be >= 1")
@@ -38,7 +41,7 @@ def partition(n_series: int, n_scenarios: Sequence[int] | int, world: int) -> Li
     if len(ks) != n_series:
         raise ValueError("n_scenarios must have one entry per series")
     out: List[List[Slice]] = [[] for _ in range(world)]
-    if n_series >= world:
+    if n_series >= world and not split_series:
         base, extra = divmod(n_series, world)
         s = 0
         for r in range(world):
@@ -72,7 +75,7 @@ def _packed_buffers(cap: int, D: int, h: int, P: int, world: int, dev):
 
 
 def sharded_forecast(compute: Callable, n_series: int, n_scenarios: Sequence[int] | int, h: int, D: int, P: int,
-                     group=None, device=None, in_place: bool = False):
+                     group=None, device=None, in_place: bool = False, split_series: bool = False):
     """Run `compute` on this rank's slices and gather with ONE collective.
 
     Host form (default): `compute(slice) -> (x [h, (k1-k0)·D], logw [(k1-k0), P])` as NumPy arrays; returns
@@ -85,7 +88,7 @@ def sharded_forecast(compute: Callable, n_series: int, n_scenarios: Sequence[int
     Either way every rank's results travel in one packed buffer `[pairs·D·h draws | pairs·P log-weights]` and one
     `all_gather_into_tensor` (NCCL over NVLink on the GPU box; the list form of `all_gather` under gloo). Works
     without an initialised process group (world = 1). Ranks may own different numbers of pairs (padded to the
-    largest)."""
+    largest). `split_series`: see `partition`."""
     import torch
     import torch.distributed as dist
 
@@ -93,7 +96,7 @@ def sharded_forecast(compute: Callable, n_series: int, n_scenarios: Sequence[int
     world = dist.get_world_size(group) if use_dist else 1
     rank = dist.get_rank(group) if use_dist else 0
     ks = [int(n_scenarios)] * n_series if np.isscalar(n_scenarios) else [int(k) for k in n_scenarios]
-    parts = partition(n_series, ks, world)
+    parts = partition(n_series, ks, world, split_series)
     mine = parts[rank]
     n_pairs = [sum(s.k1 - s.k0 for s in p) for p in parts]
     cap = max(max(n_pairs), 1)

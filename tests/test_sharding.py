@@ -32,6 +32,18 @@ def test_partition_covers_every_pair_once(S, K, world):
         assert max(cnt) - min(cnt) <= 1
 
 
+@pytest.mark.parametrize("S,K,world", [(53, 1000, 8), (5, [3, 0, 7, 1, 4], 2), (9, 10, 4)])
+def test_partition_split_series_is_even_and_complete(S, K, world):
+    """`split_series=True` (per-scenario regime): the pair list is cut into near-equal contiguous runs even when there
+    are more series than ranks; every pair is still owned exactly once, in global order."""
+    parts = partition(S, K, world, split_series=True)
+    ks = [K] * S if np.isscalar(K) else list(K)
+    counts = [sum(sl.k1 - sl.k0 for sl in p) for p in parts]
+    assert sum(counts) == sum(ks) and max(counts) - min(counts) <= 1
+    seen = [(sl.series, k) for p in parts for sl in p for k in range(sl.k0, sl.k1)]
+    assert seen == [(s, k) for s in range(S) for k in range(ks[s])]
+
+
 def test_partition_c4_shape():
     parts = partition(53, 1000, 8)
     assert [len(p) for p in parts] == [7, 7, 7, 7, 7, 6, 6, 6]
@@ -64,7 +76,7 @@ def test_sharded_forecast_single_process():
         assert np.array_equal(dr[s], edr[s]) and np.array_equal(lw[s], elw[s])
 
 
-def _worker(rank, world, port, S, ks, h, D, P, q):
+def _worker(rank, world, port, S, ks, h, D, P, q, split=False):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -76,7 +88,7 @@ def _worker(rank, world, port, S, ks, h, D, P, q):
             calls.append(sl)
             return _fake_compute(h, D, P)(sl)
 
-        dr, lw = sharded_forecast(compute, S, ks, h, D, P)
+        dr, lw = sharded_forecast(compute, S, ks, h, D, P, split_series=split)
         edr, elw = _expected(S, ks, h, D, P)
         ok = all(np.array_equal(dr[s], edr[s]) and np.array_equal(lw[s], elw[s]) for s in range(S))
         q.put((rank, ok, [(c.series, c.k0, c.k1) for c in calls]))
@@ -84,8 +96,8 @@ def _worker(rank, world, port, S, ks, h, D, P, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("S,ks", [(3, [4, 2, 5]), (1, [7])])
-def test_sharded_forecast_gloo_world2(S, ks):
+@pytest.mark.parametrize("S,ks,split", [(3, [4, 2, 5], False), (1, [7], False), (3, [4, 2, 5], True)])
+def test_sharded_forecast_gloo_world2(S, ks, split):
     import torch.multiprocessing as mp
     with socket.socket() as s_:
         s_.bind(("127.0.0.1", 0))
@@ -93,7 +105,7 @@ def test_sharded_forecast_gloo_world2(S, ks):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     h, D, P, world = 3, 2, 4, 2
-    procs = [ctx.Process(target=_worker, args=(r, world, port, S, ks, h, D, P, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, S, ks, h, D, P, q, split)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]
@@ -102,7 +114,7 @@ def test_sharded_forecast_gloo_world2(S, ks):
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res)                      # every rank holds the full, correctly ordered result
     owned = sorted(c for _, _, calls in res for c in calls)
-    want = sorted((sl.series, sl.k0, sl.k1) for part in partition(S, ks, world) for sl in part)
+    want = sorted((sl.series, sl.k0, sl.k1) for part in partition(S, ks, world, split) for sl in part)
     assert owned == want                                     # each rank computed only its own slices
 
 
