@@ -31,6 +31,25 @@
 #include "nagp_tree.cuh"
 #include "nagp_tile.cuh"
 
+#ifndef NAGP_V2_TRACE
+#define NAGP_V2_TRACE 0     // n: clock64 stamps of the n-th instance of block 0 for tools/v2_timeline.py; 0 in product builds
+#endif
+#if NAGP_V2_TRACE
+// [column][published, handed over], [warp][phase arrival], misc, [column][warp] arrival at the wait for the inverse
+__device__ long long g_v2_trace[32 * 2 + 8 * 8 + 8 + 32 * 8];
+extern "C" int nagp_debug_read_v2(long long *out, int count)
+{
+    return (int)cudaMemcpyFromSymbol(out, g_v2_trace, sizeof(long long) * count);
+}
+#define VTC(J, i) do { if (tracing && lane == 0) g_v2_trace[(J) * 2 + (i)] = clock64(); } while (0)
+#define VTW(ph) do { if (tracing && lane == 0) g_v2_trace[64 + warp * 8 + (ph)] = clock64(); } while (0)
+#define VTO(J) do { if (tracing && lane == 0) g_v2_trace[136 + (J) * 8 + warp] = clock64(); } while (0)
+#else
+#define VTC(J, i) do { } while (0)
+#define VTW(ph) do { } while (0)
+#define VTO(J) do { } while (0)
+#endif
+
 namespace nagp {
 
 namespace {
@@ -181,6 +200,9 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
         gg[i] = (a.g && i < q) ? a.g[i] : 0;
     }
 
+#if NAGP_V2_TRACE
+    int n_inst = 0;
+#endif
     // instances differ a lot in cost (kernel-tree size): hand them out dynamically
     for (;;) {
         __syncthreads();   // previous instance fully consumed (shared memory and s_next)
@@ -188,6 +210,11 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
         __syncthreads();
         const int64_t b = s_next;
         if (b >= a.B) break;
+#if NAGP_V2_TRACE
+        const bool tracing = (blockIdx.x == 0 && ++n_inst == NAGP_V2_TRACE);
+        if (tracing && tid == 0) g_v2_trace[64 + 64] = b % a.P;
+#endif
+        VTW(0);
         const int64_t s = b / a.P;
         const int p = (int)(b % a.P);
         const int64_t po = a.prog_off[p], plen = a.prog_off[p + 1] - po;
@@ -206,6 +233,7 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
         }
         for (int i = tid; i < ntheta && i < MAX_THETA; i += kT2) th[i] = theta_g[i];
         __syncthreads();
+        VTW(1);
         if (tp.error) {
             if (tid == 0) {
                 a.info[b] = tp.error;
@@ -229,6 +257,7 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
             const double *cp = th + tp.cp_theta[id];
             sig[e] = 0.5 * (1.0 + tanh((tt[i] - cp[0]) / cp[1]));
         }
+        VTW(2);
         __syncthreads();
 
         // ---- Gram into row-major tiles: a warp writes two whole tiles per iteration; lane (r, c) owns
@@ -310,6 +339,7 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                 yv[jx] = v;
             }
         }
+        VTW(3);
         __syncthreads();
 
         // ---- left-looking tile-column Cholesky with one column of lookahead ---------------------------
@@ -359,6 +389,7 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                 }
                 if (bad && lane == 0) s_info = J * 8 + bad;
                 __syncwarp();
+                VTC(J, 0);
                 asm volatile("bar.arrive 1, %0;" ::"n"(kTB + 32) : "memory");
                 if (bad) break;
             }
@@ -414,6 +445,7 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                 const bool more = J + 1 < nt;
                 const bool owns_next = more && ph == 1;
                 const int n2 = owns_next ? nsolve - 1 : nsolve;          // rows below diagonal J+1
+                VTO(J);
                 asm volatile("bar.sync 1, %0;" ::"n"(kTB + 32) : "memory");
                 // The chain warp can already be factoring tile J+1 (it only needs the hand-over of one row owner): a
                 // failure it flags there must not make a late row owner leave one column before the others.
@@ -433,6 +465,7 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                     default: break;
                     }
                     __syncwarp();
+                    VTC(J, 1);
                     asm volatile("bar.arrive 2, 64;" ::: "memory");
                     asm volatile("bar.arrive 3, %0;" ::"n"(kTB) : "memory");    // tile (J+1, J) is written
                 }
@@ -494,6 +527,7 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                 }
             }
         }
+        VTW(4);
         __syncthreads();
 
         if (KEEP && a.Lkeep && !s_info) {
@@ -579,6 +613,7 @@ __global__ void __launch_bounds__(kT2, 2) fused_v2_kernel(const FusedArgs a, con
                 a.Ltail[b * kh * kh + e] = cix <= r ? Lel(n + r, n + cix) : 0.0;
             }
         }
+        VTW(5);
     }
 }
 
