@@ -286,7 +286,11 @@ def _forecast_with_nowcasts(base_model: GPModel, nowcasts: Sequence[TData], fore
     dates = np.asarray(list(forecast_dates) if not isinstance(forecast_dates, np.ndarray) else forecast_dates)
     base_dict = base_model.to_dict()                                   # forecasting.jl:128
     ds0 = np.asarray(nowcasts[0].ds)
-    shared_ds = all(len(nc.ds) == len(ds0) and np.array_equal(np.asarray(nc.ds), ds0) for nc in nowcasts)
+    # do all scenarios share the nowcast dates (create_nowcast_data.jl builds them that way)? One vectorised comparison:
+    # a Python-level array_equal per scenario costs more than the device work of the default schedule
+    shared_ds = all(len(nc.ds) == len(ds0) for nc in nowcasts)
+    if shared_ds and any(nc.ds is not nowcasts[0].ds for nc in nowcasts):
+        shared_ds = bool((np.stack([np.asarray(nc.ds) for nc in nowcasts]) == ds0).all())
 
     def scenario_loop(ncs):
         # the reference's schedule verbatim, one model copy per scenario (forecasting.jl:133-155); every likelihood is
@@ -308,7 +312,10 @@ def _forecast_with_nowcasts(base_model: GPModel, nowcasts: Sequence[TData], fore
         # structure moves make the programs diverge per scenario
         return scenario_loop(nowcasts)
 
-    m = GPModel.from_dict(base_dict, engine=base_model.engine, rng=rng)
+    # the batched schedules without rejuvenation only read the model: no private copy needed (the reference copies per
+    # scenario because add_data! mutates; here the appended observations never enter the model object)
+    read_only = n_hmc == 0 and forecast_n_hmc is None
+    m = base_model if read_only else GPModel.from_dict(base_dict, engine=base_model.engine, rng=rng)
     alive = np.isfinite(m.log_weights)
     if not alive.all() and alive.any():
         # particles that left the fit with weight -inf (Gram not positive definite) carry no mass: the batched paths run
@@ -330,7 +337,7 @@ def _forecast_with_nowcasts(base_model: GPModel, nowcasts: Sequence[TData], fore
     t, g, step = m._times(np.concatenate([m.ds[idx], ds0.astype(m.ds.dtype), dates.astype(m.ds.dtype)]))
     yt = m.y_transform
     y1 = yt.apply(m.y[idx])
-    y2 = np.ascontiguousarray(np.stack([yt.apply(np.asarray(nc.y, np.float64)) for nc in nowcasts]))
+    y2 = np.ascontiguousarray(yt.apply(np.stack([np.asarray(nc.y, np.float64) for nc in nowcasts])))
     ens = m.ensemble()
 
     if n_hmc == 0 and forecast_n_hmc is None and k > 16:
