@@ -38,6 +38,21 @@ __device__ __forceinline__ double2 ldg128_stream(const double *p)
     return __ldcg(reinterpret_cast<const double2 *>(p));
 }
 
+// Rank-append streaming ring: stages of 8 tiles (4 KB) per warp that land in shared memory (cp.async, L2 only) instead
+// of registers, so a warp keeps (stages - 1) x 4 KB of the stored row in flight while it consumes one stage.
+// 0: the register-landed loop (4 KB in flight per warp, and only between its compute phases).
+#ifndef NAGP_APPEND_STAGES
+#define NAGP_APPEND_STAGES 3
+#endif
+constexpr int kApStages = NAGP_APPEND_STAGES;
+__device__ __forceinline__ void cp_async16(uint32_t dst, const double *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // accumulator layout (lane (r, j) holds (r, 2j), (r, 2j+1)) -> A-operand fragment (lane (r, kk) holds
 // (r, kk) and (r, kk + 4))
 __device__ __forceinline__ double2 acc_to_frag(double c0, double c1, int lane)
@@ -526,7 +541,8 @@ __global__ void __launch_bounds__(kThreads, 2) rank_append_kernel(const FusedArg
     const int I0 = n_old >> 3;
 
     double *s_x = smem;                                   // [8] X tiles of the current block (operand layout)
-    char *aux_s = reinterpret_cast<char *>(s_x + kWarps * 64);
+    double *s_ring = s_x + kWarps * 64;                   // [kWarps][kApStages][8 tiles] streaming ring (R == 1)
+    char *aux_s = reinterpret_cast<char *>(s_ring + kWarps * kApStages * 8 * 64);
     const Setup su = aux_pointers(lay, aux_s);
 
     for (int i = tid; i < Q; i += kThreads) {
@@ -564,6 +580,9 @@ __global__ void __launch_bounds__(kThreads, 2) rank_append_kernel(const FusedArg
                 // handed from warp to warp through shared memory.
                 const double *xrow = Lb + (size_t)tri(g0) * 64 + lane * 2;      // the new row (A operand)
                 const double *zrow = Lb + (size_t)tri(yrow) * 64 + lane * 2;    // z = L^-1 y
+                const uint32_t ring_a = smem_addr(s_ring) + (uint32_t)(warp * (kApStages * 4096) + lane * 16);
+#pragma unroll
+                for (int st = 0; st < kApStages - 1; ++st) cp_async_commit();   // block J0 = 0 streams nothing
                 for (int J0 = 0; J0 <= g0; J0 += kWarps) {
                     const int J = J0 + warp;
                     const bool rowv = J <= g0;
@@ -571,7 +590,7 @@ __global__ void __launch_bounds__(kThreads, 2) rank_append_kernel(const FusedArg
                     const double *lrow = Lb + (size_t)tri(rowv ? J : 0) * 64 + lane * 2;
                     double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;               // two chains of the row sum
                     double y0 = 0.0, y1 = 0.0;                                   // z_g0 sum (last row only)
-                    if (rowv) {
+                    if (rowv && kApStages == 0) {
                         int P = 0;
                         for (; P + 8 <= J0; P += 8) {      // 4 KB of the stored row in flight per warp
                             double2 bf[8], af[4];
@@ -596,6 +615,74 @@ __global__ void __launch_bounds__(kThreads, 2) rank_append_kernel(const FusedArg
                                 }
                             }
                         }
+                    } else if (kApStages > 0) {
+                        // The first stages of this row were issued before the previous block's triangle (below): every
+                        // lane copies exactly the 16 bytes per tile it consumes, so the ring needs no barrier at all.
+                        const int nch = rowv ? (J0 >> 3) : 0;          // chunks of 8 tiles: P = 8 c
+                        int slot = 0, islot = (kApStages - 1) % (kApStages > 0 ? kApStages : 1);
+                        if (last) {
+                            // the new row reads its own X tiles: they exist only now, after the previous block's triangle
+#pragma unroll
+                            for (int st = 0; st < kApStages - 1; ++st) {
+                                if (st < nch) {
+                                    const uint32_t dst = ring_a + (uint32_t)(st * 4096);
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) cp_async16(dst + i * 512, lrow + (size_t)(st * 8 + i) * 64);
+                                }
+                                cp_async_commit();
+                            }
+                        }
+                        for (int c = 0; c < nch; ++c) {
+                            if (c + kApStages - 1 < nch) {
+                                const double *src = lrow + (size_t)(c + kApStages - 1) * 8 * 64;
+                                const uint32_t dst = ring_a + (uint32_t)(islot * 4096);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) cp_async16(dst + i * 512, src + (size_t)i * 64);
+                            }
+                            cp_async_commit();
+                            cp_async_wait<(kApStages > 0 ? kApStages - 1 : 0)>();
+                            const uint32_t sa = ring_a + (uint32_t)(slot * 4096);
+                            const int P = c * 8;
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) {
+                                double2 af[4];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) af[i] = ldg128(xrow + (size_t)(P + hh * 4 + i) * 64);
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const double2 bf = lds128(sa + (uint32_t)((hh * 4 + i) * 512));
+                                    dmma(a0, a1, af[i].x, bf.x);
+                                    dmma(b0, b1, af[i].y, bf.y);
+                                }
+                            }
+                            if (last) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const double2 zf = ldg128(zrow + (size_t)(P + i) * 64);
+                                    const double2 bf = lds128(sa + (uint32_t)(i * 512));
+                                    dmma(y0, y1, zf.x, bf.x);
+                                    dmma(y0, y1, zf.y, bf.y);
+                                }
+                            }
+                            slot = slot + 1 == kApStages ? 0 : slot + 1;
+                            islot = islot + 1 == kApStages ? 0 : islot + 1;
+                        }
+                        cp_async_wait<0>();
+                        // first stages of the next block's row, in flight under this block's triangle
+                        const int Jn = J0 + kWarps + warp;
+                        if (J0 + kWarps <= g0) {
+                            const int nchn = Jn < g0 ? ((J0 + kWarps) >> 3) : 0;      // not the new row: see above
+                            const double *lrown = Lb + (size_t)tri(Jn < g0 ? Jn : 0) * 64 + lane * 2;
+#pragma unroll
+                            for (int st = 0; st < kApStages - 1; ++st) {
+                                if (st < nchn) {
+                                    const uint32_t dst = ring_a + (uint32_t)(st * 4096);
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) cp_async16(dst + i * 512, lrown + (size_t)(st * 8 + i) * 64);
+                                }
+                                cp_async_commit();
+                            }
+                        }
                     }
                     // operands of the in-block terms that do not depend on this block: L_JP (old rows), W_J, A(g0,J)
                     double2 bfb[kWarps - 1];
@@ -611,21 +698,24 @@ __global__ void __launch_bounds__(kThreads, 2) rank_append_kernel(const FusedArg
                         gt0 = out[0]; gt1 = out[1];
                     }
                     for (int j = 0; j < kWarps; ++j) {
-                        if (warp == j && rowv) {
+                        // every row still open takes the X tile of step j-1 as soon as it exists (same order of terms
+                        // as a row-by-row sum, but a step's critical path is one term, not up to seven)
+                        if (j > 0 && warp >= j && rowv) {
+                            const double2 af = *reinterpret_cast<const double2 *>(s_x + (j - 1) * 64 + lane * 2);
+                            double2 bf = af;
+                            if (!last) {
 #pragma unroll
-                            for (int i = 0; i < kWarps - 1; ++i) {
-                                if (i < j) {
-                                    const double2 af = *reinterpret_cast<const double2 *>(s_x + i * 64 + lane * 2);
-                                    const double2 bf = last ? af : bfb[i];
-                                    dmma(a0, a1, af.x, bf.x);
-                                    dmma(b0, b1, af.y, bf.y);
-                                    if (last) {
-                                        const double2 zf = ldg128(zrow + (size_t)(J0 + i) * 64);
-                                        dmma(y0, y1, zf.x, bf.x);
-                                        dmma(y0, y1, zf.y, bf.y);
-                                    }
-                                }
+                                for (int i = 0; i < kWarps - 1; ++i) bf = (i == j - 1) ? bfb[i] : bf;
                             }
+                            dmma(a0, a1, af.x, bf.x);
+                            dmma(b0, b1, af.y, bf.y);
+                            if (last) {
+                                const double2 zf = ldg128(zrow + (size_t)(J0 + j - 1) * 64);
+                                dmma(y0, y1, zf.x, bf.x);
+                                dmma(y0, y1, zf.y, bf.y);
+                            }
+                        }
+                        if (warp == j && rowv) {
                             const double c0v = gt0 - (a0 + b0), c1v = gt1 - (a1 + b1);
                             if (!last) {
                                 const double2 fr = acc_to_frag(c0v, c1v, lane);
@@ -811,7 +901,8 @@ LargePlan plan_large(int q, int q_cap, int G, int ntheta_cap, int ntab_cap, int 
     pl.yrow = pl.ntp_cap;
     pl.L_stride = ((size_t)pl.ntp_cap * (pl.ntp_cap + 1) / 2 + pl.ntp_cap) * 64;
     const int Q = pl.ntp * 8;
-    size_t base = append ? (size_t)kWarps * 64 * sizeof(double) : (size_t)(36 + 36 + kBlk) * 64 * sizeof(double);
+    size_t base = append ? (size_t)(kWarps * 64 + kWarps * kApStages * 8 * 64) * sizeof(double)
+                         : (size_t)(36 + 36 + kBlk) * 64 * sizeof(double);
     size_t sz[5];
     large_aux_sizes(Q, G, ntheta_cap, ntab_cap, ncp_cap, sz);
     const size_t static_smem = 2048 + 1024;
