@@ -500,21 +500,25 @@ def main():
         # every step after the first extends the stored factors by the new block of rows (what GPModel.fit_smc does with
         # n_mcmc = 0), against re-factoring from scratch at every step
         sched = [int(round(na * (i + 1) / 20)) for i in range(20)]
-        e0.record(stream)
-        f2 = eng.factor_store_large(wa.ens, wa.t[:sched[0]], wa.y1[:sched[0]], capacity=na, g=wa.g[:sched[0]], step=wa.step, check=False)
-        prev = sched[0]
-        for c_ in sched[1:]:
-            eng.factor_append(f2, wa.t[prev:c_], wa.y1[prev:c_], g_new=wa.g[prev:c_], check=False)
-            prev = c_
-        e1.record(stream); e1.synchronize()
-        ms_sched_app = e0.elapsed_time(e1)
-        lm_app = np.array(f2.logml_n, copy=True)
-        f2.free()
-        e0.record(stream)
-        for c_ in sched:
-            eng.logml_batch(ens_a, wa.t[:c_], d_ya[:c_], g=wa.g[:c_], step=wa.step, logml=d_lma, info=d_infa)
-        e1.record(stream); e1.synchronize()
-        ms_sched_scratch = e0.elapsed_time(e1)
+        # best of three for both arms: the appended arm allocates and frees its 4.3 GB store inside the timed region and
+        # makes 20 blocking calls, so a single run moves by tens of ms with the state of the allocator and the host
+        ms_sched_app, ms_sched_scratch, lm_app = float("inf"), float("inf"), None
+        for _rep in range(3):
+            e0.record(stream)
+            f2 = eng.factor_store_large(wa.ens, wa.t[:sched[0]], wa.y1[:sched[0]], capacity=na, g=wa.g[:sched[0]], step=wa.step, check=False)
+            prev = sched[0]
+            for c_ in sched[1:]:
+                eng.factor_append(f2, wa.t[prev:c_], wa.y1[prev:c_], g_new=wa.g[prev:c_], check=False)
+                prev = c_
+            e1.record(stream); e1.synchronize()
+            ms_sched_app = min(ms_sched_app, e0.elapsed_time(e1))
+            lm_app = np.array(f2.logml_n, copy=True)
+            f2.free()
+            e0.record(stream)
+            for c_ in sched:
+                eng.logml_batch(ens_a, wa.t[:c_], d_ya[:c_], g=wa.g[:c_], step=wa.step, logml=d_lma, info=d_infa)
+            e1.record(stream); e1.synchronize()
+            ms_sched_scratch = min(ms_sched_scratch, e0.elapsed_time(e1))
         sched_rel = float(np.abs(lm_app - d_lma.cpu().numpy()).max() / np.abs(lm_app).max())
         ms_app = float(np.median(tms[1:]))
         bytes_ = Pa * 4.0 * na * (na + 1)          # the stored factor read once

@@ -1007,7 +1007,8 @@ int32_t nagp_factor_append(nagp_ctx *ctx, nagp_factor *f, int64_t k_new, const d
     NAGP_TRY(stage_out(ctx, info, (size_t)f->P, &a.info));
     double *d_dl = nullptr;
     NAGP_TRY(stage_out(ctx, dlogml, (size_t)f->P, &d_dl));
-    LargePlan pl = plan_large(n_new, (int)f->cap, a.G, f->nth_cap, a.ntab_cap, a.ncp_cap, ctx->smem_per_sm, true);
+    const bool one_tile_row = (n_new + 7) / 8 - n_old / 8 <= 1;
+    LargePlan pl = plan_large(n_new, (int)f->cap, a.G, f->nth_cap, a.ntab_cap, a.ncp_cap, ctx->smem_per_sm, true, one_tile_row);
     if (pl.L_stride != f->L_stride) return fail(ctx, NAGP_E_ARG, "nagp_factor_append: internal layout mismatch");
     const int grid = large_grid(pl, f->P, ctx->num_sms, true);
     char *scr = nullptr;

@@ -93,10 +93,14 @@ struct LargePlan {
     int aux_off[5];
     int aux_smem[5];
     int scratch_stride;
+    int ring;             // rank-append only: shared memory holds the streaming ring
     size_t smem_bytes;
 };
 int large_max_q();
-LargePlan plan_large(int q, int q_cap, int G, int ntheta_cap, int ntab_cap, int ncp_cap, int smem_per_sm, bool append);
+// ring: rank-append launches that touch a single tile row (the HBM-bound case) stream the factor through a shared-memory
+// ring; block appends keep the space for the lag / sigma tables instead.
+LargePlan plan_large(int q, int q_cap, int G, int ntheta_cap, int ntab_cap, int ncp_cap, int smem_per_sm, bool append,
+                     bool ring = false);
 int large_grid(const LargePlan &pl, int64_t B, int num_sms, bool append);
 // keep = 1: instance b's factor goes to slot b of L (and its inverse diagonal tiles to W); 0: L is a
 // per-CTA workspace of `grid` slots.

@@ -522,10 +522,14 @@ __global__ void __launch_bounds__(kThreads, 2) chol_large_kernel(const FusedArgs
 struct AppendLayout {
     LargeLayout base;
     int n_old;
+    int ring;            // 1: the launch has the streaming ring in shared memory (appends inside one tile row)
     double *logml;       // [P] in/out: running log marginal likelihood of the stored factor
     double *dlogml;      // [P] out
 };
 
+// RING: the single-tile-row sweep streams through the shared-memory ring (its own instantiation: with both stream loops in
+// one kernel the block-append path spills twice as much at the 128-register cap and a 19-append schedule ran 10 % slower).
+template <bool RING>
 __global__ void __launch_bounds__(kThreads, 2) rank_append_kernel(const FusedArgs a, const AppendLayout al)
 {
     extern __shared__ __align__(16) double smem[];
@@ -542,7 +546,8 @@ __global__ void __launch_bounds__(kThreads, 2) rank_append_kernel(const FusedArg
 
     double *s_x = smem;                                   // [8] X tiles of the current block (operand layout)
     double *s_ring = s_x + kWarps * 64;                   // [kWarps][kApStages][8 tiles] streaming ring (R == 1)
-    char *aux_s = reinterpret_cast<char *>(s_ring + kWarps * kApStages * 8 * 64);
+    constexpr bool use_ring = RING && kApStages > 0;
+    char *aux_s = reinterpret_cast<char *>(s_ring + (use_ring ? kWarps * kApStages * 8 * 64 : 0));
     const Setup su = aux_pointers(lay, aux_s);
 
     for (int i = tid; i < Q; i += kThreads) {
@@ -590,7 +595,8 @@ __global__ void __launch_bounds__(kThreads, 2) rank_append_kernel(const FusedArg
                     const double *lrow = Lb + (size_t)tri(rowv ? J : 0) * 64 + lane * 2;
                     double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;               // two chains of the row sum
                     double y0 = 0.0, y1 = 0.0;                                   // z_g0 sum (last row only)
-                    if (rowv && kApStages == 0) {
+                    if constexpr (!use_ring) {
+                      if (rowv) {
                         int P = 0;
                         for (; P + 8 <= J0; P += 8) {      // 4 KB of the stored row in flight per warp
                             double2 bf[8], af[4];
@@ -615,7 +621,8 @@ __global__ void __launch_bounds__(kThreads, 2) rank_append_kernel(const FusedArg
                                 }
                             }
                         }
-                    } else if (kApStages > 0) {
+                      }
+                    } else {
                         // The first stages of this row were issued before the previous block's triangle (below): every
                         // lane copies exactly the 16 bytes per tile it consumes, so the ring needs no barrier at all.
                         const int nch = rowv ? (J0 >> 3) : 0;          // chunks of 8 tiles: P = 8 c
@@ -891,7 +898,8 @@ void large_aux_sizes(int Q, int G, int ntheta_cap, int ntab_cap, int ncp_cap, si
 
 int large_max_q() { return 4096; }
 
-LargePlan plan_large(int q, int q_cap, int G, int ntheta_cap, int ntab_cap, int ncp_cap, int smem_per_sm, bool append)
+LargePlan plan_large(int q, int q_cap, int G, int ntheta_cap, int ntab_cap, int ncp_cap, int smem_per_sm, bool append,
+                     bool ring)
 {
     LargePlan pl{};
     pl.nt = (q + 7) / 8;
@@ -901,7 +909,8 @@ LargePlan plan_large(int q, int q_cap, int G, int ntheta_cap, int ntab_cap, int 
     pl.yrow = pl.ntp_cap;
     pl.L_stride = ((size_t)pl.ntp_cap * (pl.ntp_cap + 1) / 2 + pl.ntp_cap) * 64;
     const int Q = pl.ntp * 8;
-    size_t base = append ? (size_t)(kWarps * 64 + kWarps * kApStages * 8 * 64) * sizeof(double)
+    pl.ring = append && ring && kApStages > 0;
+    size_t base = append ? (size_t)(kWarps * 64 + (pl.ring ? kWarps * kApStages * 8 * 64 : 0)) * sizeof(double)
                          : (size_t)(36 + 36 + kBlk) * 64 * sizeof(double);
     size_t sz[5];
     large_aux_sizes(Q, G, ntheta_cap, ntab_cap, ncp_cap, sz);
@@ -937,7 +946,8 @@ static LargeLayout make_layout(const LargePlan &pl, char *scratch, double *L, in
 int large_grid(const LargePlan &pl, int64_t B, int num_sms, bool append)
 {
     int per_sm = 0;
-    const void *fn = append ? (const void *)rank_append_kernel : (const void *)chol_large_kernel;
+    const void *fn = append ? (pl.ring ? (const void *)rank_append_kernel<true> : (const void *)rank_append_kernel<false>)
+                            : (const void *)chol_large_kernel;
     cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, pl.smem_bytes) != cudaSuccess || per_sm < 1) {
         cudaGetLastError();
@@ -963,10 +973,11 @@ cudaError_t launch_rank_append(const FusedArgs &a, const LargePlan &pl, char *sc
 {
     AppendLayout al{};
     al.base = make_layout(pl, scratch, L, 1, W, nullptr);
-    al.n_old = n_old; al.logml = logml; al.dlogml = dlogml;
-    cudaError_t e = cudaFuncSetAttribute(rank_append_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
+    al.n_old = n_old; al.ring = pl.ring; al.logml = logml; al.dlogml = dlogml;
+    auto kern = pl.ring ? rank_append_kernel<true> : rank_append_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (e != cudaSuccess) return e;
-    rank_append_kernel<<<grid, kThreads, pl.smem_bytes, stream>>>(a, al);
+    kern<<<grid, kThreads, pl.smem_bytes, stream>>>(a, al);
     return cudaGetLastError();
 }
 
