@@ -108,6 +108,44 @@ def test_grad_every_route_of_the_differentiation_pass(engine, oracle_q, use_grid
         assert abs(gnz[0, p] - wnz) < 2e-6 * scale
 
 
+def test_grad_on_a_grid_with_gaps(engine, oracle_q):
+    """Missing observations: grid indices with holes (partner rows come from the inverse index map, and the moments of
+    the additive Linear / Constant leaves still use t_b = t_a - lag * step)."""
+    w = syn.make_workload(60, 0, 0, 1, 2, seed=21)
+    keep = np.sort(np.random.default_rng(3).choice(60, size=41, replace=False))
+    t, g, y = w.t[keep], w.g[keep], w.y1[keep]
+    trees = [ROUTES[0], ROUTES[1], ROUTES[2], ALL_NODES[1]]
+    noise = np.array([0.05, 0.2, 0.1, 0.07])
+    ens = kn.pack_ensemble(trees, noise)
+    lm, gth, gnz, info = engine.logml_grad(ens, t, y, g=g, step=w.step)
+    assert (info == 0).all()
+    for p, tr in enumerate(trees):
+        prog, th = kn.flatten(tr)
+        wth, wnz = fd_grad(oracle_q, prog, th, noise[p], t, y, g, w.step)
+        got = gth[0, ens.theta_off[p]:ens.theta_off[p + 1]]
+        scale = max(np.abs(wth).max(), abs(wnz), 1.0)
+        assert np.abs(got - wth).max() < 2e-6 * scale, (p, got, wth)
+        assert abs(gnz[0, p] - wnz) < 2e-6 * scale
+
+
+def test_grad_tile_kernel_agrees_with_column_kernel_at_its_largest_size(engine, grad_variant):
+    """m = 216 (27 tile rows: the last size the tile kernel takes) and m = 209 (ragged last tile): both kernels
+    differentiate the same logML."""
+    if grad_variant != 0:
+        pytest.skip("cross-check runs once")
+    for m in (216, 209):
+        w = syn.make_workload(m, 0, 0, 1, 4, seed=m)
+        engine.set_variant(0)
+        lm0, g0, n0, i0 = engine.logml_grad(w.ens, w.t[:m], w.y1, g=w.g[:m], step=w.step)
+        engine.set_variant(1)
+        lm1, g1, n1, i1 = engine.logml_grad(w.ens, w.t[:m], w.y1, g=w.g[:m], step=w.step)
+        engine.set_variant(0)
+        assert (i0 == 0).all() and (i1 == 0).all()
+        scale = max(np.abs(g1).max(), np.abs(n1).max(), 1.0)
+        assert np.abs(g0 - g1).max() < 1e-7 * scale and np.abs(n0 - n1).max() < 1e-7 * scale
+        assert np.abs(lm0 - lm1).max() < 1e-9 * np.abs(lm1).max()
+
+
 def test_grad_prior_sampled_trees_per_scenario(engine, oracle_q):
     """K scenarios with their own hyperparameters and nowcast values: the per-scenario HMC batch."""
     n, k, P, K = 40, 2, 5, 3
