@@ -1,15 +1,16 @@
 // nagp_large.cu — factorisation beyond shared-memory size (q up to 4096) and the in-place rank-append.
 //
 //  chol_large_kernel   one CTA per instance, persistent grid with a dynamic instance queue. Blocked
-//                      left-looking Cholesky by block columns of 8 tiles (64 columns): the factor lives
+//                      left-looking Cholesky by block columns of kCB = 4 tiles (32 columns): the factor lives
 //                      in HBM/L2 as 8x8 FP64 tiles in DMMA operand order (tile-packed lower triangle,
 //                      plus one tile row for z = L^-1 y), Gram tiles are evaluated on the fly by the
-//                      kernel-tree interpreter and never stored. Per block column the warps pull row
-//                      tiles from a shared queue: a row accumulates sum_P L_IP L_JP^T for all 8 column
-//                      tiles in registers (DMMA; one 16-byte fragment load per operand tile), the 8
-//                      rows of the diagonal block go to shared memory where one warp factors the 64x64
-//                      block (8x8 in-register Cholesky + inverse per tile), every other row finishes with
-//                      an in-register triangular solve against that block and writes its 8 tiles.
+//                      kernel-tree interpreter and never stored. Per block column the warps pull rows from a
+//                      shared queue: a row (two rows at a time from n = 640 up) accumulates sum_P L_IP L_JP^T
+//                      for the block's column tiles in registers (DMMA; one 16-byte fragment load per operand
+//                      tile), the rows of the diagonal block go to shared memory where one warp factors the
+//                      32x32 block (8x8 in-register Cholesky + inverse per tile) while the others run ahead,
+//                      every other row finishes with an in-register right-looking triangular solve against
+//                      that block and writes its tiles.
 //  rank_append_kernel  one CTA per particle: extends a stored factor by new rows in place (up-looking):
 //                      streams the existing L once in storage order, split-K over the warps.
 //
@@ -27,7 +28,18 @@ namespace nagp {
 
 namespace {
 
-constexpr int kBlk = 8;   // tile columns per block column
+constexpr int kBlk = 8;   // tile rows per storage block / rank-append group
+#ifndef NAGP_LARGE_CB
+#define NAGP_LARGE_CB 4     // measured (1024 x n = 512 / 256 x n = 2048, one row per warp): 8 -> 4.38 / 49.2 ms, 4 -> 4.20 / 46.1 ms
+#endif
+constexpr int kCB = NAGP_LARGE_CB;                // tile columns per block column of chol_large_kernel
+constexpr int kCBT = kCB * (kCB + 1) / 2;
+// Rows below the diagonal block that a warp sums at a time against the same panel tiles (one panel load per kRows DMMA
+// pairs; the L1 hit rate of those loads was 69 % and the L2 hit rate 53 %): a template parameter of the kernel. Two
+// rows pay from n = 768 up (512 x n = 768 / 1024 / 1536: 6.19 / 13.7 / 41.8 ms with one row, 5.79 / 12.3 / 37.1 ms with
+// two; 256 x n = 2048: 46.1 -> 43.3 ms) and cost at n = 512 (4.20 -> 4.40 ms); four rows, or two at kCB = 8, spill.
+constexpr int kRowsLargeFrom = 80;                // tile rows (n >= 640): two rows per warp
+static_assert(kBlk % kCB == 0, "block columns must tile the storage blocks");
 
 __device__ __forceinline__ double2 ldg128(const double *p)
 {
@@ -202,7 +214,7 @@ __device__ __forceinline__ int factor_diag_block(double *s_C, double *s_L, doubl
                                                  int q, int n, int m, int lane, double &ld_n, double &ld_m)
 {
     int info = 0;
-    for (int j = 0; j < kBlk; ++j) {
+    for (int j = 0; j < kCB; ++j) {
         const int Jg = c0 + j;
         double2 cj = *reinterpret_cast<double2 *>(s_C + (tri(j) + j) * 64 + lane * 2);
         double d0 = cj.x, d1 = cj.y, w0, w1, piv[8];
@@ -225,7 +237,7 @@ __device__ __forceinline__ int factor_diag_block(double *s_C, double *s_L, doubl
         __syncwarp();
         const double2 ib = *reinterpret_cast<double2 *>(s_W + j * 64 + lane * 2);
         // column trsm: X_aj = C_aj W_jj^T
-        for (int a = j + 1; a < kBlk; ++a) {
+        for (int a = j + 1; a < kCB; ++a) {
             const double2 c = *reinterpret_cast<double2 *>(s_C + (tri(a) + j) * 64 + lane * 2);
             const double2 fr = acc_to_frag(c.x, c.y, lane);
             double x0 = 0.0, x1 = 0.0;
@@ -236,7 +248,7 @@ __device__ __forceinline__ int factor_diag_block(double *s_C, double *s_L, doubl
         }
         __syncwarp();
         // trailing update inside the block: C_ab -= X_aj X_bj^T
-        for (int a = j + 1; a < kBlk; ++a) {
+        for (int a = j + 1; a < kCB; ++a) {
             double2 af = *reinterpret_cast<double2 *>(s_L + (tri(a) + j) * 64 + lane * 2);
             af.x = -af.x; af.y = -af.y;
             for (int b = j + 1; b <= a; ++b) {
@@ -253,6 +265,7 @@ __device__ __forceinline__ int factor_diag_block(double *s_C, double *s_L, doubl
     return info;
 }
 
+template <int kRows>
 __global__ void __launch_bounds__(kThreads, 2) chol_large_kernel(const FusedArgs a, const LargeLayout lay)
 {
     extern __shared__ __align__(16) double smem[];
@@ -270,10 +283,10 @@ __global__ void __launch_bounds__(kThreads, 2) chol_large_kernel(const FusedArgs
     const bool have_y2 = (a.y2 != nullptr) || k == 0;
     const int ny = have_y2 ? m : n;
 
-    double *s_C = smem;                    // 36 tiles, accumulator layout
-    double *s_L = s_C + 36 * 64;           // 36 tiles, operand layout
-    double *s_W = s_L + 36 * 64;           // 8 tiles, operand layout
-    char *aux_s = reinterpret_cast<char *>(s_W + kBlk * 64);
+    double *s_C = smem;                    // tri(kCB) tiles, accumulator layout
+    double *s_L = s_C + kCBT * 64;         // tri(kCB) tiles, operand layout
+    double *s_W = s_L + kCBT * 64;         // kCB tiles, operand layout
+    char *aux_s = reinterpret_cast<char *>(s_W + kCB * 64);
     const Setup su = aux_pointers(lay, aux_s);
 
     for (int i = tid; i < Q; i += kThreads) {
@@ -315,49 +328,72 @@ __global__ void __launch_bounds__(kThreads, 2) chol_large_kernel(const FusedArgs
         }
         gc.single_table = (tp.clen == 1 && tp.cop[0] == OP_TABLE);
 
-        const int nbc = ntp / kBlk;
+        const int nbc = ntp / kCB;
         for (int Jb = 0; Jb < nbc; ++Jb) {
-            const int c0 = Jb * kBlk;
-            const int nitems = kBlk + (ntp - c0 - kBlk) + 1;   // diagonal-block rows, rows below, the y row
+            const int c0 = Jb * kCB;
+            // items: the kCB rows of the diagonal block, the rows below in groups of kRows (a warp sums kRows rows against
+            // the same panel tiles: one operand load per kRows DMMA pairs), the y row
+            const int ngroups = (ntp - c0 - kCB) / kRows;
+            const int nitems = kCB + ngroups + 1;
             for (;;) {
                 int item = 0;
                 if (lane == 0) item = atomicAdd(&s_queue, 1);
                 item = __shfl_sync(kFull, item, 0);
                 if (item >= nitems) break;
-                const bool diag = item < kBlk;
-                const int arow = kBlk - 1 - item;                       // longest diagonal rows first
+                const bool diag = item < kCB;
+                const int arow = kCB - 1 - item;                       // longest diagonal rows first
                 const bool is_y = (item == nitems - 1);
-                const int I = diag ? c0 + arow : (is_y ? yrow : c0 + item);
-                const int NC = diag ? arow + 1 : kBlk;
+                const int I = diag ? c0 + arow : (is_y ? yrow : c0 + kCB + (item - kCB) * kRows);
+                const int NC = diag ? arow + 1 : kCB;
+                const int NR = (diag || is_y) ? 1 : kRows;              // rows I .. I + NR - 1
 
                 // ---- sum_{P < c0} L_IP L_{c0+b,P}^T for the NC column tiles ------------------------
-                double acc[kBlk][2];
+                double acc[kRows][kCB][2];
 #pragma unroll
-                for (int bb = 0; bb < kBlk; ++bb) { acc[bb][0] = 0.0; acc[bb][1] = 0.0; }
+                for (int r = 0; r < kRows; ++r)
+#pragma unroll
+                    for (int bb = 0; bb < kCB; ++bb) { acc[r][bb][0] = 0.0; acc[r][bb][1] = 0.0; }
                 {
                     const double *arowp = Lb + (size_t)tri(I) * 64 + lane * 2;
                     const double *browp = Lb + (size_t)tri(c0) * 64 + lane * 2;
-                    if (NC == kBlk) {
+                    if (NR == kRows && kRows > 1) {
+#pragma unroll 2
+                        for (int P = 0; P < c0; ++P) {
+                            double2 af[kRows];
+#pragma unroll
+                            for (int r = 0; r < kRows; ++r)      // row I + r starts r * I + tri(r) tiles after row I
+                                af[r] = ldg128_stream(arowp + ((size_t)(r * I + ((r * (r + 1)) >> 1)) + P) * 64);
+#pragma unroll
+                            for (int bb = 0; bb < kCB; ++bb) {
+                                // tile (c0+bb, P) sits tri(c0+bb) - tri(c0) = bb*c0 + tri(bb) tiles after (c0, P)
+                                const double2 bf = ldg128(browp + ((size_t)(bb * c0 + ((bb * (bb + 1)) >> 1)) + P) * 64);
+#pragma unroll
+                                for (int r = 0; r < kRows; ++r) {
+                                    dmma(acc[r][bb][0], acc[r][bb][1], af[r].x, bf.x);
+                                    dmma(acc[r][bb][0], acc[r][bb][1], af[r].y, bf.y);
+                                }
+                            }
+                        }
+                    } else if (NC == kCB) {
 #pragma unroll 2
                         for (int P = 0; P < c0; ++P) {
                             const double2 af = ldg128_stream(arowp + (size_t)P * 64);
 #pragma unroll
-                            for (int bb = 0; bb < kBlk; ++bb) {
-                                // tile (c0+bb, P) sits tri(c0+bb) - tri(c0) = bb*c0 + tri(bb) tiles after (c0, P)
+                            for (int bb = 0; bb < kCB; ++bb) {
                                 const double2 bf = ldg128(browp + ((size_t)(bb * c0 + ((bb * (bb + 1)) >> 1)) + P) * 64);
-                                dmma(acc[bb][0], acc[bb][1], af.x, bf.x);
-                                dmma(acc[bb][0], acc[bb][1], af.y, bf.y);
+                                dmma(acc[0][bb][0], acc[0][bb][1], af.x, bf.x);
+                                dmma(acc[0][bb][0], acc[0][bb][1], af.y, bf.y);
                             }
                         }
                     } else {
                         for (int P = 0; P < c0; ++P) {
                             const double2 af = ldg128(arowp + (size_t)P * 64);
 #pragma unroll
-                            for (int bb = 0; bb < kBlk; ++bb) {
+                            for (int bb = 0; bb < kCB; ++bb) {
                                 if (bb < NC) {
                                     const double2 bf = ldg128(browp + ((size_t)(bb * c0 + ((bb * (bb + 1)) >> 1)) + P) * 64);
-                                    dmma(acc[bb][0], acc[bb][1], af.x, bf.x);
-                                    dmma(acc[bb][0], acc[bb][1], af.y, bf.y);
+                                    dmma(acc[0][bb][0], acc[0][bb][1], af.x, bf.x);
+                                    dmma(acc[0][bb][0], acc[0][bb][1], af.y, bf.y);
                                 }
                             }
                         }
@@ -366,36 +402,41 @@ __global__ void __launch_bounds__(kThreads, 2) chol_large_kernel(const FusedArgs
                 // ---- C_b = A(I, c0+b) - acc_b --------------------------------------------------------
                 if (is_y) {
 #pragma unroll
-                    for (int bb = 0; bb < kBlk; ++bb) {
+                    for (int bb = 0; bb < kCB; ++bb) {
                         double y0, y1v;
                         y_tile(a, b, s, c0 + bb, ny, lane, y0, y1v);
-                        acc[bb][0] = y0 - acc[bb][0];
-                        acc[bb][1] = y1v - acc[bb][1];
+                        acc[0][bb][0] = y0 - acc[0][bb][0];
+                        acc[0][bb][1] = y1v - acc[0][bb][1];
                     }
                 } else {
 #pragma unroll
-                    for (int bb = 0; bb < kBlk; bb += 2) {
-                        if (bb < NC) {
-                            double out[4];
-                            gram_pair(tp, gc, I, c0 + bb, c0 + bb + 1, lane, out);
-                            acc[bb][0] = out[0] - acc[bb][0];
-                            acc[bb][1] = out[1] - acc[bb][1];
-                            acc[bb + 1][0] = out[2] - acc[bb + 1][0];
-                            acc[bb + 1][1] = out[3] - acc[bb + 1][1];
+                    for (int r = 0; r < kRows; ++r) {
+                        if (r < NR) {
+#pragma unroll
+                            for (int bb = 0; bb < kCB; bb += 2) {
+                                if (bb < NC) {
+                                    double out[4];
+                                    gram_pair(tp, gc, I + r, c0 + bb, c0 + bb + 1, lane, out);
+                                    acc[r][bb][0] = out[0] - acc[r][bb][0];
+                                    acc[r][bb][1] = out[1] - acc[r][bb][1];
+                                    acc[r][bb + 1][0] = out[2] - acc[r][bb + 1][0];
+                                    acc[r][bb + 1][1] = out[3] - acc[r][bb + 1][1];
+                                }
+                            }
                         }
                     }
                 }
                 if (diag) {
 #pragma unroll
-                    for (int bb = 0; bb < kBlk; ++bb)
+                    for (int bb = 0; bb < kCB; ++bb)
                         if (bb < NC)
-                            *reinterpret_cast<double2 *>(s_C + (tri(arow) + bb) * 64 + lane * 2) = make_double2(acc[bb][0], acc[bb][1]);
+                            *reinterpret_cast<double2 *>(s_C + (tri(arow) + bb) * 64 + lane * 2) = make_double2(acc[0][bb][0], acc[0][bb][1]);
                     __threadfence_block();
                     __syncwarp();
                     int done = 0;
                     if (lane == 0) done = atomicAdd(&s_diagdone, 1);
                     done = __shfl_sync(kFull, done, 0);
-                    if (done == kBlk - 1) {
+                    if (done == kCB - 1) {
                         // last diagonal row in: this warp factors the block while the others run ahead
                         __threadfence_block();
                         double ld_n = 0.0, ld_m = 0.0;
@@ -414,24 +455,29 @@ __global__ void __launch_bounds__(kThreads, 2) chol_large_kernel(const FusedArgs
                 while (s_flag < Jb + 1) __nanosleep(64);
                 __threadfence_block();
                 __syncwarp();
-                double2 xa[kBlk];
+                // right-looking: a solved tile goes into every column tile still open at once (independent DMMA chains, same
+                // order of terms per tile as a left-looking sum); the rows of a group are independent chains too
 #pragma unroll
-                for (int bb = 0; bb < kBlk; ++bb) {
+                for (int aa = 0; aa < kCB; ++aa) {
+                    const double2 ib = *reinterpret_cast<const double2 *>(s_W + aa * 64 + lane * 2);
 #pragma unroll
-                    for (int aa = 0; aa < bb; ++aa) {
-                        const double2 bf = *reinterpret_cast<const double2 *>(s_L + (tri(bb) + aa) * 64 + lane * 2);
-                        dmma(acc[bb][0], acc[bb][1], xa[aa].x, bf.x);
-                        dmma(acc[bb][0], acc[bb][1], xa[aa].y, bf.y);
-                    }
-                    const double2 fr = acc_to_frag(acc[bb][0], acc[bb][1], lane);
-                    const double2 ib = *reinterpret_cast<const double2 *>(s_W + bb * 64 + lane * 2);
-                    double x0 = 0.0, x1 = 0.0;
-                    dmma(x0, x1, fr.x, ib.x);
-                    dmma(x0, x1, fr.y, ib.y);
-                    store_op(Lb + ((size_t)tri(I) + c0 + bb) * 64, x0, x1, lane);
-                    if (bb + 1 < kBlk) {
-                        const double2 xf = acc_to_frag(x0, x1, lane);
-                        xa[bb] = make_double2(-xf.x, -xf.y);
+                    for (int r = 0; r < kRows; ++r) {
+                        if (r < NR) {
+                            const double2 fr = acc_to_frag(acc[r][aa][0], acc[r][aa][1], lane);
+                            double x0 = 0.0, x1 = 0.0;
+                            dmma(x0, x1, fr.x, ib.x);
+                            dmma(x0, x1, fr.y, ib.y);
+                            store_op(Lb + ((size_t)tri(I + r) + c0 + aa) * 64, x0, x1, lane);
+                            if (aa + 1 < kCB) {
+                                const double2 xf = acc_to_frag(x0, x1, lane);
+#pragma unroll
+                                for (int bb = aa + 1; bb < kCB; ++bb) {
+                                    const double2 bf = *reinterpret_cast<const double2 *>(s_L + (tri(bb) + aa) * 64 + lane * 2);
+                                    dmma(acc[r][bb][0], acc[r][bb][1], -xf.x, bf.x);
+                                    dmma(acc[r][bb][0], acc[r][bb][1], -xf.y, bf.y);
+                                }
+                            }
+                        }
                     }
                 }
             }
@@ -911,7 +957,7 @@ LargePlan plan_large(int q, int q_cap, int G, int ntheta_cap, int ntab_cap, int 
     const int Q = pl.ntp * 8;
     pl.ring = append && ring && kApStages > 0;
     size_t base = append ? (size_t)(kWarps * 64 + (pl.ring ? kWarps * kApStages * 8 * 64 : 0)) * sizeof(double)
-                         : (size_t)(36 + 36 + kBlk) * 64 * sizeof(double);
+                         : (size_t)(2 * kCBT + kCB) * 64 * sizeof(double);
     size_t sz[5];
     large_aux_sizes(Q, G, ntheta_cap, ntab_cap, ncp_cap, sz);
     const size_t static_smem = 2048 + 1024;
@@ -947,7 +993,7 @@ int large_grid(const LargePlan &pl, int64_t B, int num_sms, bool append)
 {
     int per_sm = 0;
     const void *fn = append ? (pl.ring ? (const void *)rank_append_kernel<true> : (const void *)rank_append_kernel<false>)
-                            : (const void *)chol_large_kernel;
+                            : (pl.nt >= kRowsLargeFrom ? (const void *)chol_large_kernel<2> : (const void *)chol_large_kernel<1>);
     cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, pl.smem_bytes) != cudaSuccess || per_sm < 1) {
         cudaGetLastError();
@@ -962,9 +1008,10 @@ cudaError_t launch_chol_large(const FusedArgs &a, const LargePlan &pl, char *scr
     cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
     LargeLayout lay = make_layout(pl, scratch, L, keep, W, work_counter);
-    e = cudaFuncSetAttribute(chol_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
+    auto kern = pl.nt >= kRowsLargeFrom ? chol_large_kernel<2> : chol_large_kernel<1>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (e != cudaSuccess) return e;
-    chol_large_kernel<<<grid, kThreads, pl.smem_bytes, stream>>>(a, lay);
+    kern<<<grid, kThreads, pl.smem_bytes, stream>>>(a, lay);
     return cudaGetLastError();
 }
 
