@@ -24,6 +24,19 @@
 #include "nagp_tree.cuh"
 #include "nagp_tile.cuh"
 
+#ifndef NAGP_LARGE_TRACE
+#define NAGP_LARGE_TRACE 0  // n: clock64 stamps of the n-th instance of block 0 for tools/large_timeline.py; 0 in product builds
+#endif
+#if NAGP_LARGE_TRACE
+// [block column][warp][arrival at the end, cycles waited for the diagonal block, row groups solved, -], then
+// [block column][start, diagonal block begins, ends, -]
+__device__ long long g_large_trace[128 * 8 * 4 + 128 * 4];
+extern "C" int nagp_debug_read_large(long long *out, int count)
+{
+    return (int)cudaMemcpyFromSymbol(out, g_large_trace, sizeof(long long) * count);
+}
+#endif
+
 namespace nagp {
 
 namespace {
@@ -38,6 +51,10 @@ constexpr int kCBT = kCB * (kCB + 1) / 2;
 // pairs; the L1 hit rate of those loads was 69 % and the L2 hit rate 53 %): a template parameter of the kernel. Two
 // rows pay from n = 768 up (512 x n = 768 / 1024 / 1536: 6.19 / 13.7 / 41.8 ms with one row, 5.79 / 12.3 / 37.1 ms with
 // two; 256 x n = 2048: 46.1 -> 43.3 ms) and cost at n = 512 (4.20 -> 4.40 ms); four rows, or two at kCB = 8, spill.
+#ifndef NAGP_LARGE_DIAG_UNROLL
+#define NAGP_LARGE_DIAG_UNROLL 4
+#endif
+constexpr int kDiagUnroll = NAGP_LARGE_DIAG_UNROLL;
 constexpr int kRowsLargeFrom = 80;                // tile rows (n >= 640): two rows per warp
 static_assert(kBlk % kCB == 0, "block columns must tile the storage blocks");
 
@@ -211,7 +228,7 @@ __device__ __forceinline__ void y_tile(const FusedArgs &a, int64_t b, int64_t s,
 // right-looking over its 8 tile columns. Writes L tiles (operand layout) to s_L and to the factor, inverse
 // diagonal tiles to s_W (and the factor's W store). Returns 0 or the 1-based index of the first bad pivot.
 __device__ __forceinline__ int factor_diag_block(double *s_C, double *s_L, double *s_W, double *Lb, double *Wb, int c0,
-                                                 int q, int n, int m, int lane, double &ld_n, double &ld_m)
+                                                 int q, int lane)
 {
     int info = 0;
     for (int j = 0; j < kCB; ++j) {
@@ -220,15 +237,6 @@ __device__ __forceinline__ int factor_diag_block(double *s_C, double *s_L, doubl
         double d0 = cj.x, d1 = cj.y, w0, w1, piv[8];
         const int bad = chol8_inv(d0, d1, w0, w1, lane, q - Jg * 8, piv);
         if (bad && !info) info = Jg * 8 + bad;
-#pragma unroll
-        for (int p = 0; p < 8; ++p) {
-            const int row = Jg * 8 + p;
-            if (row < m) {
-                const double l = 0.5 * log(piv[p]);
-                ld_m += l;
-                if (row < n) ld_n += l;
-            }
-        }
         double *ltile = s_L + (tri(j) + j) * 64;
         store_op(ltile, d0, d1, lane);
         store_op(Lb + ((size_t)tri(Jg) + Jg) * 64, d0, d1, lane);
@@ -274,7 +282,6 @@ __global__ void __launch_bounds__(kThreads, 2) chol_large_kernel(const FusedArgs
     __shared__ long long s_next;
     __shared__ int s_queue, s_diagdone;
     __shared__ volatile int s_flag;
-    __shared__ double s_ld[2];
     __shared__ double s_red[4][kWarps];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -294,6 +301,9 @@ __global__ void __launch_bounds__(kThreads, 2) chol_large_kernel(const FusedArgs
         su.gg[i] = (a.g && i < q) ? a.g[i] : 0;
     }
 
+#if NAGP_LARGE_TRACE
+    int n_inst = 0;
+#endif
     for (;;) {
         __syncthreads();
         if (tid == 0) s_next = (long long)atomicAdd(lay.work_counter, 1ull);
@@ -306,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, 2) chol_large_kernel(const FusedArgs
         double *Lb = lay.L + slot * lay.L_stride;
         double *Wb = lay.W ? lay.W + slot * lay.W_stride : nullptr;
 
-        if (tid == 0) { s_info = 0; s_flag = 0; s_queue = 0; s_diagdone = 0; s_ld[0] = 0.0; s_ld[1] = 0.0; }
+        if (tid == 0) { s_info = 0; s_flag = 0; s_queue = 0; s_diagdone = 0; }
         instance_setup(tp, a, su, s, p, Q, tid);
         if (tp.error) {
             if (tid == 0) {
@@ -329,8 +339,15 @@ __global__ void __launch_bounds__(kThreads, 2) chol_large_kernel(const FusedArgs
         gc.single_table = (tp.clen == 1 && tp.cop[0] == OP_TABLE);
 
         const int nbc = ntp / kCB;
+#if NAGP_LARGE_TRACE
+        const bool tracing = (blockIdx.x == 0 && ++n_inst == NAGP_LARGE_TRACE && nbc <= 128);
+#endif
         for (int Jb = 0; Jb < nbc; ++Jb) {
             const int c0 = Jb * kCB;
+#if NAGP_LARGE_TRACE
+            long long waited = 0; int items_done = 0;
+            if (tracing && tid == 0) g_large_trace[128 * 8 * 4 + Jb * 4] = clock64();
+#endif
             // items: the kCB rows of the diagonal block, the rows below in groups of kRows (a warp sums kRows rows against
             // the same panel tiles: one operand load per kRows DMMA pairs), the y row
             const int ngroups = (ntp - c0 - kCB) / kRows;
@@ -386,8 +403,11 @@ __global__ void __launch_bounds__(kThreads, 2) chol_large_kernel(const FusedArgs
                             }
                         }
                     } else {
+                        // the rows of the diagonal block: everything else ends up waiting for them (and for the
+                        // factorisation that follows), so their operand loads are issued four terms ahead
+#pragma unroll kDiagUnroll
                         for (int P = 0; P < c0; ++P) {
-                            const double2 af = ldg128(arowp + (size_t)P * 64);
+                            const double2 af = ldg128_stream(arowp + (size_t)P * 64);
 #pragma unroll
                             for (int bb = 0; bb < kCB; ++bb) {
                                 if (bb < NC) {
@@ -439,12 +459,14 @@ __global__ void __launch_bounds__(kThreads, 2) chol_large_kernel(const FusedArgs
                     if (done == kCB - 1) {
                         // last diagonal row in: this warp factors the block while the others run ahead
                         __threadfence_block();
-                        double ld_n = 0.0, ld_m = 0.0;
-                        const int bad = factor_diag_block(s_C, s_L, s_W, Lb, Wb, c0, q, n, m, lane, ld_n, ld_m);
-                        if (lane == 0) {
-                            if (bad && !s_info) s_info = bad;
-                            s_ld[0] += ld_n; s_ld[1] += ld_m;
-                        }
+#if NAGP_LARGE_TRACE
+                        if (tracing && lane == 0) g_large_trace[128 * 8 * 4 + Jb * 4 + 1] = clock64();
+#endif
+                        const int bad = factor_diag_block(s_C, s_L, s_W, Lb, Wb, c0, q, lane);
+#if NAGP_LARGE_TRACE
+                        if (tracing && lane == 0) g_large_trace[128 * 8 * 4 + Jb * 4 + 2] = clock64();
+#endif
+                        if (lane == 0 && bad && !s_info) s_info = bad;
                         __threadfence_block();
                         __syncwarp();
                         if (lane == 0) s_flag = Jb + 1;
@@ -452,7 +474,13 @@ __global__ void __launch_bounds__(kThreads, 2) chol_large_kernel(const FusedArgs
                     continue;
                 }
                 // ---- wait for the diagonal block, then the in-register triangular solve -------------------
+#if NAGP_LARGE_TRACE
+                const long long tw0 = clock64();
+#endif
                 while (s_flag < Jb + 1) __nanosleep(64);
+#if NAGP_LARGE_TRACE
+                waited += clock64() - tw0; ++items_done;
+#endif
                 __threadfence_block();
                 __syncwarp();
                 // right-looking: a solved tile goes into every column tile still open at once (independent DMMA chains, same
@@ -481,6 +509,12 @@ __global__ void __launch_bounds__(kThreads, 2) chol_large_kernel(const FusedArgs
                     }
                 }
             }
+#if NAGP_LARGE_TRACE
+            if (tracing && lane == 0) {
+                long long *tr = g_large_trace + (Jb * 8 + warp) * 4;
+                tr[0] = clock64(); tr[1] = waited; tr[2] = items_done;
+            }
+#endif
             __syncthreads();
             if (tid == 0) { s_queue = 0; s_diagdone = 0; }
             __syncthreads();
@@ -503,21 +537,28 @@ __global__ void __launch_bounds__(kThreads, 2) chol_large_kernel(const FusedArgs
         auto zel = [&](int r) { return Lb[((size_t)tri(yrow) + (r >> 3)) * 64 + op_idx(0, r & 7)]; };
 
         // ---- logML(n), logML(m) ----------------------------------------------------------------------
-        double qd_n = 0, qd_m = 0;
-        for (int r = tid; r < ny; r += kThreads) {
-            const double zz = zel(r);
-            qd_m = fma(zz, zz, qd_m);
-            if (r < n) qd_n = fma(zz, zz, qd_n);
+        // (the logs of the diagonal are taken here by all threads: inside the one-warp factorisation of the diagonal block
+        // the other warps were waiting for them)
+        double qd_n = 0, qd_m = 0, ld_n = 0, ld_m = 0;
+        for (int r = tid; r < m; r += kThreads) {
+            const double l = log(Lel(r, r));
+            ld_m += l;
+            if (r < n) ld_n += l;
+            if (r < ny) {
+                const double zz = zel(r);
+                qd_m = fma(zz, zz, qd_m);
+                if (r < n) qd_n = fma(zz, zz, qd_n);
+            }
         }
-        qd_n = warp_sum(qd_n); qd_m = warp_sum(qd_m);
-        if (lane == 0) { s_red[0][warp] = qd_n; s_red[1][warp] = qd_m; }
+        qd_n = warp_sum(qd_n); qd_m = warp_sum(qd_m); ld_n = warp_sum(ld_n); ld_m = warp_sum(ld_m);
+        if (lane == 0) { s_red[0][warp] = qd_n; s_red[1][warp] = qd_m; s_red[2][warp] = ld_n; s_red[3][warp] = ld_m; }
         __syncthreads();
         if (tid == 0) {
-            double r2 = 0, r3 = 0;
-            for (int w = 0; w < kWarps; ++w) { r2 += s_red[0][w]; r3 += s_red[1][w]; }
+            double r2 = 0, r3 = 0, l0 = 0, l1 = 0;
+            for (int w = 0; w < kWarps; ++w) { r2 += s_red[0][w]; r3 += s_red[1][w]; l0 += s_red[2][w]; l1 += s_red[3][w]; }
             const double log2pi = 1.8378770664093454835606594728112;
-            double lmn = -0.5 * ((double)n * log2pi + 2.0 * s_ld[0] + r2);
-            double lmm = have_y2 ? -0.5 * ((double)m * log2pi + 2.0 * s_ld[1] + r3) : nan("");
+            double lmn = -0.5 * ((double)n * log2pi + 2.0 * l0 + r2);
+            double lmm = have_y2 ? -0.5 * ((double)m * log2pi + 2.0 * l1 + r3) : nan("");
             if (a.logml_n) a.logml_n[b] = lmn;
             if (a.logml_m) a.logml_m[b] = lmm;
             if (a.logw) a.logw[b] = (a.logw0 ? a.logw0[p] : 0.0) + (lmm - lmn);

@@ -10,14 +10,14 @@ w = syn.make_workload(n, 0, 0, 1, B, seed=20261018 + 3, max_depth=4, period=365.
 eng = Engine(0)
 for i in range(2):
     eng.logml_batch(w.ens, w.t[:n], w.y1, g=w.g[:n], step=w.step)
-N = 64 * 8 * 4 + 64 * 4
+N = 128 * 8 * 4 + 128 * 4
 buf = (C.c_longlong * N)()
 eng._lib.nagp_debug_read_large.argtypes = [C.c_void_p, C.c_int]
 assert eng._lib.nagp_debug_read_large(buf, N) == 0
-wt = np.array(buf[:64 * 32]).reshape(64, 8, 4)
-bc = np.array(buf[64 * 32:]).reshape(64, 4)
-nbc = (n + 63) // 64
-print("block col | length | diag block: starts after, takes | per warp: [busy until, waited for the diagonal block, rows solved]")
+wt = np.array(buf[:128 * 32]).reshape(128, 8, 4)
+bc = np.array(buf[128 * 32:]).reshape(128, 4)
+nbc = ((n + 63) // 64) * 2          # block columns of 4 tiles
+print("block col | length | diag block: starts after, takes | per warp: [busy until, waited for the diagonal block, row groups solved]")
 for J in range(nbc):
     t0 = bc[J, 0]
     end = wt[J, :, 0].max()
