@@ -55,6 +55,8 @@ constexpr int kCBT = kCB * (kCB + 1) / 2;
 #define NAGP_LARGE_DIAG_UNROLL 4
 #endif
 constexpr int kDiagUnroll = NAGP_LARGE_DIAG_UNROLL;
+// unroll depth of the accumulate loops (terms whose operand loads are issued together): measured 1024 x n = 512 /
+// 512 x n = 1024 / 256 x n = 2048 at depth 2: 3.79 / 11.7 / 37.0 ms, 3: 3.73 / 12.2 / 45.1, 4: 3.71 / 11.5 / 40.0
 constexpr int kRowsLargeFrom = 80;                // tile rows (n >= 640): two rows per warp
 static_assert(kBlk % kCB == 0, "block columns must tile the storage blocks");
 
@@ -392,7 +394,7 @@ __global__ void __launch_bounds__(kThreads, 2) chol_large_kernel(const FusedArgs
                             }
                         }
                     } else if (NC == kCB) {
-#pragma unroll 2
+#pragma unroll 4
                         for (int P = 0; P < c0; ++P) {
                             const double2 af = ldg128_stream(arowp + (size_t)P * 64);
 #pragma unroll
