@@ -59,6 +59,7 @@ constexpr int kDiagUnroll = NAGP_LARGE_DIAG_UNROLL;
 // 512 x n = 1024 / 256 x n = 2048 at depth 2: 3.79 / 11.7 / 37.0 ms, 3: 3.73 / 12.2 / 45.1, 4: 3.71 / 11.5 / 40.0
 constexpr int kRowsLargeFrom = 80;                // tile rows (n >= 640): two rows per warp
 static_assert(kBlk % kCB == 0, "block columns must tile the storage blocks");
+static_assert(kWarps == 2 * kCB, "the rows of a diagonal block are summed by two warps each");
 
 __device__ __forceinline__ double2 ldg128(const double *p)
 {
@@ -295,7 +296,8 @@ __global__ void __launch_bounds__(kThreads, 2) chol_large_kernel(const FusedArgs
     double *s_C = smem;                    // tri(kCB) tiles, accumulator layout
     double *s_L = s_C + kCBT * 64;         // tri(kCB) tiles, operand layout
     double *s_W = s_L + kCBT * 64;         // kCB tiles, operand layout
-    char *aux_s = reinterpret_cast<char *>(s_W + kCB * 64);
+    double *s_P = s_W + kCB * 64;          // tri(kCB) tiles: partial sums of the diagonal block's rows (second half of the terms)
+    char *aux_s = reinterpret_cast<char *>(s_P + kCBT * 64);
     const Setup su = aux_pointers(lay, aux_s);
 
     for (int i = tid; i < Q; i += kThreads) {
@@ -354,11 +356,21 @@ __global__ void __launch_bounds__(kThreads, 2) chol_large_kernel(const FusedArgs
             // the same panel tiles: one operand load per kRows DMMA pairs), the y row
             const int ngroups = (ntp - c0 - kCB) / kRows;
             const int nitems = kCB + ngroups + 1;
+            // The rows of the diagonal block come first and on all eight warps (each row's sum split in two): everything
+            // else ends up waiting for them and for the factorisation that follows, and warps that stream rows below at the
+            // same time take three quarters of the FP64 tensor pipe away from them (trace: 52 terms at 780 cycles each).
+            bool diag_phase = true;
             for (;;) {
-                int item = 0;
-                if (lane == 0) item = atomicAdd(&s_queue, 1);
-                item = __shfl_sync(kFull, item, 0);
-                if (item >= nitems) break;
+                int item = kCB - 1 - (warp % kCB), Plo = 0, Phi = c0;
+                const int half = diag_phase ? warp / kCB : 0;
+                if (diag_phase) {
+                    const int mid = c0 >> 1;
+                    Plo = half ? mid : 0; Phi = half ? c0 : mid;
+                } else {
+                    if (lane == 0) item = kCB + atomicAdd(&s_queue, 1);
+                    item = __shfl_sync(kFull, item, 0);
+                    if (item >= nitems) break;
+                }
                 const bool diag = item < kCB;
                 const int arow = kCB - 1 - item;                       // longest diagonal rows first
                 const bool is_y = (item == nitems - 1);
@@ -377,7 +389,7 @@ __global__ void __launch_bounds__(kThreads, 2) chol_large_kernel(const FusedArgs
                     const double *browp = Lb + (size_t)tri(c0) * 64 + lane * 2;
                     if (NR == kRows && kRows > 1) {
 #pragma unroll 2
-                        for (int P = 0; P < c0; ++P) {
+                        for (int P = Plo; P < Phi; ++P) {
                             double2 af[kRows];
 #pragma unroll
                             for (int r = 0; r < kRows; ++r)      // row I + r starts r * I + tri(r) tiles after row I
@@ -395,7 +407,7 @@ __global__ void __launch_bounds__(kThreads, 2) chol_large_kernel(const FusedArgs
                         }
                     } else if (NC == kCB) {
 #pragma unroll 4
-                        for (int P = 0; P < c0; ++P) {
+                        for (int P = Plo; P < Phi; ++P) {
                             const double2 af = ldg128_stream(arowp + (size_t)P * 64);
 #pragma unroll
                             for (int bb = 0; bb < kCB; ++bb) {
@@ -408,7 +420,7 @@ __global__ void __launch_bounds__(kThreads, 2) chol_large_kernel(const FusedArgs
                         // the rows of the diagonal block: everything else ends up waiting for them (and for the
                         // factorisation that follows), so their operand loads are issued four terms ahead
 #pragma unroll kDiagUnroll
-                        for (int P = 0; P < c0; ++P) {
+                        for (int P = Plo; P < Phi; ++P) {
                             const double2 af = ldg128_stream(arowp + (size_t)P * 64);
 #pragma unroll
                             for (int bb = 0; bb < kCB; ++bb) {
@@ -430,6 +442,9 @@ __global__ void __launch_bounds__(kThreads, 2) chol_large_kernel(const FusedArgs
                         acc[0][bb][0] = y0 - acc[0][bb][0];
                         acc[0][bb][1] = y1v - acc[0][bb][1];
                     }
+                } else if (diag && half) {
+#pragma unroll
+                    for (int bb = 0; bb < kCB; ++bb) { acc[0][bb][0] = -acc[0][bb][0]; acc[0][bb][1] = -acc[0][bb][1]; }
                 } else {
 #pragma unroll
                     for (int r = 0; r < kRows; ++r) {
@@ -449,6 +464,24 @@ __global__ void __launch_bounds__(kThreads, 2) chol_large_kernel(const FusedArgs
                     }
                 }
                 if (diag) {
+                    // acc holds A - (first half of the terms) on the warps with half == 0 and -(second half) on the others
+                    if (half) {
+#pragma unroll
+                        for (int bb = 0; bb < kCB; ++bb)
+                            if (bb < NC)
+                                *reinterpret_cast<double2 *>(s_P + (tri(arow) + bb) * 64 + lane * 2) = make_double2(acc[0][bb][0], acc[0][bb][1]);
+                    }
+                    __syncthreads();
+                    diag_phase = false;
+                    if (half) continue;
+#pragma unroll
+                    for (int bb = 0; bb < kCB; ++bb) {
+                        if (bb < NC) {
+                            const double2 pp = *reinterpret_cast<const double2 *>(s_P + (tri(arow) + bb) * 64 + lane * 2);
+                            acc[0][bb][0] += pp.x;
+                            acc[0][bb][1] += pp.y;
+                        }
+                    }
 #pragma unroll
                     for (int bb = 0; bb < kCB; ++bb)
                         if (bb < NC)
@@ -1000,7 +1033,7 @@ LargePlan plan_large(int q, int q_cap, int G, int ntheta_cap, int ntab_cap, int 
     const int Q = pl.ntp * 8;
     pl.ring = append && ring && kApStages > 0;
     size_t base = append ? (size_t)(kWarps * 64 + (pl.ring ? kWarps * kApStages * 8 * 64 : 0)) * sizeof(double)
-                         : (size_t)(2 * kCBT + kCB) * 64 * sizeof(double);
+                         : (size_t)(3 * kCBT + kCB) * 64 * sizeof(double);
     size_t sz[5];
     large_aux_sizes(Q, G, ntheta_cap, ntab_cap, ncp_cap, sz);
     const size_t static_smem = 2048 + 1024;
