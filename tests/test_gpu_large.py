@@ -16,7 +16,7 @@ def rel(a, b):
 
 
 @pytest.mark.parametrize("use_grid", [False, True])
-@pytest.mark.parametrize("n,P", [(233, 5), (256, 3), (300, 6), (512, 4), (777, 2)])
+@pytest.mark.parametrize("n,P", [(233, 5), (256, 3), (300, 6), (512, 4), (631, 2), (633, 2), (777, 2)])   # 80 tile rows: two rows per warp
 def test_large_logml_matches_oracle(engine, oracle, n, P, use_grid):
     w = syn.make_workload(n, 0, 0, 1, P, seed=900 + n)
     g = w.g[:n] if use_grid else None
@@ -39,9 +39,10 @@ def test_large_many_instances_dynamic_queue(engine, oracle):
     assert rel(got, np.tile(want, P // 7)) < RTOL
 
 
+@pytest.mark.parametrize("n", [400, 700])      # one / two rows per warp below the diagonal block
 @pytest.mark.parametrize("use_grid", [False, True])
-def test_large_forecast_instances_match_oracle(engine, oracle, use_grid):
-    n, k, h, P, K = 400, 2, 6, 3, 2
+def test_large_forecast_instances_match_oracle(engine, oracle, use_grid, n):
+    k, h, P, K = 2, 6, 3, 2
     w = syn.make_workload(n, k, h, K, P, seed=41)
     g = w.g if use_grid else None
     r = engine.forecast_instances(w.ens, n, k, h, w.t, w.y1, w.y2, w.logw0, w.ya, w.yb, g=g, step=w.step)
