@@ -5,7 +5,7 @@
 //                      in HBM/L2 as 8x8 FP64 tiles in DMMA operand order (tile-packed lower triangle,
 //                      plus one tile row for z = L^-1 y), Gram tiles are evaluated on the fly by the
 //                      kernel-tree interpreter and never stored. Per block column the warps pull rows from a
-//                      shared queue: a row (two rows at a time from n = 640 up) accumulates sum_P L_IP L_JP^T
+//                      shared queue: a row (two rows at a time from n = 768 up) accumulates sum_P L_IP L_JP^T
 //                      for the block's column tiles in registers (DMMA; one 16-byte fragment load per operand
 //                      tile), the rows of the diagonal block go to shared memory where one warp factors the
 //                      32x32 block (8x8 in-register Cholesky + inverse per tile) while the others run ahead,
@@ -57,7 +57,10 @@ constexpr int kCBT = kCB * (kCB + 1) / 2;
 constexpr int kDiagUnroll = NAGP_LARGE_DIAG_UNROLL;
 // unroll depth of the accumulate loops (terms whose operand loads are issued together): measured 1024 x n = 512 /
 // 512 x n = 1024 / 256 x n = 2048 at depth 2: 3.79 / 11.7 / 37.0 ms, 3: 3.73 / 12.2 / 45.1, 4: 3.71 / 11.5 / 40.0
-constexpr int kRowsLargeFrom = 80;                // tile rows (n >= 640): two rows per warp
+#ifndef NAGP_LARGE_ROWS_FROM
+#define NAGP_LARGE_ROWS_FROM 96     // tile rows (n >= 768); final build, one / two rows: n = 512 3.59 / 3.74 ms, 640: 3.54 / 3.67, 768: 5.42 / 5.40, 1024: 12.7 / 11.6, 2048: 44.4 / 39.0
+#endif
+constexpr int kRowsLargeFrom = NAGP_LARGE_ROWS_FROM;                // tile rows (n >= 640): two rows per warp
 static_assert(kBlk % kCB == 0, "block columns must tile the storage blocks");
 static_assert(kWarps == 2 * kCB, "the rows of a diagonal block are summed by two warps each");
 

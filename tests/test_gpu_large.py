@@ -16,7 +16,7 @@ def rel(a, b):
 
 
 @pytest.mark.parametrize("use_grid", [False, True])
-@pytest.mark.parametrize("n,P", [(233, 5), (256, 3), (300, 6), (512, 4), (631, 2), (633, 2), (777, 2)])   # 80 tile rows: two rows per warp
+@pytest.mark.parametrize("n,P", [(233, 5), (256, 3), (300, 6), (512, 4), (631, 2), (759, 2), (761, 2), (900, 2)])   # from 96 tile rows: two rows per warp
 def test_large_logml_matches_oracle(engine, oracle, n, P, use_grid):
     w = syn.make_workload(n, 0, 0, 1, P, seed=900 + n)
     g = w.g[:n] if use_grid else None
@@ -39,7 +39,7 @@ def test_large_many_instances_dynamic_queue(engine, oracle):
     assert rel(got, np.tile(want, P // 7)) < RTOL
 
 
-@pytest.mark.parametrize("n", [400, 700])      # one / two rows per warp below the diagonal block
+@pytest.mark.parametrize("n", [400, 800])      # one / two rows per warp below the diagonal block
 @pytest.mark.parametrize("use_grid", [False, True])
 def test_large_forecast_instances_match_oracle(engine, oracle, use_grid, n):
     k, h, P, K = 2, 6, 3, 2
