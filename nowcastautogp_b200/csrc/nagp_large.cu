@@ -931,19 +931,43 @@ __global__ void __launch_bounds__(kThreads, 2) rank_append_kernel(const FusedArg
                     }
                     for (; P < J0; ++P) terms(P, ldg128_stream(lrow + (size_t)P * 64));
                 }
-                // ---- the 8 x 8-tile triangle of this block: row J0+j needs the tiles finished by rows < J0+j --
+                // ---- everything of the block that depends on nobody else, in parallel on the eight warps: the Gram tiles
+                // (and y) of every open row against column J, turned into C = A - sum at once. (They used to be evaluated
+                // inside the row's turn of the triangle below, i.e. by one warp at a time with seven waiting: up to eight
+                // interpreter passes per turn.)
+                const int r_d = J - g0;                 // J is itself a new row: its diagonal tile is slot r_d
+                if (rowv) {
+#pragma unroll
+                    for (int r = 0; r <= kBlk; ++r) {
+                        const bool isy = (r == kBlk);
+                        const bool open = isy ? y_on : (r < R && g0 + r >= J);      // rows below J, and J's own diagonal tile
+                        if (!open) continue;
+                        double g0v, g1v;
+                        if (isy) {
+                            y_tile(a, 0, 0, J, n, lane, g0v, g1v);
+                        } else {
+                            double out[4];
+                            gram_pair(tp, gc, g0 + r, J, J, lane, out);
+                            g0v = out[0]; g1v = out[1];
+                        }
+                        acc[r][0] = g0v - acc[r][0];
+                        acc[r][1] = g1v - acc[r][1];
+                    }
+                }
+                // ---- the 8 x 8-tile triangle of this block: row J0+j needs the tiles finished by rows < J0+j; every row
+                // still open takes the tiles of step j-1 as soon as they exist, so a turn is one term and the solves
                 for (int j = 0; j < kWarps; ++j) {
+                    if (j > 0 && warp >= j && rowv) {
+                        const double2 bf = ldg128(lrow + (size_t)(J0 + j - 1) * 64);
+                        terms(J0 + j - 1, make_double2(-bf.x, -bf.y));
+                    }
                     if (warp == j && rowv) {
-                        for (int P = J0; P < J; ++P) terms(P, ldg128(lrow + (size_t)P * 64));
                         double2 ib;
                         if (J >= g0) {
                             // J is a new row: its diagonal tile (new row r = J - g0)
-                            double s0 = 0.0, s1 = 0.0;
+                            double d0 = 0.0, d1 = 0.0, w0, w1, piv[8];
 #pragma unroll
-                            for (int r = 0; r < kBlk; ++r) if (r == J - g0) { s0 = acc[r][0]; s1 = acc[r][1]; }
-                            double out[4];
-                            gram_pair(tp, gc, J, J, J, lane, out);
-                            double d0 = out[0] - s0, d1 = out[1] - s1, w0, w1, piv[8];
+                            for (int r = 0; r < kBlk; ++r) if (r == r_d) { d0 = acc[r][0]; d1 = acc[r][1]; }
                             const int bad = chol8_inv(d0, d1, w0, w1, lane, q - J * 8, piv);
                             if (bad && lane == 0 && !s_info) s_info = J * 8 + bad;
                             double ld = 0.0;
@@ -962,15 +986,7 @@ __global__ void __launch_bounds__(kThreads, 2) rank_append_kernel(const FusedArg
                         for (int r = 0; r <= kBlk; ++r) {
                             const bool isy = (r == kBlk);
                             if (isy ? !y_on : !(r < R && g0 + r > J)) continue;
-                            double g0v, g1v;
-                            if (isy) {
-                                y_tile(a, 0, 0, J, n, lane, g0v, g1v);
-                            } else {
-                                double out[4];
-                                gram_pair(tp, gc, g0 + r, J, J, lane, out);
-                                g0v = out[0]; g1v = out[1];
-                            }
-                            const double2 fr = acc_to_frag(g0v - acc[r][0], g1v - acc[r][1], lane);
+                            const double2 fr = acc_to_frag(acc[r][0], acc[r][1], lane);
                             double x0 = 0.0, x1 = 0.0;
                             dmma(x0, x1, fr.x, ib.x);
                             dmma(x0, x1, fr.y, ib.y);
