@@ -670,9 +670,10 @@ __global__ void __launch_bounds__(kThreads, 2) rank_append_kernel(const FusedArg
     const int I0 = n_old >> 3;
 
     double *s_x = smem;                                   // [8] X tiles of the current block (operand layout)
-    double *s_ring = s_x + kWarps * 64;                   // [kWarps][kApStages][8 tiles] streaming ring (R == 1)
+    double *s_ring = s_x + kWarps * 64;                   // RING: [kWarps][kApStages][8 tiles] streaming ring (R == 1)
+    double *s_T = s_ring;                                 // !RING: [kBlk][kWarps] C tiles of a block, by new row (block appends)
     constexpr bool use_ring = RING && kApStages > 0;
-    char *aux_s = reinterpret_cast<char *>(s_ring + (use_ring ? kWarps * kApStages * 8 * 64 : 0));
+    char *aux_s = reinterpret_cast<char *>(s_ring + (use_ring ? kWarps * kApStages * 8 * 64 : kBlk * kWarps * 64));
     const Setup su = aux_pointers(lay, aux_s);
 
     for (int i = tid; i < Q; i += kThreads) {
@@ -954,6 +955,50 @@ __global__ void __launch_bounds__(kThreads, 2) rank_append_kernel(const FusedArg
                         acc[r][1] = g1v - acc[r][1];
                     }
                 }
+                if (!RING && J0 + kWarps <= g0) {
+                    // ---- block of stored rows only: the new rows do not depend on each other here, so the block's
+                    // triangle is solved per NEW row — one exchange through shared memory, then every warp runs an
+                    // in-register right-looking solve of its new row against the (stored) 8 x 8-tile diagonal block,
+                    // with no turn-taking at all
+                    // (z = L^-1 y does not change at stored columns: no y row here)
+#pragma unroll
+                    for (int r = 0; r < kBlk; ++r)
+                        if (r < R)
+                            *reinterpret_cast<double2 *>(s_T + (r * kWarps + warp) * 64 + lane * 2) = make_double2(acc[r][0], acc[r][1]);
+                    __syncthreads();
+                    for (int u = warp; u < R; u += kWarps) {
+                        const int ru = u;
+                        const int I = g0 + u;
+                        double c[kWarps][2];
+#pragma unroll
+                        for (int cc = 0; cc < kWarps; ++cc) {
+                            const double2 v = *reinterpret_cast<const double2 *>(s_T + (ru * kWarps + cc) * 64 + lane * 2);
+                            c[cc][0] = v.x; c[cc][1] = v.y;
+                        }
+#pragma unroll
+                        for (int cc = 0; cc < kWarps; ++cc) {
+                            const int Jc = J0 + cc;
+                            const double2 ib = ldg128(Wb + (size_t)Jc * 64 + lane * 2);
+                            const double2 fr = acc_to_frag(c[cc][0], c[cc][1], lane);
+                            double x0 = 0.0, x1 = 0.0;
+                            dmma(x0, x1, fr.x, ib.x);
+                            dmma(x0, x1, fr.y, ib.y);
+                            store_op(Lb + ((size_t)tri(I) + Jc) * 64, x0, x1, lane);
+                            if (cc + 1 < kWarps) {
+                                const double2 xf = acc_to_frag(x0, x1, lane);
+#pragma unroll
+                                for (int c2 = cc + 1; c2 < kWarps; ++c2) {
+                                    const double2 bf = ldg128(Lb + ((size_t)tri(J0 + c2) + Jc) * 64 + lane * 2);
+                                    dmma(c[c2][0], c[c2][1], -xf.x, bf.x);
+                                    dmma(c[c2][0], c[c2][1], -xf.y, bf.y);
+                                }
+                            }
+                        }
+                    }
+                    __threadfence_block();
+                    __syncthreads();
+                    continue;
+                }
                 // ---- the 8 x 8-tile triangle of this block: row J0+j needs the tiles finished by rows < J0+j; every row
                 // still open takes the tiles of step j-1 as soon as they exist, so a turn is one term and the solves
                 for (int j = 0; j < kWarps; ++j) {
@@ -1051,7 +1096,7 @@ LargePlan plan_large(int q, int q_cap, int G, int ntheta_cap, int ntab_cap, int 
     pl.L_stride = ((size_t)pl.ntp_cap * (pl.ntp_cap + 1) / 2 + pl.ntp_cap) * 64;
     const int Q = pl.ntp * 8;
     pl.ring = append && ring && kApStages > 0;
-    size_t base = append ? (size_t)(kWarps * 64 + (pl.ring ? kWarps * kApStages * 8 * 64 : 0)) * sizeof(double)
+    size_t base = append ? (size_t)(kWarps * 64 + (pl.ring ? kWarps * kApStages * 8 * 64 : kBlk * kWarps * 64)) * sizeof(double)
                          : (size_t)(3 * kCBT + kCB) * 64 * sizeof(double);
     size_t sz[5];
     large_aux_sizes(Q, G, ntheta_cap, ntab_cap, ncp_cap, sz);
