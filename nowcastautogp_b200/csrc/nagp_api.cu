@@ -20,6 +20,8 @@ using namespace nagp;
 
 // One NVTX range per C-ABI entry point (SURVEY §5 tracing row): header-only NVTX v3, a no-op unless a profiler is attached.
 namespace {
+
+constexpr int kAppendByRowsFrom = 4;   // new tile rows from which nagp_factor_append uses the factorisation kernel
 struct NvtxRange {
     explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
     ~NvtxRange() { nvtxRangePop(); }
@@ -1007,13 +1009,24 @@ int32_t nagp_factor_append(nagp_ctx *ctx, nagp_factor *f, int64_t k_new, const d
     NAGP_TRY(stage_out(ctx, info, (size_t)f->P, &a.info));
     double *d_dl = nullptr;
     NAGP_TRY(stage_out(ctx, dlogml, (size_t)f->P, &d_dl));
-    const bool one_tile_row = (n_new + 7) / 8 - n_old / 8 <= 1;
-    LargePlan pl = plan_large(n_new, (int)f->cap, a.G, f->nth_cap, a.ntab_cap, a.ncp_cap, ctx->smem_per_sm, true, one_tile_row);
+    const int new_tile_rows = (n_new + 7) / 8 - n_old / 8;
+    const bool one_tile_row = new_tile_rows <= 1;
+    // Appends of many rows at once (the steps of a fit_smc schedule) go through the factorisation kernel restricted to the
+    // new tile rows: it reads the stored factor once however many rows arrive and sums two rows per warp against each
+    // panel tile, where the row-streaming kernel takes one pass over the factor per eight new tile rows.
+    const bool by_rows = new_tile_rows >= kAppendByRowsFrom && !getenv("NAGP_APPEND_STREAM");
+    LargePlan pl = plan_large(n_new, (int)f->cap, a.G, f->nth_cap, a.ntab_cap, a.ncp_cap, ctx->smem_per_sm, !by_rows, one_tile_row);
     if (pl.L_stride != f->L_stride) return fail(ctx, NAGP_E_ARG, "nagp_factor_append: internal layout mismatch");
-    const int grid = large_grid(pl, f->P, ctx->num_sms, true);
+    const int grid = large_grid(pl, f->P, ctx->num_sms, !by_rows);
     char *scr = nullptr;
     if (pl.scratch_stride) NAGP_TRY(scratch(ctx, (size_t)grid * pl.scratch_stride, &scr));
-    NAGP_CUDA(ctx, launch_rank_append(a, pl, scr, f->Lbig, f->Wbig, n_old, f->logml_n, d_dl, grid, st));
+    if (by_rows) {
+        unsigned long long *counter = nullptr;
+        NAGP_TRY(scratch(ctx, 1, &counter));
+        NAGP_CUDA(ctx, launch_chol_large(a, pl, scr, f->Lbig, 1, f->Wbig, counter, grid, st, n_old, d_dl, f->logml_n));
+    } else {
+        NAGP_CUDA(ctx, launch_rank_append(a, pl, scr, f->Lbig, f->Wbig, n_old, f->logml_n, d_dl, grid, st));
+    }
     ctx->launches += 1;
     f->n = n_new;
     if (logml) NAGP_CUDA(ctx, cudaMemcpyAsync(logml, f->logml_n, f->P * sizeof(double), cudaMemcpyDefault, st));

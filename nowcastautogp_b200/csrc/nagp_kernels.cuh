@@ -104,8 +104,11 @@ LargePlan plan_large(int q, int q_cap, int G, int ntheta_cap, int ntab_cap, int 
 int large_grid(const LargePlan &pl, int64_t B, int num_sms, bool append);
 // keep = 1: instance b's factor goes to slot b of L (and its inverse diagonal tiles to W); 0: L is a
 // per-CTA workspace of `grid` slots.
+// dlogml != nullptr: block-append mode on kept factors (keep = 1): the tile rows from n_old / 8 on are (re)computed against
+// the stored rows above them, the increment of logML over the points n_old .. a.n-1 goes to dlogml and is added to logml_acc.
 cudaError_t launch_chol_large(const FusedArgs &a, const LargePlan &pl, char *scratch, double *L, int keep, double *W,
-                              unsigned long long *work_counter, int grid, cudaStream_t stream);
+                              unsigned long long *work_counter, int grid, cudaStream_t stream, int n_old = 0,
+                              double *dlogml = nullptr, double *logml_acc = nullptr);
 // Extend the stored factors (slots 0..B-1) from n_old to a.n points in place; a.t/a.g/a.y1 cover all a.n points.
 cudaError_t launch_rank_append(const FusedArgs &a, const LargePlan &pl, char *scratch, double *L, double *W,
                                int n_old, double *logml, double *dlogml, int grid, cudaStream_t stream);

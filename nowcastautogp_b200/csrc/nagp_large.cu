@@ -122,6 +122,11 @@ struct LargeLayout {
     double *W;           // [slot][ntp_cap] inverse diagonal tiles (operand layout), nullable
     size_t W_stride;
     unsigned long long *work_counter;
+    // block-append mode of chol_large_kernel: tile rows >= i0 are (re)computed against the stored rows above them, the
+    // diagonal blocks above are loaded instead of factored; the increment of logML over the points n_old .. n-1 goes to
+    // dlogml and is added to logml_acc
+    int i0, n_old;
+    double *dlogml, *logml_acc;
 };
 
 struct Setup {
@@ -358,11 +363,26 @@ __global__ void __launch_bounds__(kThreads, 2) chol_large_kernel(const FusedArgs
             // items: the kCB rows of the diagonal block, the rows below in groups of kRows (a warp sums kRows rows against
             // the same panel tiles: one operand load per kRows DMMA pairs), the y row
             const int ngroups = (ntp - c0 - kCB) / kRows;
-            const int nitems = kCB + ngroups + 1;
+            // append mode: a block column above the first new tile row has its diagonal block in the store (loaded, not
+            // factored), no z tiles to compute, and only the row groups that reach the new rows to sum
+            const bool old_block = c0 + kCB <= lay.i0;
+            const int gfirst = old_block ? (lay.i0 - c0 - kCB) / kRows : 0;
+            const int nitems = kCB + ngroups + (old_block ? 0 : 1);
             // The rows of the diagonal block come first and on all eight warps (each row's sum split in two): everything
             // else ends up waiting for them and for the factorisation that follows, and warps that stream rows below at the
             // same time take three quarters of the FP64 tensor pipe away from them (trace: 52 terms at 780 cycles each).
-            bool diag_phase = true;
+            bool diag_phase = !old_block;
+            if (old_block) {
+                for (int i = tid; i < kCBT * 64; i += kThreads) {
+                    const int tl = i >> 6, e = i & 63;
+                    int ra = 0;
+                    while (tri(ra + 1) <= tl) ++ra;                 // tile tl of the packed block is (ra, tl - tri(ra))
+                    s_L[i] = Lb[((size_t)tri(c0 + ra) + c0 + (tl - tri(ra))) * 64 + e];
+                }
+                for (int i = tid; i < kCB * 64; i += kThreads) s_W[i] = Wb[(size_t)c0 * 64 + i];
+                if (tid == 0) { s_queue = gfirst; s_flag = Jb + 1; }
+                __syncthreads();
+            }
             for (;;) {
                 int item = kCB - 1 - (warp % kCB), Plo = 0, Phi = c0;
                 const int half = diag_phase ? warp / kCB : 0;
@@ -376,7 +396,7 @@ __global__ void __launch_bounds__(kThreads, 2) chol_large_kernel(const FusedArgs
                 }
                 const bool diag = item < kCB;
                 const int arow = kCB - 1 - item;                       // longest diagonal rows first
-                const bool is_y = (item == nitems - 1);
+                const bool is_y = !old_block && (item == nitems - 1);
                 const int I = diag ? c0 + arow : (is_y ? yrow : c0 + kCB + (item - kCB) * kRows);
                 const int NC = diag ? arow + 1 : kCB;
                 const int NR = (diag || is_y) ? 1 : kRows;              // rows I .. I + NR - 1
@@ -533,7 +553,7 @@ __global__ void __launch_bounds__(kThreads, 2) chol_large_kernel(const FusedArgs
                             double x0 = 0.0, x1 = 0.0;
                             dmma(x0, x1, fr.x, ib.x);
                             dmma(x0, x1, fr.y, ib.y);
-                            store_op(Lb + ((size_t)tri(I + r) + c0 + aa) * 64, x0, x1, lane);
+                            if (I + r >= lay.i0) store_op(Lb + ((size_t)tri(I + r) + c0 + aa) * 64, x0, x1, lane);   // (append mode: a stored row that shares a group with a new one stays as it is)
                             if (aa + 1 < kCB) {
                                 const double2 xf = acc_to_frag(x0, x1, lane);
 #pragma unroll
@@ -562,6 +582,7 @@ __global__ void __launch_bounds__(kThreads, 2) chol_large_kernel(const FusedArgs
         if (s_info) {
             if (tid == 0) {
                 a.info[b] = s_info;
+                if (lay.dlogml) { lay.dlogml[b] = nan(""); if (lay.logml_acc) lay.logml_acc[b] = nan(""); }
                 if (a.logml_n) a.logml_n[b] = nan("");
                 if (a.logml_m) a.logml_m[b] = nan("");
                 if (a.logw) a.logw[b] = nan("");
@@ -591,6 +612,29 @@ __global__ void __launch_bounds__(kThreads, 2) chol_large_kernel(const FusedArgs
         qd_n = warp_sum(qd_n); qd_m = warp_sum(qd_m); ld_n = warp_sum(ld_n); ld_m = warp_sum(ld_m);
         if (lane == 0) { s_red[0][warp] = qd_n; s_red[1][warp] = qd_m; s_red[2][warp] = ld_n; s_red[3][warp] = ld_m; }
         __syncthreads();
+        if (lay.dlogml) {
+            // block-append mode: the increment over the new points only
+            __syncthreads();
+            double ld = 0.0, qd = 0.0;
+            for (int r = lay.n_old + tid; r < n; r += kThreads) {
+                ld += log(Lel(r, r));
+                const double zz = zel(r);
+                qd = fma(zz, zz, qd);
+            }
+            ld = warp_sum(ld); qd = warp_sum(qd);
+            if (lane == 0) { s_red[0][warp] = ld; s_red[1][warp] = qd; }
+            __syncthreads();
+            if (tid == 0) {
+                double l0 = 0, q0 = 0;
+                for (int w = 0; w < kWarps; ++w) { l0 += s_red[0][w]; q0 += s_red[1][w]; }
+                const double log2pi = 1.8378770664093454835606594728112;
+                const double dl = -0.5 * ((double)(n - lay.n_old) * log2pi + 2.0 * l0 + q0);
+                lay.dlogml[b] = dl;
+                if (lay.logml_acc) lay.logml_acc[b] += dl;
+                a.info[b] = 0;
+            }
+            continue;
+        }
         if (tid == 0) {
             double r2 = 0, r3 = 0, l0 = 0, l1 = 0;
             for (int w = 0; w < kWarps; ++w) { r2 += s_red[0][w]; r3 += s_red[1][w]; l0 += s_red[2][w]; l1 += s_red[3][w]; }
@@ -1143,11 +1187,13 @@ int large_grid(const LargePlan &pl, int64_t B, int num_sms, bool append)
 }
 
 cudaError_t launch_chol_large(const FusedArgs &a, const LargePlan &pl, char *scratch, double *L, int keep, double *W,
-                              unsigned long long *work_counter, int grid, cudaStream_t stream)
+                              unsigned long long *work_counter, int grid, cudaStream_t stream, int n_old, double *dlogml,
+                              double *logml_acc)
 {
     cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
     LargeLayout lay = make_layout(pl, scratch, L, keep, W, work_counter);
+    lay.i0 = dlogml ? n_old >> 3 : 0; lay.n_old = n_old; lay.dlogml = dlogml; lay.logml_acc = logml_acc;
     auto kern = pl.nt >= kRowsLargeFrom ? chol_large_kernel<2> : chol_large_kernel<1>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_bytes);
     if (e != cudaSuccess) return e;

@@ -74,9 +74,20 @@ def test_large_fast_path_factor_append_predict(engine, oracle):
     assert rel(x, xo) < 1e-8
 
 
+@pytest.fixture(params=[False, True], ids=["by-rows", "streamed"])
+def append_path(request, monkeypatch):
+    """Appends of four or more tile rows go through the factorisation kernel restricted to the new rows; with
+    NAGP_APPEND_STREAM set (read per call) they take the row-streaming kernel like the small ones."""
+    if request.param:
+        monkeypatch.setenv("NAGP_APPEND_STREAM", "1")
+    else:
+        monkeypatch.delenv("NAGP_APPEND_STREAM", raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize("use_grid", [False, True])
-@pytest.mark.parametrize("n0,adds", [(260, [1, 7, 8, 70]), (64, [3, 200]), (250, [1, 1, 1]), (10, [300])])
-def test_rank_append_matches_full_refactor(engine, oracle, n0, adds, use_grid):
+@pytest.mark.parametrize("n0,adds", [(260, [1, 7, 8, 70]), (64, [3, 200]), (250, [1, 1, 1]), (10, [300]), (100, [29, 33, 64])])
+def test_rank_append_matches_full_refactor(engine, oracle, n0, adds, use_grid, append_path):
     """SMC data annealing: logML after each in-place append == logML of a from-scratch factorisation of
     the grown series (oracle), and dlogml is the increment."""
     P = 4
