@@ -21,7 +21,9 @@ using namespace nagp;
 // One NVTX range per C-ABI entry point (SURVEY §5 tracing row): header-only NVTX v3, a no-op unless a profiler is attached.
 namespace {
 
-constexpr int kAppendByRowsFrom = 4;   // new tile rows from which nagp_factor_append uses the factorisation kernel
+// new tile rows from which nagp_factor_append uses the factorisation kernel. Measured at 256 x n = 2048, by rows / streamed:
+// one tile row 5.2 / 1.1 ms, two 5.1 / 5.6, three 5.9 / 7.4, four 5.7 / 9.0, eight 6.3 / 17 (1024 x n = 512: two 1.4 / 1.7, four 1.7 / 2.6)
+constexpr int kAppendByRowsFrom = 2;
 struct NvtxRange {
     explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
     ~NvtxRange() { nvtxRangePop(); }
@@ -1014,7 +1016,8 @@ int32_t nagp_factor_append(nagp_ctx *ctx, nagp_factor *f, int64_t k_new, const d
     // Appends of many rows at once (the steps of a fit_smc schedule) go through the factorisation kernel restricted to the
     // new tile rows: it reads the stored factor once however many rows arrive and sums two rows per warp against each
     // panel tile, where the row-streaming kernel takes one pass over the factor per eight new tile rows.
-    const bool by_rows = new_tile_rows >= kAppendByRowsFrom && !getenv("NAGP_APPEND_STREAM");
+    const char *from_env = getenv("NAGP_APPEND_BY_ROWS_FROM");        // measurement hook
+    const bool by_rows = new_tile_rows >= (from_env ? atoi(from_env) : kAppendByRowsFrom) && !getenv("NAGP_APPEND_STREAM");
     LargePlan pl = plan_large(n_new, (int)f->cap, a.G, f->nth_cap, a.ntab_cap, a.ncp_cap, ctx->smem_per_sm, !by_rows, one_tile_row);
     if (pl.L_stride != f->L_stride) return fail(ctx, NAGP_E_ARG, "nagp_factor_append: internal layout mismatch");
     const int grid = large_grid(pl, f->P, ctx->num_sms, !by_rows);

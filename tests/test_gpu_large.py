@@ -76,7 +76,7 @@ def test_large_fast_path_factor_append_predict(engine, oracle):
 
 @pytest.fixture(params=[False, True], ids=["by-rows", "streamed"])
 def append_path(request, monkeypatch):
-    """Appends of four or more tile rows go through the factorisation kernel restricted to the new rows; with
+    """Appends of two or more tile rows go through the factorisation kernel restricted to the new rows; with
     NAGP_APPEND_STREAM set (read per call) they take the row-streaming kernel like the small ones."""
     if request.param:
         monkeypatch.setenv("NAGP_APPEND_STREAM", "1")
