@@ -251,7 +251,7 @@ def main():
     ap.add_argument("--skip-sanity", action="store_true", help="timing experiments with deliberately wrong kernels")
     ap.add_argument("--only-value", action="store_true", help="time only the device-resident step")
     ap.add_argument("--no-micro", action="store_true", help="skip the configs[2]/configs[4] micro-benchmarks")
-    ap.add_argument("--variant", type=int, default=0, help="factorisation kernel: 0 auto, 2 tile kernel, 3 slot kernel")
+    ap.add_argument("--variant", type=int, default=0, help="factorisation kernel: 0 auto, 2 tile kernel, 3 slot kernel, 4 large-path kernel")
     ap.add_argument("--c4", action="store_true", help="run the BASELINE configs[3] block at any N (default: only at N = 8)")
     ap.add_argument("--no-c4", action="store_true")
     args = ap.parse_args()

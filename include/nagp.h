@@ -59,7 +59,8 @@ int32_t nagp_set_jitter(nagp_ctx *ctx, double jitter);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t nagp_launch_count(const nagp_ctx *ctx);
 /* Pick the factorisation kernel for q <= 232: 0 = auto, 1 = shared-memory column kernel, 2 = tile kernel,
- * 3 = slot kernel (three matrices per SM) wherever it applies (lag-grid times, q <= 168), else as 2. */
+ * 3 = slot kernel (three matrices per SM) wherever it applies (lag-grid times, q <= 168), else as 2,
+ * 4 = the factor-in-HBM kernel of the large path at every size (cross-check; 11.9 ms against 5.1 ms at the vignette size). */
 int32_t nagp_set_variant(nagp_ctx *ctx, int32_t variant);
 /* Which factorisation kernel the last fused launch of this context used: 1 column, 2 tile, 3 slot, 4 large; 0 none yet. */
 int32_t nagp_last_kernel(const nagp_ctx *ctx);

@@ -306,7 +306,7 @@ int32_t run_fused(nagp_ctx *ctx, FusedArgs a, const int64_t *theta_off_host)
             }
         }
     }
-    if (ctx->variant != 1 && q <= fused_v2_max_q()) {
+    if (ctx->variant != 1 && q <= fused_v2_max_q() && ctx->variant != 4) {
         int64_t nth = 1;
         for (int64_t p = 0; p < a.P; ++p) nth = std::max(nth, theta_off_host[p + 1] - theta_off_host[p]);
         V2Plan pl = plan_fused_v2(q, a.G, (int)std::min<int64_t>(nth, MAX_THETA), a.ntab_cap, a.ncp_cap,
@@ -429,7 +429,7 @@ int32_t nagp_last_kernel(const nagp_ctx *ctx) { return ctx ? ctx->last_kernel : 
 
 int32_t nagp_set_variant(nagp_ctx *ctx, int32_t variant)
 {
-    if (!ctx || variant < 0 || variant > 3) return NAGP_E_ARG;
+    if (!ctx || variant < 0 || variant > 4) return NAGP_E_ARG;
     ctx->variant = variant;
     return NAGP_OK;
 }

@@ -14,10 +14,11 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-9
 
 
-@pytest.fixture(params=[1, 2, 3], ids=["column-kernel", "tile-kernel", "slot-kernel"])
+@pytest.fixture(params=[1, 2, 3, 4], ids=["column-kernel", "tile-kernel", "slot-kernel", "large-kernel"])
 def veng(engine, request):
     """The engine pinned to one factorisation kernel (1 = shared-memory column, 2 = DMMA tile, 3 = slot kernel
-    wherever it applies: lag-grid times and 17 <= q <= 168; the tile kernel elsewhere)."""
+    wherever it applies: lag-grid times and 17 <= q <= 168; the tile kernel elsewhere, 4 = the factor-in-HBM kernel of the
+    large path at every size)."""
     engine.set_variant(request.param)
     yield engine
     engine.set_variant(0)
