@@ -1,5 +1,7 @@
+"""nagp_logml_batch across the size where the tile kernel hands over to the large-path kernel (q = 232 / 233):
+`python tools/boundary_probe.py` (4000 instances per size, host buffers)."""
 import os, sys, time
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from nowcastautogp_b200 import synthetic as syn
 from nowcastautogp_b200.engine import Engine
