@@ -225,6 +225,7 @@ def device_noise_spec(config: GPConfig):
 
 
 HMC_DEFAULT = {"n_leapfrog": 10, "eps": 0.02}     # Gen.hmc's L = 10 [R]; step sized for N(0,1)-scaled z
+GRAD_KERNEL_MAX_N = 232                            # nagp_logml_grad / nagp_hmc keep a chain's factor in shared memory
 
 
 @dataclass
@@ -569,8 +570,11 @@ class GPModel:
         noise = (np.full(flat.P, float(cfg.noise)) if cfg.noise is not None
                  else transform_slots(flat.noise_codes, NZ, cfg))
         ens = kn.FlatEnsemble(flat.prog, flat.prog_off, theta, flat.off, noise)
-        lm, gth, gnz, info = self._engine().logml_grad(ens, t, y, g=g, step=step)
-        lm, gth, gnz, info = lm[0], gth[0], gnz[0], info[0]
+        if len(y) > GRAD_KERNEL_MAX_N or getattr(self, "_force_fd_gradient", False):
+            lm, gth, gnz, info = self._logml_grad_by_differences(ens, flat, t, g, step, y)
+        else:
+            lm, gth, gnz, info = self._engine().logml_grad(ens, t, y, g=g, step=step)
+            lm, gth, gnz, info = lm[0], gth[0], gnz[0], info[0]
         lp = np.where(info == 0, lm, -np.inf)
         dZ = np.where(np.isfinite(gth), gth, 0.0) * dtheta_dz_slots(flat.codes, Z, theta, cfg) - Z
         dZ = np.where(np.isfinite(dZ), dZ, 0.0)
@@ -582,17 +586,58 @@ class GPModel:
             lp = lp - 0.5 * NZ ** 2
         return lp, dZ, dNZ
 
+    def _logml_grad_by_differences(self, ens, flat: "_FlatChains", t, g, step, y):
+        """logML and its gradient in the constrained parameters for series beyond the gradient kernels' size
+        (n > 232: they keep a chain's factor in shared memory): central differences of the DEVICE log marginal likelihood,
+        every perturbation of every particle in one batched call through the large-path kernel (scenario s of the batch
+        perturbs slot (s - 1) // 2 of each particle by ±h; the particles are independent, so one scenario moves them
+        all). 2·(slots per particle) + 3 factorisations per particle instead of one factorisation and one inverse, but
+        the leapfrog integrator only needs a deterministic force field to stay reversible and volume-preserving, and the
+        accept step uses the exact logML: the chain targets the same posterior as with the analytic gradient."""
+        P, off = flat.P, np.asarray(flat.off)
+        ns = np.diff(off)
+        D = int(ns.max()) if P else 0
+        learn_noise = self.config.noise is None
+        K = 1 + 2 * D + (2 if learn_noise else 0)
+        theta, noise = np.asarray(ens.theta, np.float64), np.asarray(ens.noise, np.float64)
+        TH, NZ = np.tile(theta, (K, 1)), np.tile(noise, (K, 1))
+        h_th = 1e-6 * np.maximum(1.0, np.abs(theta))
+        h_nz = 1e-6 * np.maximum(1.0, np.abs(noise))
+        for j in range(D):
+            sel = off[:-1][ns > j] + j
+            TH[1 + 2 * j, sel] += h_th[sel]
+            TH[2 + 2 * j, sel] -= h_th[sel]
+        if learn_noise:
+            NZ[1 + 2 * D] += h_nz
+            NZ[2 + 2 * D] -= h_nz
+        n = len(y)
+        lm = np.empty((K, P))
+        r = self._engine().forecast_instances(ens, n, 0, 0, t, y, np.empty((K, 0)), np.zeros(P), 1.0, 0.0, g=g, step=step,
+                                              theta=TH, noise=NZ, K=K, logml_m=lm, want_moments=False)
+        info = np.asarray(r["info"])
+        lm = np.where(info == 0, lm, np.nan)
+        gth = np.zeros_like(theta)
+        for j in range(D):
+            sel = off[:-1][ns > j] + j
+            pj = np.nonzero(ns > j)[0]
+            gth[sel] = (lm[1 + 2 * j, pj] - lm[2 + 2 * j, pj]) / ((TH[1 + 2 * j, sel] - TH[2 + 2 * j, sel]))
+        gnz = np.zeros(P)
+        if learn_noise:
+            gnz = (lm[1 + 2 * D] - lm[2 + 2 * D]) / (NZ[1 + 2 * D] - NZ[2 + 2 * D])
+        return lm[0], gth, gnz, info[0]
+
     def mcmc_parameters(self, n_hmc: int, hmc_config: Optional[dict] = None) -> float:
         """`AutoGP.mcmc_parameters!(model, n_hmc)` (`src/forecasting.jl:148,65`): `n_hmc` Hamiltonian Monte
         Carlo steps on the unconstrained hyperparameters of every particle (N(0,1) prior on z [R]), all
         particles advanced together in ONE device call (`nagp_hmc`): the leapfrog integrator, the z -> theta
         maps and the accept/reject step run on the device, the host only supplies the momenta and the uniforms
         (drawn in the order the host integrator `_mcmc_parameters_host` draws them, so both walk the same
-        chain). Beyond the gradient kernel's size limit the move degrades to random-walk Metropolis on the same
-        target. Returns the acceptance rate."""
+        chain). Beyond the gradient kernels' size limit (n > 232) the integrator runs on the host over gradients taken as
+        central differences of the device logML (`_logml_grad_by_differences`): same target, same move. Returns the
+        acceptance rate."""
         from .engine import NagpError
         hc = dict(HMC_DEFAULT, **(hmc_config or getattr(self, "_hmc_config", None) or {}))
-        if not hc.get("device", True):
+        if not hc.get("device", True) or self.n_obs > GRAD_KERNEL_MAX_N:
             return self._mcmc_parameters_host(n_hmc, hmc_config)
         idx = self._obs_idx()
         P = len(self.particles)

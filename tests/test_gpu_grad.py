@@ -259,3 +259,36 @@ def test_per_scenario_device_hmc_in_forecast_with_nowcasts(engine):
             api.HMC_DEFAULT.pop("device", None)
     assert xs[0].shape == (4, 18) and np.isfinite(xs[0]).all()
     np.testing.assert_allclose(xs[0], xs[1], rtol=1e-6, atol=1e-6)
+
+
+def test_gradient_by_differences_for_long_series(engine):
+    """Beyond the gradient kernels' size the host takes central differences of the device logML (one batched call through
+    the large-path kernel). At a size both routes take, the two gradients agree; at n = 300 the HMC move runs on it."""
+    from nowcastautogp_b200.gpmodel import GPModel
+    n = 120
+    w = syn.make_workload(n, 0, 0, 1, 6, seed=31)
+    dates = np.datetime64("2020-01-05") + 7 * np.arange(n)
+    m = GPModel(dates, w.y1, n_particles=6, rng=np.random.default_rng(5), engine=engine)
+    m.fit_smc(schedule=[n], n_mcmc=0, n_hmc=0, shuffle=False)
+    idx = m._obs_idx()
+    lp0, dz0, dn0 = m._logpost_grad(m.particles, idx)
+    m._force_fd_gradient = True
+    lp1, dz1, dn1 = m._logpost_grad(m.particles, idx)
+    m._force_fd_gradient = False
+    ok = np.isfinite(lp0)
+    assert ok.any() and np.allclose(lp0[ok], lp1[ok], rtol=1e-10)
+    for a_, b_, good in zip(dz0, dz1, ok):
+        if good:
+            assert np.abs(a_ - b_).max() < 1e-4 * max(1.0, np.abs(a_).max())
+    assert np.abs(dn0[ok] - dn1[ok]).max() < 1e-4 * max(1.0, np.abs(dn0[ok]).max())
+    # a long series: the move runs, keeps every particle finite and accepts something
+    n = 300
+    t = np.arange(n)
+    y = np.sin(2 * np.pi * t / 52) + 0.01 * t + 0.1 * np.random.default_rng(2).standard_normal(n)
+    dates = np.datetime64("2016-01-03") + 7 * np.arange(n)
+    m = GPModel(dates, y, n_particles=4, rng=np.random.default_rng(6), engine=engine)
+    m.fit_smc(schedule=[n], n_mcmc=0, n_hmc=0, shuffle=False)
+    before = np.array(m._logml, copy=True)
+    rate = m.mcmc_parameters(3)
+    assert 0.0 <= rate <= 1.0 and np.isfinite(np.asarray(m._logml)[np.isfinite(before)]).all()
+    assert rate > 0.0
