@@ -95,6 +95,19 @@ def make_and_fit_models(datas: Sequence[TData], *, n_particles: int = 1, smc_dat
     same_dates = all(len(d.ds) == len(datas[0].ds) and np.array_equal(np.asarray(d.ds), np.asarray(datas[0].ds))
                      for d in datas)
     order = rngs[S].permutation(len(datas[0].y)) if (share_order and same_dates and kwargs.get("shuffle", True)) else None
+    if max(len(d.y) for d in datas) > 232:
+        # Long series (the large path, n > 232): one series' particles already fill the device, and a fit on its own engine
+        # keeps an appendable factor store between un-rejuvenated schedule steps (block appends are ~4x cheaper than
+        # re-factoring) — which a lockstep fit, whose every step must stay a mergeable request, cannot.
+        out = []
+        for s in range(S):
+            kw = dict(kwargs)
+            if order is not None:
+                kw["obs_order"] = order
+            out.append(make_and_fit_model(datas[s], n_particles=n_particles, smc_data_proportion=smc_data_proportion,
+                                          flat_threshold=flat_threshold, config=config, rng=rngs[s], engine=eng, **kw))
+        make_and_fit_models.last_stats = {"requests": 0, "device_calls": 0, "one_by_one": True}
+        return out
     hub = CoalescingEngine(eng, S)
     models: List[Optional[GPModel]] = [None] * S
     errors: List[Optional[BaseException]] = [None] * S
