@@ -145,6 +145,31 @@ def test_lockstep_fit_equals_one_at_a_time(engine):
     assert x.shape == (4, 10) and np.isfinite(x).all()
 
 
+@pytest.mark.gpu
+def test_long_series_are_fitted_one_at_a_time_with_the_appendable_store(engine):
+    """n > 232: `make_and_fit_models` runs the series one by one on the plain engine, so the un-rejuvenated schedule
+    steps extend an appendable factor store instead of re-factoring; the result is what `make_and_fit_model` gives with
+    the same generators and observation order."""
+    import nowcastautogp_b200 as ng
+    from nowcastautogp_b200.api import make_and_fit_models
+    rng = np.random.default_rng(3)
+    n, S = 260, 2
+    dates = np.datetime64("2019-01-06") + 7 * np.arange(n)
+    datas = [ng.TData(dates, 30 + 4 * np.sin(np.arange(n) / (5.0 + s)) + 0.02 * np.arange(n) + 0.4 * rng.standard_normal(n),
+                      transformation=lambda v: v) for s in range(S)]
+    kw = dict(n_particles=3, smc_data_proportion=0.25, n_mcmc=0, n_hmc=0)
+    models = make_and_fit_models(datas, rng=np.random.default_rng(11), engine=engine, **kw)
+    assert make_and_fit_models.last_stats.get("one_by_one")
+    assert all(m.append_steps > 0 for m in models)                      # the store served schedule steps
+    seq = np.random.SeedSequence(np.random.default_rng(11).integers(2 ** 63))
+    rngs = [np.random.default_rng(ss) for ss in seq.spawn(S + 1)]
+    order = rngs[S].permutation(n)
+    for s in range(S):
+        solo = ng.make_and_fit_model(datas[s], rng=rngs[s], engine=engine, obs_order=order, **kw)
+        assert [p.prog for p in solo.particles] == [p.prog for p in models[s].particles]
+        assert np.array_equal(solo.log_weights, models[s].log_weights)
+
+
 def test_hmc_requests_merge():
     fake = FakeEngine()
     S = 4
